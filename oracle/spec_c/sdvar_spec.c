@@ -1,0 +1,223 @@
+/*
+ * sdvar_spec.c -- bit-exact arithmetic SPEC of the two index-producing kernels
+ * (TEST INFRASTRUCTURE ONLY; never linked into the product library).
+ *
+ *   K3  sdvar_spec_sample : CFG mix -> top-k -> top-p -> softmax -> exponential-race sample
+ *        follows reference models/var.py:199-202 and models/helpers.py:6-19
+ *        (torch.multinomial(n=1) == argmax(p / Exp(1)), SURVEY.md A5 / pin P4)
+ *   K4  sdvar_spec_verify : target-vs-draft softmax, accept u*q[d] < p[d], residual resample,
+ *        first-reject scan per (image, stage)   -- north_star item 3, SURVEY.md A7.
+ *        PARITY UNPINNED: nothing in the reference computes this rule.
+ *
+ * The CUDA kernels in sdvar_b200/csrc/sampling.cu must reproduce these functions BIT FOR BIT
+ * (same exp polynomial, same reduction order, IEEE mul/sub/div without contraction).  Where the
+ * reference leaves the floating-point evaluation order to ATen (softmax sum, ascending cumsum)
+ * this spec fixes one order; the deviation from ATen is a few ulp and changes a token only on
+ * near-ties (probability ~1e-7 per token) -- the golden tests pin that on recorded vectors.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC (see oracle/spec_c/Makefile).
+ *
+ * Canonical reduction order over a row of V floats (V % 4 == 0), "256-lane order":
+ *   lane t in [0,256) owns float4 chunks f = i*256 + t (i = 0,1,..), i.e. elements 4f..4f+3;
+ *   lane partial = sequential sum over i then over the 4 components, starting from +0;
+ *   the 32 lanes of a warp are combined with an xor butterfly (offsets 16,8,4,2,1);
+ *   the 8 warp results are added left to right.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define LANES 256
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* order-preserving map float -> uint32 (x<y  <=>  key(x)<key(y) for non-NaN, -0 < +0) */
+static inline uint32_t fkey(float f) {
+  uint32_t b = f2u(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+/* exp(x) for x <= ~88: Cody-Waite reduction, degree-7 Taylor/Horner in fmaf, exact 2^n scaling */
+float sdvar_spec_expf(float x) {
+  if (x < -104.0f) return 0.0f; /* also -inf */
+  const float t = x * 1.44269504088896340736f;
+  const float n = rintf(t);
+  float r = fmaf(n, -0.693145751953125f, x);
+  r = fmaf(n, -1.42860682030941723212e-6f, r);
+  float p = 1.0f / 5040.0f;
+  p = fmaf(p, r, 1.0f / 720.0f);
+  p = fmaf(p, r, 1.0f / 120.0f);
+  p = fmaf(p, r, 1.0f / 24.0f);
+  p = fmaf(p, r, 1.0f / 6.0f);
+  p = fmaf(p, r, 0.5f);
+  p = fmaf(p, r, 1.0f);
+  p = fmaf(p, r, 1.0f);
+  const int ni = (int)n;
+  if (ni >= -126) return p * u2f((uint32_t)(ni + 127) << 23);
+  return (p * u2f((uint32_t)(ni + 100 + 127) << 23)) * u2f((uint32_t)(-100 + 127) << 23);
+}
+
+/* canonical sum of term[v] * (pred ? 1 : 0); `keys`==NULL means no predicate */
+static float canon_sum(const float* term, int V, const uint32_t* keys, uint32_t kmax_incl) {
+  float lane[LANES];
+  const int nvec = V / 4;
+  for (int t = 0; t < LANES; ++t) {
+    float acc = 0.0f;
+    for (int f = t; f < nvec; f += LANES)
+      for (int c = 0; c < 4; ++c) {
+        const int v = 4 * f + c;
+        const float a = (keys == NULL || keys[v] <= kmax_incl) ? term[v] : 0.0f;
+        acc = acc + a;
+      }
+    lane[t] = acc;
+  }
+  float total = 0.0f;
+  for (int w = 0; w < LANES / 32; ++w) {
+    float* l = lane + 32 * w;
+    for (int off = 16; off >= 1; off >>= 1) {
+      float nl[32];
+      for (int i = 0; i < 32; ++i) nl[i] = l[i] + l[i ^ off];
+      memcpy(l, nl, sizeof(nl));
+    }
+    total = (w == 0) ? l[0] : total + l[0];
+  }
+  return total;
+}
+
+static int find_seg(const int* seg_begin, int S, int pos) {
+  int j = 0;
+  while (j + 1 < S && pos >= seg_begin[j + 1]) ++j;
+  return j;
+}
+
+/* ---- K3 ------------------------------------------------------------------------------- */
+/* one row; x is scratch of V floats that receives the mixed+masked logits */
+static long long sample_row(const float* xc, const float* xu, float t1, float t2, int V, int top_k, float thr,
+                            const float* noise, float* x, float* e, uint32_t* keys, float* prob_out) {
+  for (int v = 0; v < V; ++v) x[v] = xc[v] * t1 - xu[v] * t2; /* two roundings of the products, then the difference */
+  for (int v = 0; v < V; ++v) keys[v] = fkey(x[v]);
+  if (top_k > 0 && top_k < V) {
+    /* K = key of the k-th largest = largest K with #{key >= K} >= k */
+    uint32_t K = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t tr = K | (1u << bit);
+      int cnt = 0;
+      for (int v = 0; v < V; ++v) cnt += keys[v] >= tr;
+      if (cnt >= top_k) K = tr;
+    }
+    for (int v = 0; v < V; ++v)
+      if (keys[v] < K) { x[v] = -INFINITY; keys[v] = fkey(-INFINITY); }
+  }
+  float m = -INFINITY;
+  uint32_t kmax = 0;
+  for (int v = 0; v < V; ++v) { if (x[v] > m) m = x[v]; if (keys[v] > kmax) kmax = keys[v]; }
+  for (int v = 0; v < V; ++v) e[v] = sdvar_spec_expf(x[v] - m);
+  if (thr >= 0.0f) {
+    const float Z = canon_sum(e, V, NULL, 0);
+    /* p_v = e_v / Z, mass(K) = canon_sum(p_v [key_v <= K]); K* = largest K with mass(K) <= thr */
+    static __thread float p[65536];
+    for (int v = 0; v < V; ++v) p[v] = e[v] / Z;
+    uint32_t K = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t tr = K | (1u << bit);
+      if (canon_sum(p, V, keys, tr) <= thr) K = tr;
+    }
+    for (int v = 0; v < V; ++v)
+      if (keys[v] <= K && keys[v] != kmax) { x[v] = -INFINITY; e[v] = 0.0f; }
+  }
+  if (noise == NULL) return -1;
+  const float Z2 = canon_sum(e, V, NULL, 0);
+  float best = -1.0f;
+  long long bi = 0;
+  float bp = 0.0f;
+  for (int v = 0; v < V; ++v) {
+    const float p = e[v] / Z2;
+    const float r = p / noise[v];
+    if (r > best) { best = r; bi = v; bp = p; }
+  }
+  if (prob_out) *prob_out = bp;
+  return bi;
+}
+
+/* rows are (b,pos), b<B, pos<L; cond logits at row b*L+pos, uncond at (B+b)*L+pos of logits_2BLV;
+ * seg_begin[S+1] partitions [0,L) into stages, stage j uses t1[j]=fl32(1+t), t2[j]=fl32(t);
+ * thr = fl32(1-top_p) or <0 when top_p is disabled; noise/idx_out/mixed_out/prob_out may be NULL. */
+int sdvar_spec_sample(const float* logits_2BLV, int B, int L, int V, const int* seg_begin, int S, const float* t1,
+                      const float* t2, int top_k, float thr, const float* noise, long long* idx_out,
+                      float* mixed_out, float* prob_out) {
+  if (V % 4 != 0 || V > 65536 || S < 1) return -1;
+  static __thread float x[65536], e[65536];
+  static __thread uint32_t keys[65536];
+  for (int b = 0; b < B; ++b)
+    for (int pos = 0; pos < L; ++pos) {
+      const long long row = (long long)b * L + pos;
+      const int j = find_seg(seg_begin, S, pos);
+      float pr = 0.0f;
+      const long long id = sample_row(logits_2BLV + row * V, logits_2BLV + ((long long)(B + b) * L + pos) * V, t1[j],
+                                      t2[j], V, top_k, thr, noise ? noise + row * V : NULL, x, e, keys, &pr);
+      if (idx_out && noise) idx_out[row] = id;
+      if (prob_out && noise) prob_out[row] = pr;
+      if (mixed_out) memcpy(mixed_out + row * V, x, sizeof(float) * V);
+    }
+  return 0;
+}
+
+/* ---- K4 ------------------------------------------------------------------------------- */
+int sdvar_spec_verify(const float* xt, const float* xd, const long long* draft_idx, const float* u, const float* noise,
+                      int B, int L, int V, const int* seg_begin, int S, long long* out_idx, unsigned char* accept,
+                      float* p_d_out, float* q_d_out, int* first_reject /*(B,S)*/, int* n_accept /*(B,S)*/,
+                      int* accepted_stages /*(B)*/, int* summary /*[4]: min accepted stages, #accept, #reject, 0*/) {
+  if (V % 4 != 0 || V > 65536 || S < 1) return -1;
+  static __thread float et[65536], ed[65536], r[65536];
+  int tot_acc = 0, tot_rej = 0, min_stages = S;
+  for (int b = 0; b < B; ++b) {
+    for (int j = 0; j < S; ++j) { first_reject[b * S + j] = seg_begin[j + 1] - seg_begin[j]; n_accept[b * S + j] = 0; }
+    for (int pos = 0; pos < L; ++pos) {
+      const long long row = (long long)b * L + pos;
+      const int j = find_seg(seg_begin, S, pos);
+      const float *t = xt + row * V, *d = xd + row * V;
+      float mt = -INFINITY, md = -INFINITY;
+      for (int v = 0; v < V; ++v) { if (t[v] > mt) mt = t[v]; if (d[v] > md) md = d[v]; }
+      for (int v = 0; v < V; ++v) { et[v] = sdvar_spec_expf(t[v] - mt); ed[v] = sdvar_spec_expf(d[v] - md); }
+      const float Zt = canon_sum(et, V, NULL, 0), Zd = canon_sum(ed, V, NULL, 0);
+      const long long di = draft_idx[row];
+      const float pd = et[di] / Zt, qd = ed[di] / Zd;
+      const int acc = (u[row] * qd) < pd;
+      long long o = di;
+      if (!acc) {
+        int anypos = 0;
+        for (int v = 0; v < V; ++v) {
+          const float pv = et[v] / Zt;
+          float rv = pv - ed[v] / Zd;
+          rv = rv > 0.0f ? rv : 0.0f;
+          r[v] = rv;
+          anypos |= rv > 0.0f;
+        }
+        float best = -1.0f;
+        o = 0;
+        for (int v = 0; v < V; ++v) {
+          const float num = anypos ? r[v] : et[v] / Zt;
+          const float q = num / noise[row * V + v];
+          if (q > best) { best = q; o = v; }
+        }
+      }
+      out_idx[row] = o;
+      accept[row] = (unsigned char)acc;
+      if (p_d_out) p_d_out[row] = pd;
+      if (q_d_out) q_d_out[row] = qd;
+      if (acc) { n_accept[b * S + j]++; tot_acc++; }
+      else {
+        tot_rej++;
+        const int within = pos - seg_begin[j];
+        if (within < first_reject[b * S + j]) first_reject[b * S + j] = within;
+      }
+    }
+    int a = 0;
+    while (a < S && n_accept[b * S + a] == seg_begin[a + 1] - seg_begin[a]) ++a;
+    accepted_stages[b] = a;
+    if (a < min_stages) min_stages = a;
+  }
+  summary[0] = min_stages; summary[1] = tot_acc; summary[2] = tot_rej; summary[3] = 0;
+  return 0;
+}
