@@ -1,0 +1,87 @@
+// common.cuh -- shared helpers of libsdvar_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/sdvar_b200.h"
+
+namespace sdvar {
+
+// ---- error plumbing (no exceptions cross the C ABI) -------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_arch();  // SDVAR_OK iff the current device is sm_100
+
+#define SDVAR_REQUIRE(cond, ...)                     \
+  do {                                               \
+    if (!(cond)) {                                   \
+      sdvar::set_error(__VA_ARGS__);                 \
+      return SDVAR_ERR_ARG;                          \
+    }                                                \
+  } while (0)
+
+#define SDVAR_CUDA(call)                                                                       \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      sdvar::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return SDVAR_ERR_CUDA;                                                                   \
+    }                                                                                          \
+  } while (0)
+
+#define SDVAR_LAUNCH_CHECK()                                                                   \
+  do {                                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                                      \
+    if (e__ != cudaSuccess) {                                                                  \
+      sdvar::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return SDVAR_ERR_CUDA;                                                                   \
+    }                                                                                          \
+    sdvar::count_launch();                                                                     \
+  } while (0)
+
+struct SegTable {
+  int S;
+  int begin[SDVAR_MAX_SEG + 1];
+  float t1[SDVAR_MAX_SEG];
+  float t2[SDVAR_MAX_SEG];
+};
+
+__device__ __forceinline__ int seg_of(const SegTable& s, int pos) {
+  int j = 0;
+#pragma unroll 1
+  while (j + 1 < s.S && pos >= s.begin[j + 1]) ++j;
+  return j;
+}
+
+// ---- streaming 128-bit loads / stores -----------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
+
+// order-preserving float -> uint32 (oracle/spec_c/sdvar_spec.c:fkey)
+__device__ __forceinline__ uint32_t fkey(float f) {
+  const uint32_t b = f2u(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) { return u2f((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+}  // namespace sdvar

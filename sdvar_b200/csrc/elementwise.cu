@@ -1,0 +1,100 @@
+// elementwise.cu -- LayerNorm + adaLN modulate (fp32 -> bf16 GEMM operand), SiLU, casts.
+//
+// ln_modulate replaces `ln_wo_grad(x).mul(scale.add(1)).add_(shift)` at models/basic_var.py:157-158 and
+// :173-174.  HBM-bound: one warp per row, the row is staged once in shared memory (single global read),
+// mean and centred variance are reduced with warp shuffles, the bf16 result is written with 8-byte stores.
+#include "common.cuh"
+
+namespace sdvar {
+
+constexpr int kLnWarps = 4;
+
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_modulate_kernel(const float* __restrict__ x, int M, int C, int tokens_per_img, const float* __restrict__ scale,
+                   const float* __restrict__ shift, int ld_mod, float eps, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) float rowbuf[];  // [kLnWarps][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + warp;
+  if (row >= M) return;
+  float* buf = rowbuf + (size_t)warp * C;
+  const int nvec = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * C);
+  float sum = 0.0f;
+  for (int i = lane; i < nvec; i += 32) {
+    const float4 v = ldg_stream(xr + i);
+    reinterpret_cast<float4*>(buf)[i] = v;
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float mean = sum / (float)C;
+  float var = 0.0f;
+  for (int i = lane; i < nvec; i += 32) {
+    const float4 v = reinterpret_cast<const float4*>(buf)[i];
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    var += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) var += __shfl_xor_sync(0xffffffffu, var, off);
+  const float rstd = rsqrtf(var / (float)C + eps);
+  const int img = row / tokens_per_img;
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)img * ld_mod);
+  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)img * ld_mod);
+  uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * C);
+  for (int i = lane; i < nvec; i += 32) {
+    const float4 v = reinterpret_cast<const float4*>(buf)[i];
+    const float4 s = __ldg(sc + i), h = __ldg(sh + i);
+    const float y0 = (v.x - mean) * rstd * (1.0f + s.x) + h.x;
+    const float y1 = (v.y - mean) * rstd * (1.0f + s.y) + h.y;
+    const float y2 = (v.z - mean) * rstd * (1.0f + s.z) + h.z;
+    const float y3 = (v.w - mean) * rstd * (1.0f + s.w) + h.w;
+    o[i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+  }
+}
+
+__global__ void silu_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    out[i] = __float2bfloat16_rn(v / (1.0f + __expf(-v)));
+  }
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(x[i]);
+}
+
+}  // namespace sdvar
+
+using namespace sdvar;
+
+extern "C" int sdvar_ln_modulate(const float* x, int M, int C, int tokens_per_img, const float* scale, const float* shift,
+                                 int ld_mod, float eps, sdvar_bf16* out, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(x && scale && shift && out, "NULL argument");
+  SDVAR_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && tokens_per_img > 0 && ld_mod % 4 == 0, "bad geometry M=%d C=%d", M, C);
+  SDVAR_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0 && ((uintptr_t)out & 7) == 0,
+                "alignment");
+  const size_t smem = (size_t)kLnWarps * C * sizeof(float);
+  SDVAR_REQUIRE(smem <= 48 * 1024, "C=%d too large for ln_modulate", C);
+  ln_modulate_kernel<<<(M + kLnWarps - 1) / kLnWarps, kLnWarps * 32, smem, (cudaStream_t)stream>>>(
+      x, M, C, tokens_per_img, scale, shift, ld_mod, eps, reinterpret_cast<__nv_bfloat16*>(out));
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
+
+extern "C" int sdvar_silu_bf16(const float* x, long long n, sdvar_bf16* out, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(x && out && n > 0, "bad argument");
+  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  silu_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, reinterpret_cast<__nv_bfloat16*>(out));
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
+extern "C" int sdvar_f32_to_bf16(const float* x, long long n, sdvar_bf16* out, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(x && out && n > 0, "bad argument");
+  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  f32_to_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, reinterpret_cast<__nv_bfloat16*>(out));
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}

@@ -1,0 +1,537 @@
+// sampling.cu -- K3 fused logits epilogue and K4 speculative verify (HBM-bound row kernels).
+//
+// Both kernels give one 256-thread CTA a row of V fp32 logits (V = 1024*NV): thread t owns the float4
+// chunks f = i*256 + t, i.e. 128-bit coalesced streaming loads, 4*NV values in registers.  Every float
+// operation that decides an index uses explicit round-to-nearest intrinsics (no FMA contraction) and the
+// reduction order of oracle/spec_c/sdvar_spec.c ("256-lane order"), so the result is BIT-EXACT to that
+// spec: top-k is a 32-step radix select on order-preserving keys (integer counts), top-p a 32-step
+// bisection on the canonical masked mass, the sample an argmax with lowest-index tie break.
+//
+// Reference semantics: models/var.py:199-202, models/helpers.py:6-19; verify: SURVEY.md A7.
+#include "common.cuh"
+
+namespace sdvar {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// exp(x), bit-identical to sdvar_spec_expf
+__device__ __forceinline__ float spec_expf(float x) {
+  if (x < -104.0f) return 0.0f;
+  const float t = __fmul_rn(x, 1.44269504088896340736f);
+  const float n = rintf(t);
+  float r = __fmaf_rn(n, -0.693145751953125f, x);
+  r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
+  float p = 1.0f / 5040.0f;
+  p = __fmaf_rn(p, r, 1.0f / 720.0f);
+  p = __fmaf_rn(p, r, 1.0f / 120.0f);
+  p = __fmaf_rn(p, r, 1.0f / 24.0f);
+  p = __fmaf_rn(p, r, 1.0f / 6.0f);
+  p = __fmaf_rn(p, r, 0.5f);
+  p = __fmaf_rn(p, r, 1.0f);
+  p = __fmaf_rn(p, r, 1.0f);
+  const int ni = (int)n;
+  if (ni >= -126) return __fmul_rn(p, u2f((uint32_t)(ni + 127) << 23));
+  return __fmul_rn(__fmul_rn(p, u2f((uint32_t)(ni + 100 + 127) << 23)), u2f((uint32_t)(-100 + 127) << 23));
+}
+
+// ---- block reductions.  `slot` alternates between two smem buffers so one barrier per reduction suffices.
+struct RedSmem {
+  float f[2][2][kWarps];
+  int i[2][kWarps];
+  unsigned long long u64[2][kWarps];
+  uint32_t u[2][2][kWarps];
+  int flag[2];
+  float pq[2][2];
+};
+
+// canonical float sum of two independent quantities at once
+__device__ __forceinline__ void block_sum2(float& a, float& b, RedSmem& s, int& slot) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, off));
+    b = __fadd_rn(b, __shfl_xor_sync(0xffffffffu, b, off));
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s.f[slot][0][w] = a; s.f[slot][1][w] = b; }
+  __syncthreads();
+  a = s.f[slot][0][0];
+  b = s.f[slot][1][0];
+#pragma unroll
+  for (int k = 1; k < kWarps; ++k) { a = __fadd_rn(a, s.f[slot][0][k]); b = __fadd_rn(b, s.f[slot][1][k]); }
+  slot ^= 1;
+}
+__device__ __forceinline__ float block_sum(float a, RedSmem& s, int& slot) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, off));
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) s.f[slot][0][w] = a;
+  __syncthreads();
+  a = s.f[slot][0][0];
+#pragma unroll
+  for (int k = 1; k < kWarps; ++k) a = __fadd_rn(a, s.f[slot][0][k]);
+  slot ^= 1;
+  return a;
+}
+__device__ __forceinline__ int block_sum_int(int c, RedSmem& s, int& slot) {
+  c = __reduce_add_sync(0xffffffffu, c);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) s.i[slot][w] = c;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int k = 0; k < kWarps; ++k) t += s.i[slot][k];
+  slot ^= 1;
+  return t;
+}
+__device__ __forceinline__ void block_max_u32x2(uint32_t& a, uint32_t& b, RedSmem& s, int& slot) {
+  a = __reduce_max_sync(0xffffffffu, a);
+  b = __reduce_max_sync(0xffffffffu, b);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s.u[slot][0][w] = a; s.u[slot][1][w] = b; }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kWarps; ++k) { a = max(a, s.u[slot][0][k]); b = max(b, s.u[slot][1][k]); }
+  slot ^= 1;
+}
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, RedSmem& s, int& slot) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, off);
+    v = o > v ? o : v;
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) s.u64[slot][w] = v;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kWarps; ++k) v = s.u64[slot][k] > v ? s.u64[slot][k] : v;
+  slot ^= 1;
+  return v;
+}
+// (value, index) -> u64 whose max is "largest value, then lowest index"
+__device__ __forceinline__ unsigned long long pack_best(float r, int idx) {
+  return ((unsigned long long)fkey(r) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
+}
+
+// ================================================================================================
+// K3
+// ================================================================================================
+template <int NV>
+__global__ void __launch_bounds__(kThreads, 2)
+k3_sample_kernel(const float* __restrict__ logits, int B, int L, SegTable seg, int top_k, float thr,
+                 const float* __restrict__ noise, long long* __restrict__ idx_out, float* __restrict__ mixed_out,
+                 float* __restrict__ prob_out) {
+  constexpr int V = NV * 1024;
+  constexpr int E = NV * 4;
+  __shared__ RedSmem sm;
+  int slot = 0;
+  const int tid = threadIdx.x;
+  const long long rows = (long long)B * L;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+    const int j = seg_of(seg, pos);
+    const float t1 = seg.t1[j], t2 = seg.t2[j];
+    const float4* pc = reinterpret_cast<const float4*>(logits + row * V);
+    const float4* pu = reinterpret_cast<const float4*>(logits + ((long long)(B + b) * L + pos) * V);
+    float x[E];
+    uint32_t key[E];
+    {
+      float4 a[NV], c[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { a[i] = ldg_stream(pc + i * kThreads + tid); c[i] = ldg_stream(pu + i * kThreads + tid); }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        x[4 * i + 0] = __fsub_rn(__fmul_rn(a[i].x, t1), __fmul_rn(c[i].x, t2));
+        x[4 * i + 1] = __fsub_rn(__fmul_rn(a[i].y, t1), __fmul_rn(c[i].y, t2));
+        x[4 * i + 2] = __fsub_rn(__fmul_rn(a[i].z, t1), __fmul_rn(c[i].z, t2));
+        x[4 * i + 3] = __fsub_rn(__fmul_rn(a[i].w, t1), __fmul_rn(c[i].w, t2));
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) key[e] = fkey(x[e]);
+
+    // ---- top-k: K = key of the k-th largest (radix select, MSB first) ----
+    if (top_k > 0 && top_k < V) {
+      uint32_t K = 0;
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t tr = K | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) c += (key[e] >= tr) ? 1 : 0;
+        if (block_sum_int(c, sm, slot) >= top_k) K = tr;
+      }
+      const uint32_t kneg = fkey(-INFINITY);
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (key[e] < K) { x[e] = -INFINITY; key[e] = kneg; }
+    }
+
+    // ---- row max (exact, on keys) and exponentials ----
+    uint32_t kmax = 0, dummy = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) kmax = max(kmax, key[e]);
+    block_max_u32x2(kmax, dummy, sm, slot);
+    const float m = fkey_inv(kmax);
+    float ex[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) ex[e] = spec_expf(__fsub_rn(x[e], m));
+
+    // ---- top-p: remove v iff mass{key <= key_v} <= thr, never the max ----
+    if (thr >= 0.0f) {
+      float z = 0.0f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) z = __fadd_rn(z, ex[e]);
+      const float Z = block_sum(z, sm, slot);
+      float p[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) p[e] = __fdiv_rn(ex[e], Z);
+      uint32_t K = 0;
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t tr = K | (1u << bit);
+        float a = 0.0f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) a = __fadd_rn(a, (key[e] <= tr) ? p[e] : 0.0f);
+        if (block_sum(a, sm, slot) <= thr) K = tr;
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (key[e] <= K && key[e] != kmax) { x[e] = -INFINITY; ex[e] = 0.0f; }
+    }
+
+    if (mixed_out != nullptr) {
+      float4* po = reinterpret_cast<float4*>(mixed_out + row * V);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) stg_stream(po + i * kThreads + tid, make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]));
+    }
+
+    if (noise != nullptr) {
+      const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
+      float4 nz[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) nz[i] = ldg_stream(pn + i * kThreads + tid);
+      float z = 0.0f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) z = __fadd_rn(z, ex[e]);
+      const float Z2 = block_sum(z, sm, slot);
+      float best = -1.0f, bestp = 0.0f;
+      int bi = 0x7FFFFFFF;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float pv = __fdiv_rn(ex[4 * i + c], Z2);
+          const float r = __fdiv_rn(pv, nn[c]);
+          if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; bestp = pv; }
+        }
+      }
+      const unsigned long long w = block_max_u64(pack_best(best, bi), sm, slot);
+      int win = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
+      if (win == 0x7FFFFFFF) win = 0;
+      if (bi == win || (tid == 0 && (uint32_t)(w >> 32) == fkey(-1.0f))) {
+        if (idx_out) idx_out[row] = win;
+        if (prob_out) prob_out[row] = (bi == win) ? bestp : 0.0f;
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// K4
+// ================================================================================================
+__global__ void k4_init_kernel(int* first_reject, int* n_accept, int B, SegTable seg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * seg.S) {
+    const int j = i % seg.S;
+    first_reject[i] = seg.begin[j + 1] - seg.begin[j];
+    n_accept[i] = 0;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kThreads, 2)
+k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, const long long* __restrict__ draft_idx,
+                 const float* __restrict__ u, const float* __restrict__ noise, int B, int L, SegTable seg,
+                 long long* __restrict__ out_idx, unsigned char* __restrict__ accept, float* __restrict__ p_d_out,
+                 float* __restrict__ q_d_out, int* first_reject, int* n_accept, int* accepted_stages, int* summary,
+                 int* counter) {
+  constexpr int V = NV * 1024;
+  constexpr int E = NV * 4;
+  __shared__ RedSmem sm;
+  __shared__ int s_last;
+  int slot = 0;
+  const int tid = threadIdx.x;
+  const long long rows = (long long)B * L;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+    const int j = seg_of(seg, pos);
+    const float4* pt = reinterpret_cast<const float4*>(xt + row * V);
+    const float4* pd = reinterpret_cast<const float4*>(xd + row * V);
+    float et[E], ed[E];
+    {
+      float4 a[NV], c[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { a[i] = ldg_stream(pt + i * kThreads + tid); c[i] = ldg_stream(pd + i * kThreads + tid); }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        et[4 * i] = a[i].x; et[4 * i + 1] = a[i].y; et[4 * i + 2] = a[i].z; et[4 * i + 3] = a[i].w;
+        ed[4 * i] = c[i].x; ed[4 * i + 1] = c[i].y; ed[4 * i + 2] = c[i].z; ed[4 * i + 3] = c[i].w;
+      }
+    }
+    const int d = (int)draft_idx[row];
+    const float uu = u[row];
+    uint32_t kt = 0, kd = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) { kt = max(kt, fkey(et[e])); kd = max(kd, fkey(ed[e])); }
+    block_max_u32x2(kt, kd, sm, slot);
+    const float mt = fkey_inv(kt), md = fkey_inv(kd);
+    float zt = 0.0f, zd = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      et[e] = spec_expf(__fsub_rn(et[e], mt));
+      ed[e] = spec_expf(__fsub_rn(ed[e], md));
+      zt = __fadd_rn(zt, et[e]);
+      zd = __fadd_rn(zd, ed[e]);
+    }
+    block_sum2(zt, zd, sm, slot);  // zt, zd now hold Zt, Zd
+    // the owner of element d evaluates the accept test (flag/pq are rewritten only after two more
+    // block barriers of the next row, so a single buffer is race-free)
+    const int fs = 0;
+    {
+      const int fd = d >> 2;
+      if ((fd & (kThreads - 1)) == tid) {
+        float etd = 0.0f, edd = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (4 * (i * kThreads + tid) + c == d) { etd = et[4 * i + c]; edd = ed[4 * i + c]; }
+        const float pdv = __fdiv_rn(etd, zt), qdv = __fdiv_rn(edd, zd);
+        sm.flag[fs] = (__fmul_rn(uu, qdv) < pdv) ? 1 : 0;
+        sm.pq[fs][0] = pdv;
+        sm.pq[fs][1] = qdv;
+      }
+    }
+    __syncthreads();
+    const int acc = sm.flag[fs];
+    const float pdv = sm.pq[fs][0], qdv = sm.pq[fs][1];
+    int out = d;
+    if (!acc) {  // block-uniform
+      const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
+      float4 nz[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) nz[i] = ldg_stream(pn + i * kThreads + tid);
+      int anyp = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float pv = __fdiv_rn(et[e], zt);
+        float rv = __fsub_rn(pv, __fdiv_rn(ed[e], zd));
+        rv = rv > 0.0f ? rv : 0.0f;
+        anyp |= (rv > 0.0f) ? 1 : 0;
+        ed[e] = rv;   // residual
+        et[e] = pv;   // target probability
+      }
+      anyp = __syncthreads_or(anyp);
+      float best = -1.0f;
+      int bi = 0x7FFFFFFF;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float num = anyp ? ed[4 * i + c] : et[4 * i + c];
+          const float r = __fdiv_rn(num, nn[c]);
+          if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; }
+        }
+      }
+      const unsigned long long w = block_max_u64(pack_best(best, bi), sm, slot);
+      out = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
+      if (out == 0x7FFFFFFF) out = 0;
+    }
+    if (tid == 0) {
+      out_idx[row] = out;
+      accept[row] = (unsigned char)acc;
+      if (p_d_out) p_d_out[row] = pdv;
+      if (q_d_out) q_d_out[row] = qdv;
+      if (acc) atomicAdd(&n_accept[b * seg.S + j], 1);
+      else atomicMin(&first_reject[b * seg.S + j], pos - seg.begin[j]);
+    }
+  }
+  // ---- last CTA finalises the per-image / batch scan (integer atomics => deterministic) ----
+  __threadfence();
+  if (tid == 0) s_last = (atomicAdd(counter, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    int mn = seg.S, na = 0;
+    for (int b = tid; b < B; b += kThreads) {
+      int a = 0;
+      bool open = true;
+      for (int j2 = 0; j2 < seg.S; ++j2) {
+        const int n = __ldcg(&n_accept[b * seg.S + j2]);
+        na += n;
+        if (open && n == seg.begin[j2 + 1] - seg.begin[j2]) ++a; else open = false;
+      }
+      accepted_stages[b] = a;
+      mn = min(mn, a);
+    }
+    // min over images via max of (S - accepted)
+    uint32_t neg = (uint32_t)(seg.S - mn), z = 0;
+    block_max_u32x2(neg, z, sm, slot);
+    const int total_acc = block_sum_int(na, sm, slot);
+    if (tid == 0) {
+      summary[0] = seg.S - (int)neg;
+      summary[1] = total_acc;
+      summary[2] = (int)rows - total_acc;
+      summary[3] = 0;
+      *counter = 0;
+    }
+  }
+}
+
+// reference rule: top-1 match (models/var.py:1199-1206)
+template <int NV>
+__global__ void __launch_bounds__(kThreads, 4)
+top1_match_kernel(const float* __restrict__ xt, const long long* __restrict__ draft_idx, int B, int L, SegTable seg,
+                  unsigned char* __restrict__ match, int* n_match) {
+  constexpr int V = NV * 1024;
+  __shared__ RedSmem sm;
+  int slot = 0;
+  const int tid = threadIdx.x;
+  const long long rows = (long long)B * L;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+    const float4* pt = reinterpret_cast<const float4*>(xt + row * V);
+    float best = -INFINITY;
+    int bi = 0x7FFFFFFF;
+    bool first = true;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = ldg_stream(pt + i * kThreads + tid);
+      const float vv[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (first || vv[c] > best) { best = vv[c]; bi = 4 * (i * kThreads + tid) + c; first = false; }
+    }
+    const unsigned long long w = block_max_u64(pack_best(best, bi), sm, slot);
+    if (tid == 0) {
+      const int am = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
+      const int mt = (am == (int)draft_idx[row]) ? 1 : 0;
+      match[row] = (unsigned char)mt;
+      if (mt) atomicAdd(&n_match[b * seg.S + seg_of(seg, pos)], 1);
+    }
+  }
+}
+
+static int fill_seg(SegTable& seg, const int* seg_begin_host, int S, int L, const float* t1, const float* t2) {
+  SDVAR_REQUIRE(S >= 1 && S <= SDVAR_MAX_SEG, "S=%d out of range [1,%d]", S, SDVAR_MAX_SEG);
+  SDVAR_REQUIRE(seg_begin_host != nullptr, "seg_begin_host is NULL");
+  SDVAR_REQUIRE(seg_begin_host[0] == 0 && seg_begin_host[S] == L, "segment table must cover [0,L)");
+  seg.S = S;
+  for (int j = 0; j <= S; ++j) seg.begin[j] = seg_begin_host[j];
+  for (int j = 0; j < S; ++j) {
+    SDVAR_REQUIRE(seg.begin[j + 1] > seg.begin[j], "empty segment %d", j);
+    seg.t1[j] = t1 ? t1[j] : 1.0f;
+    seg.t2[j] = t2 ? t2[j] : 0.0f;
+  }
+  return SDVAR_OK;
+}
+
+static int row_grid(long long rows, int blocks_per_sm) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long g = (long long)sms * blocks_per_sm;
+  return (int)(rows < g ? rows : g);
+}
+
+}  // namespace sdvar
+
+using namespace sdvar;
+
+extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L, int V, const int* seg_begin_host, int S,
+                                          const float* t1_host, const float* t2_host, int top_k, float one_minus_top_p,
+                                          const float* noise, long long* idx_out, float* mixed_out, float* prob_out,
+                                          void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(logits_2BLV && B > 0 && L > 0, "bad logits/B/L");
+  SDVAR_REQUIRE(V % 1024 == 0 && V >= 1024 && V <= 8192, "V=%d must be a multiple of 1024 in [1024,8192]", V);
+  SDVAR_REQUIRE(((uintptr_t)logits_2BLV & 15) == 0 && ((uintptr_t)noise & 15) == 0 && ((uintptr_t)mixed_out & 15) == 0,
+                "row pointers must be 16-byte aligned");
+  SDVAR_REQUIRE(t1_host && t2_host, "t1/t2 are NULL");
+  SegTable seg;
+  if (int rc = fill_seg(seg, seg_begin_host, S, L, t1_host, t2_host)) return rc;
+  const long long rows = (long long)B * L;
+  const int grid = row_grid(rows, 2);
+  cudaStream_t st = (cudaStream_t)stream;
+#define SDVAR_K3(NV)                                                                                          \
+  case NV:                                                                                                    \
+    k3_sample_kernel<NV><<<grid, kThreads, 0, st>>>(logits_2BLV, B, L, seg, top_k, one_minus_top_p, noise,   \
+                                                    idx_out, mixed_out, prob_out);                           \
+    break;
+  switch (V / 1024) {
+    SDVAR_K3(1) SDVAR_K3(2) SDVAR_K3(4) SDVAR_K3(8)
+    default:
+      SDVAR_REQUIRE(false, "V=%d unsupported (1024,2048,4096,8192)", V);
+  }
+#undef SDVAR_K3
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
+
+extern "C" int sdvar_verify_accept_resample(const float* xt, const float* xd, const long long* draft_idx, const float* u,
+                                            const float* noise, int B, int L, int V, const int* seg_begin_host, int S,
+                                            long long* out_idx, unsigned char* accept, float* p_d_out, float* q_d_out,
+                                            int* first_reject, int* n_accept, int* accepted_stages, int* summary,
+                                            int* workspace, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(xt && xd && draft_idx && u && noise && out_idx && accept && first_reject && n_accept && accepted_stages &&
+                    summary && workspace,
+                "NULL argument");
+  SDVAR_REQUIRE(B > 0 && L > 0, "bad B/L");
+  SDVAR_REQUIRE(V % 1024 == 0 && V >= 1024 && V <= 8192, "V=%d must be a multiple of 1024 in [1024,8192]", V);
+  SDVAR_REQUIRE(((uintptr_t)xt & 15) == 0 && ((uintptr_t)xd & 15) == 0 && ((uintptr_t)noise & 15) == 0, "16-byte alignment");
+  SegTable seg;
+  if (int rc = fill_seg(seg, seg_begin_host, S, L, nullptr, nullptr)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  k4_init_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(first_reject, n_accept, B, seg);
+  SDVAR_LAUNCH_CHECK();
+  const int grid = row_grid((long long)B * L, 2);
+#define SDVAR_K4(NV)                                                                                               \
+  case NV:                                                                                                         \
+    k4_verify_kernel<NV><<<grid, kThreads, 0, st>>>(xt, xd, draft_idx, u, noise, B, L, seg, out_idx, accept,      \
+                                                    p_d_out, q_d_out, first_reject, n_accept, accepted_stages,    \
+                                                    summary, workspace);                                           \
+    break;
+  switch (V / 1024) {
+    SDVAR_K4(1) SDVAR_K4(2) SDVAR_K4(4) SDVAR_K4(8)
+    default:
+      SDVAR_REQUIRE(false, "V=%d unsupported", V);
+  }
+#undef SDVAR_K4
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
+
+extern "C" int sdvar_verify_top1(const float* xt, const long long* draft_idx, int B, int L, int V,
+                                 const int* seg_begin_host, int S, unsigned char* match, int* n_match, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(xt && draft_idx && match && n_match, "NULL argument");
+  SDVAR_REQUIRE(V % 1024 == 0 && V >= 1024 && V <= 8192, "V=%d must be a multiple of 1024 in [1024,8192]", V);
+  SegTable seg;
+  if (int rc = fill_seg(seg, seg_begin_host, S, L, nullptr, nullptr)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  SDVAR_CUDA(cudaMemsetAsync(n_match, 0, sizeof(int) * B * S, st));
+  const int grid = row_grid((long long)B * L, 4);
+  switch (V / 1024) {
+    case 1: top1_match_kernel<1><<<grid, kThreads, 0, st>>>(xt, draft_idx, B, L, seg, match, n_match); break;
+    case 2: top1_match_kernel<2><<<grid, kThreads, 0, st>>>(xt, draft_idx, B, L, seg, match, n_match); break;
+    case 4: top1_match_kernel<4><<<grid, kThreads, 0, st>>>(xt, draft_idx, B, L, seg, match, n_match); break;
+    case 8: top1_match_kernel<8><<<grid, kThreads, 0, st>>>(xt, draft_idx, B, L, seg, match, n_match); break;
+    default: SDVAR_REQUIRE(false, "V=%d unsupported", V);
+  }
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}

@@ -1,0 +1,55 @@
+#include "tmap.cuh"
+
+namespace sdvar {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || p == nullptr)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available (driver too old or no driver)");
+    return SDVAR_ERR_CUDA;
+  }
+  SDVAR_REQUIRE(rank >= 2 && rank <= 3, "tensor map rank %d", rank);
+  SDVAR_REQUIRE(((uintptr_t)base & 15) == 0, "TMA base must be 16-byte aligned");
+  cuuint64_t gdims[3];
+  cuuint64_t gstr[2];
+  cuuint32_t gbox[3], estr[3];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    SDVAR_REQUIRE(box[i] >= 1 && box[i] <= 256, "TMA box[%d]=%u", i, box[i]);
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    SDVAR_REQUIRE(strides_bytes[i] % 16 == 0, "TMA stride %llu not a multiple of 16 bytes", (unsigned long long)strides_bytes[i]);
+  }
+  SDVAR_REQUIRE(box[0] * 2 == 128, "inner box must be 128 bytes for SWIZZLE_128B");
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1]);
+    return SDVAR_ERR_CUDA;
+  }
+  return SDVAR_OK;
+}
+
+}  // namespace sdvar

@@ -1,0 +1,16 @@
+// tmap.cuh -- host-side TMA tensor-map construction.  cuTensorMapEncodeTiled is resolved at run time via
+// cudaGetDriverEntryPoint, so libsdvar_b200.so has no link-time dependency on libcuda.so.1.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace sdvar {
+
+// bf16 tensor, up to 3 dims (dims[0] innermost, contiguous), 128-byte swizzle, zero fill out of bounds.
+// strides_bytes[i] is the byte stride of dims[i+1].  box[0] must be 64 elements (=128 bytes).
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+}  // namespace sdvar

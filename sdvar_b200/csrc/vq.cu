@@ -1,0 +1,251 @@
+// vq.cu -- K5: VectorQuantizer2 next-input step and the stage input maps.
+//
+// Replaces models/var.py:205-211 + models/quant.py:187-196 (get_next_autoregressive_input),
+// :199-206 (Phi = 0.5*h + 0.5*conv3x3(h)), and models/var.py:179-188 (stage input maps).
+//
+// f_hat is tiny (32 KiB per image at 256 px), so this step is latency-bound, not HBM-bound: the design
+// goal is few launches and on-chip staging.  Kernel A gives each CTA one output row of one image: it
+// gathers only the codebook rows the bicubic taps of rows y-1..y+1 touch, interpolates separably in
+// shared memory, runs the 3x3 Phi conv with the weights staged in shared memory ([ci][tap][co], bank =
+// co) and adds into f_hat through a transposing shared tile so the global update is row-contiguous.
+// Kernel B is the overlapping-window area pooling (adaptive average) to the next stage's resolution.
+#include "common.cuh"
+
+namespace sdvar {
+
+constexpr int kC = 32;       // Cvae
+constexpr int kMaxHW = 32;   // 512 px pyramid
+constexpr int kMaxSrcRows = 8;
+
+// Keys cubic convolution coefficients, A = -0.75 (ATen upsample_bicubic2d, align_corners=False)
+__device__ __forceinline__ void cubic_coeffs(float t, float w[4]) {
+  const float A = -0.75f;
+  float x = t + 1.0f;
+  w[0] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+  x = t;
+  w[1] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+  x = 1.0f - t;
+  w[2] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+  x = 2.0f - t;
+  w[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+}
+// source index / fraction of output coordinate o (half-pixel centres, no clamping of the real coordinate)
+__device__ __forceinline__ void cubic_src(int o, int pn, int HW, int& ix, float& t) {
+  const float scale = (float)pn / (float)HW;
+  const float s = scale * ((float)o + 0.5f) - 0.5f;
+  const float fl = floorf(s);
+  ix = (int)fl;
+  t = s - fl;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+struct VqSmem {
+  float w[kC * 9 * kC];                       // [ci][tap][co]
+  float bias[kC];
+  float src[kMaxSrcRows][kMaxHW][kC];         // gathered codebook rows  [r][q][c]
+  float tmp[kMaxSrcRows][kMaxHW][kC];         // after horizontal interpolation [r][x][c]
+  float hup[3][kMaxHW + 2][kC];               // rows y-1,y,y+1 with one zero column on each side [dy][x+1][c]
+  float outT[kC][kMaxHW + 1];                 // conv result transposed [co][x]
+};
+
+__global__ void __launch_bounds__(256)
+vq_accumulate_kernel(const long long* __restrict__ idx, int pn, int HW, const float* __restrict__ codebook,
+                     const float* __restrict__ phi_w, const float* __restrict__ phi_b, float* __restrict__ f_hat) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  VqSmem& s = *reinterpret_cast<VqSmem*>(smem_raw);
+  const int b = blockIdx.y, y = blockIdx.x, tid = threadIdx.x;
+  const int lane = tid & 31, grp = tid >> 5;
+  const bool up = (pn != HW);
+
+  // stage Phi weights as [ci][tap][co] (global layout is [co][ci][3][3])
+  for (int i = tid; i < kC * kC * 9; i += 256) {
+    const int co = i / (kC * 9), rem = i - co * kC * 9, ci = rem / 9, tap = rem - ci * 9;
+    s.w[(ci * 9 + tap) * kC + co] = phi_w[i];
+  }
+  if (tid < kC) s.bias[tid] = phi_b[tid];
+
+  // source rows needed by output rows y-1..y+1
+  int r0, r1;
+  if (up) {
+    int ixa, ixb; float t;
+    cubic_src(max(y - 1, 0), pn, HW, ixa, t);
+    cubic_src(min(y + 1, HW - 1), pn, HW, ixb, t);
+    r0 = clampi(ixa - 1, 0, pn - 1);
+    r1 = clampi(ixb + 2, 0, pn - 1);
+  } else {
+    r0 = max(y - 1, 0);
+    r1 = min(y + 1, HW - 1);
+  }
+  const int nr = r1 - r0 + 1;  // <= kMaxSrcRows (upscaling factor >= 1 => at most 6 rows)
+  // gather: one warp per token, lane = channel (128-byte coalesced codebook rows)
+  for (int tk = grp; tk < nr * pn; tk += 8) {
+    const int r = tk / pn, q = tk - r * pn;
+    const long long id = idx[(long long)b * pn * pn + (r0 + r) * pn + q];
+    s.src[r][q][lane] = codebook[id * kC + lane];
+  }
+  __syncthreads();
+  if (up) {
+    // horizontal: tmp[r][x][c]
+    for (int i = grp; i < nr * HW; i += 8) {
+      const int r = i / HW, x = i - r * HW;
+      int ix; float t, w[4];
+      cubic_src(x, pn, HW, ix, t);
+      cubic_coeffs(t, w);
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc += w[k] * s.src[r][clampi(ix - 1 + k, 0, pn - 1)][lane];
+      s.tmp[r][x][lane] = acc;
+    }
+    __syncthreads();
+  }
+  // vertical + zero padding: hup[dy][x+1][c]
+  for (int i = grp; i < 3 * (HW + 2); i += 8) {
+    const int dy = i / (HW + 2), xp = i - dy * (HW + 2);
+    const int yy = y - 1 + dy, x = xp - 1;
+    float v = 0.0f;
+    if (yy >= 0 && yy < HW && x >= 0 && x < HW) {
+      if (up) {
+        int iy; float t, w[4];
+        cubic_src(yy, pn, HW, iy, t);
+        cubic_coeffs(t, w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v += w[k] * s.tmp[clampi(iy - 1 + k, 0, pn - 1) - r0][x][lane];
+      } else {
+        v = s.src[yy - r0][x][lane];
+      }
+    }
+    s.hup[dy][xp][lane] = v;
+  }
+  __syncthreads();
+  // conv: thread (co = lane, x = grp, grp+8, ..)
+  for (int x = grp; x < HW; x += 8) {
+    float acc = s.bias[lane];
+#pragma unroll 4
+    for (int ci = 0; ci < kC; ++ci) {
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+          acc += s.w[(ci * 9 + dy * 3 + dx) * kC + lane] * s.hup[dy][x + dx][ci];
+    }
+    s.outT[lane][x] = 0.5f * s.hup[1][x + 1][lane] + 0.5f * acc;
+  }
+  __syncthreads();
+  // f_hat[b, c, y, :] += outT[c][:]   (row-contiguous)
+  for (int i = tid; i < kC * HW; i += 256) {
+    const int c = i / HW, x = i - c * HW;
+    float* p = f_hat + (((long long)b * kC + c) * HW + y) * HW + x;
+    *p += s.outT[c][x];
+  }
+}
+
+// adaptive average pooling (F.interpolate(mode='area')): window [floor(o*HW/pn2), ceil((o+1)*HW/pn2))
+__global__ void __launch_bounds__(256)
+vq_area_down_kernel(const float* __restrict__ f_hat, int HW, int pn2, float* __restrict__ next_map) {
+  const int b = blockIdx.x;
+  const int n = kC * pn2 * pn2;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i / (pn2 * pn2), rem = i - c * pn2 * pn2, oy = rem / pn2, ox = rem - oy * pn2;
+    const int y0 = (oy * HW) / pn2, y1 = ((oy + 1) * HW + pn2 - 1) / pn2;
+    const int x0 = (ox * HW) / pn2, x1 = ((ox + 1) * HW + pn2 - 1) / pn2;
+    const float* src = f_hat + ((long long)b * kC + c) * HW * HW;
+    float acc = 0.0f;
+    for (int yy = y0; yy < y1; ++yy)
+      for (int xx = x0; xx < x1; ++xx) acc += src[yy * HW + xx];
+    next_map[(long long)b * n + i] = acc / (float)((y1 - y0) * (x1 - x0));
+  }
+}
+
+// x[r,t,:] = W @ nm[b,:,t] + bias + lvl_pos[t,:], r in {b, B+b}   (models/var.py:185-188)
+constexpr int kEmbTok = 8;
+__global__ void __launch_bounds__(256)
+embed_next_map_kernel(const float* __restrict__ nm, int B, int l, int C, const float* __restrict__ W,
+                      const float* __restrict__ bias, const float* __restrict__ lvl_pos, float* __restrict__ x,
+                      int ldx_tokens, int tok_off) {
+  __shared__ float tok[kEmbTok][kC];
+  const int b = blockIdx.y, t0 = blockIdx.x * kEmbTok;
+  const int nt = min(kEmbTok, l - t0);
+  for (int i = threadIdx.x; i < kEmbTok * kC; i += blockDim.x) {
+    const int tt = i / kC, c = i - tt * kC;
+    tok[tt][c] = (tt < nt) ? nm[((long long)b * kC + c) * l + t0 + tt] : 0.0f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float w[kC];
+    const float4* wr = reinterpret_cast<const float4*>(W + (long long)c * kC);
+#pragma unroll
+    for (int k = 0; k < kC / 4; ++k) {
+      const float4 v = __ldg(wr + k);
+      w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+    }
+    const float bc = bias[c];
+    for (int tt = 0; tt < nt; ++tt) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < kC; ++k) acc += w[k] * tok[tt][k];
+      const float v = acc + bc + lvl_pos[(long long)(t0 + tt) * C + c];
+      x[((long long)b * ldx_tokens + tok_off + t0 + tt) * C + c] = v;
+      x[((long long)(B + b) * ldx_tokens + tok_off + t0 + tt) * C + c] = v;
+    }
+  }
+}
+
+__global__ void first_map_kernel(const float* __restrict__ cond, int first_l, int C, const float* __restrict__ pos_start,
+                                 const float* __restrict__ lvl_pos, float* __restrict__ x, int ldx_tokens, int tok_off) {
+  const int r = blockIdx.y, t = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    x[((long long)r * ldx_tokens + tok_off + t) * C + c] = cond[(long long)r * C + c] + pos_start[(long long)t * C + c] + lvl_pos[(long long)t * C + c];
+}
+
+}  // namespace sdvar
+
+using namespace sdvar;
+
+extern "C" int sdvar_vq_next_input(const long long* idx_Bl, int B, int pn, int HW, int pn_next, int Cvae,
+                                   const float* codebook, const float* phi_w, const float* phi_b, float* f_hat,
+                                   float* next_map, float* scratch, void* stream) {
+  (void)scratch;
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(idx_Bl && codebook && phi_w && phi_b && f_hat, "NULL argument");
+  SDVAR_REQUIRE(Cvae == kC, "Cvae=%d unsupported (32)", Cvae);
+  SDVAR_REQUIRE(B > 0 && pn >= 1 && pn <= HW && HW <= kMaxHW, "bad geometry pn=%d HW=%d", pn, HW);
+  SDVAR_REQUIRE(pn_next >= 0 && pn_next <= HW, "bad pn_next=%d", pn_next);
+  SDVAR_REQUIRE(pn_next == 0 || next_map != nullptr, "next_map is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDVAR_CUDA(cudaFuncSetAttribute(vq_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VqSmem)));
+    attr_set = true;
+  }
+  vq_accumulate_kernel<<<dim3(HW, B), 256, sizeof(VqSmem), st>>>(idx_Bl, pn, HW, codebook, phi_w, phi_b, f_hat);
+  SDVAR_LAUNCH_CHECK();
+  if (pn_next > 0) {
+    vq_area_down_kernel<<<B, 256, 0, st>>>(f_hat, HW, pn_next, next_map);
+    SDVAR_LAUNCH_CHECK();
+  }
+  return SDVAR_OK;
+}
+
+extern "C" int sdvar_embed_next_map(const float* next_map, int B, int l, int Cvae, int C, const float* W_we,
+                                    const float* b_we, const float* lvl_pos, float* x, int ldx_tokens, int tok_off,
+                                    void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(next_map && W_we && b_we && lvl_pos && x, "NULL argument");
+  SDVAR_REQUIRE(Cvae == kC, "Cvae=%d unsupported (32)", Cvae);
+  SDVAR_REQUIRE(B > 0 && l > 0 && C > 0 && ldx_tokens >= tok_off + l, "bad geometry");
+  SDVAR_REQUIRE(((uintptr_t)W_we & 15) == 0, "W_we must be 16-byte aligned");
+  embed_next_map_kernel<<<dim3((l + kEmbTok - 1) / kEmbTok, B), 256, 0, (cudaStream_t)stream>>>(
+      next_map, B, l, C, W_we, b_we, lvl_pos, x, ldx_tokens, tok_off);
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
+
+extern "C" int sdvar_first_map(const float* cond_2BC, int B2, int first_l, int C, const float* pos_start,
+                               const float* lvl_pos, float* x, int ldx_tokens, int tok_off, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(cond_2BC && pos_start && lvl_pos && x && B2 > 0 && first_l > 0 && C > 0, "bad argument");
+  first_map_kernel<<<dim3(first_l, B2), 256, 0, (cudaStream_t)stream>>>(cond_2BC, first_l, C, pos_start, lvl_pos, x,
+                                                                          ldx_tokens, tok_off);
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}

@@ -1,0 +1,310 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes), against the oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from sdvar_b200.weights import hashed
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+P256 = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)
+
+
+def _seg(ls):
+    return [0] + list(np.cumsum(ls))
+
+
+# ------------------------------------------------------------------------------------------------ K3
+@pytest.mark.parametrize("scale,top_k,top_p", [(0.05, 0, 0.0), (0.05, 900, 0.96), (3.0, 900, 0.96), (3.0, 0, 0.9),
+                                                (1.0, 50, 0.5), (3.0, 600, 0.0)])
+def test_sample_bit_exact_vs_c_spec(cuda_lib, scale, top_k, top_p):
+    from oracle import spec
+    B, V = 3, 4096
+    ls = [4, 9, 16]                      # a 3-stage window with per-stage CFG strength
+    L = sum(ls)
+    seg = _seg(ls)
+    lg = hashed(f"k3.{scale}", 1, (2 * B, L, V), scale)
+    noise = torch.empty(B * L, V).exponential_(generator=torch.Generator().manual_seed(3))
+    t1, t2 = spec.cfg_scalars(1.5, [1, 2, 3], 10)
+    idx_ref, mixed_ref, prob_ref = spec.sample(lg, seg, t1, t2, top_k, top_p, noise)
+    idx = torch.empty(B, L, dtype=torch.int64, device=DEV)
+    mixed = torch.empty(B, L, V, device=DEV)
+    prob = torch.empty(B, L, device=DEV)
+    cuda_lib.sample_cfg_topk_topp(lg.to(DEV), B, L, V, seg, t1, t2, top_k, spec.top_p_threshold(top_p), noise.to(DEV),
+                                  idx, mixed, prob)
+    torch.cuda.synchronize()
+    assert torch.equal(idx.cpu(), idx_ref)
+    assert torch.equal(mixed.cpu().view(torch.int32), mixed_ref.view(torch.int32))      # bit-exact incl. -inf pattern
+    assert torch.equal(prob.cpu().view(torch.int32), prob_ref.view(torch.int32))
+
+
+def test_sample_filter_only_and_ragged_rows(cuda_lib):
+    """noise=NULL => filter only; rows > grid exercise the persistent loop; single-token stage."""
+    from oracle import spec
+    B, V, ls = 2, 4096, [1, 700]
+    L, seg = sum(ls), _seg(ls)
+    lg = hashed("k3.big", 2, (2 * B, L, V), 2.0)
+    t1, t2 = spec.cfg_scalars(4.0, [0, 9], 10)
+    _, mixed_ref, _ = spec.sample(lg[:, :40].contiguous(), [0, 1, 40], t1, t2, 900, 0.96, None)
+    mixed = torch.empty(B, L, V, device=DEV)
+    cuda_lib.sample_cfg_topk_topp(lg.to(DEV), B, L, V, seg, t1, t2, 900, spec.top_p_threshold(0.96), None, None, mixed, None)
+    torch.cuda.synchronize()
+    assert torch.equal(mixed.cpu()[:, :40].contiguous().view(torch.int32), mixed_ref.view(torch.int32))
+
+
+def test_sample_matches_torch_reference_sampler(cuda_lib):
+    """tokens equal the reference's own sampler (helpers.py:6-19) fed the same pre-drawn noise"""
+    from oracle import spec
+    from oracle.ref_model import cfg_mix, sample_with_noise_
+    B, L, V = 4, 64, 4096
+    lg = hashed("k3.torch", 5, (2 * B, L, V), 1.5)
+    noise = torch.empty(B * L, V).exponential_(generator=torch.Generator().manual_seed(11))
+    si, K = 6, 10
+    t1, t2 = spec.cfg_scalars(1.5, [si], K)
+    ref = sample_with_noise_(cfg_mix(lg, B, 1.5 * si / (K - 1)), noise, 900, 0.96)
+    idx = torch.empty(B, L, dtype=torch.int64, device=DEV)
+    cuda_lib.sample_cfg_topk_topp(lg.to(DEV), B, L, V, [0, L], t1, t2, 900, spec.top_p_threshold(0.96), noise.to(DEV), idx, None, None)
+    assert torch.equal(idx.cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ K4
+def _verify_inputs(B, ls, V, scale, seed, top_k=0, top_p=0.0):
+    from oracle import spec
+    L = sum(ls)
+    g = torch.Generator().manual_seed(seed)
+    xt = hashed(f"k4t.{scale}", seed, (B, L, V), scale)
+    xd = xt + hashed(f"k4d.{scale}", seed, (B, L, V), scale * 0.35)      # draft = perturbed target
+    if top_k or top_p:
+        from oracle.ref_model import filter_top_k_top_p_
+        filter_top_k_top_p_(xt, top_k, top_p); filter_top_k_top_p_(xd, top_k, top_p)
+    d = torch.multinomial(xd.softmax(-1).view(-1, V), 1, generator=g).view(B, L)
+    u = torch.rand(B, L, generator=g)
+    noise = torch.empty(B * L, V).exponential_(generator=g)
+    return xt, xd, d, u, noise
+
+
+@pytest.mark.parametrize("scale,top_k,top_p", [(0.05, 0, 0.0), (3.0, 0, 0.0), (3.0, 900, 0.96)])
+def test_verify_bit_exact_vs_c_spec(cuda_lib, scale, top_k, top_p):
+    from oracle import spec
+    B, V, ls = 5, 4096, [1, 4, 9, 16, 25]
+    L, seg, S = sum(ls), _seg(ls), len(ls)
+    xt, xd, d, u, noise = _verify_inputs(B, ls, V, scale, 7, top_k, top_p)
+    ref = spec.verify(xt, xd, d, u, noise, seg)
+    out = dict(out_idx=torch.empty(B, L, dtype=torch.int64, device=DEV), accept=torch.empty(B, L, dtype=torch.uint8, device=DEV),
+               p_d=torch.empty(B, L, device=DEV), q_d=torch.empty(B, L, device=DEV),
+               first_reject=torch.empty(B, S, dtype=torch.int32, device=DEV), n_accept=torch.empty(B, S, dtype=torch.int32, device=DEV),
+               accepted_stages=torch.empty(B, dtype=torch.int32, device=DEV), summary=torch.empty(4, dtype=torch.int32, device=DEV))
+    ws = torch.zeros(4, dtype=torch.int32, device=DEV)
+    for _ in range(2):   # second call checks that the workspace counter was left at zero
+        cuda_lib.verify_accept_resample(xt.to(DEV), xd.to(DEV), d.to(DEV), u.to(DEV), noise.to(DEV), B, L, V, seg,
+                                        out["out_idx"], out["accept"], out["p_d"], out["q_d"], out["first_reject"],
+                                        out["n_accept"], out["accepted_stages"], out["summary"], ws)
+        torch.cuda.synchronize()
+        for k, v in ref.items():
+            got = out[k].cpu()
+            if v.dtype == torch.float32:
+                assert torch.equal(got.view(torch.int32), v.view(torch.int32)), k
+            else:
+                assert torch.equal(got, v), k
+    assert 0 < int(ref["summary"][2]) or scale < 1          # peaked case must exercise the reject path
+    assert int(ws[0]) == 0
+
+
+def test_verify_identical_distributions_accept_everything(cuda_lib):
+    """p == q  =>  u*q < p for every u in [0,1): all accepted, prefix = all stages (edge: no reject anywhere)"""
+    B, V, ls = 2, 4096, [4, 9]
+    L, seg, S = sum(ls), _seg(ls), 2
+    xt, _, d, u, noise = _verify_inputs(B, ls, V, 2.0, 9)
+    x = xt.to(DEV)
+    o = torch.empty(B, L, dtype=torch.int64, device=DEV); a = torch.empty(B, L, dtype=torch.uint8, device=DEV)
+    fr = torch.empty(B, S, dtype=torch.int32, device=DEV); na = torch.empty(B, S, dtype=torch.int32, device=DEV)
+    st = torch.empty(B, dtype=torch.int32, device=DEV); sm = torch.empty(4, dtype=torch.int32, device=DEV)
+    ws = torch.zeros(4, dtype=torch.int32, device=DEV)
+    cuda_lib.verify_accept_resample(x, x, d.to(DEV), u.to(DEV), noise.to(DEV), B, L, V, seg, o, a, None, None, fr, na, st, sm, ws)
+    assert bool(a.all()) and torch.equal(o.cpu(), d)
+    assert st.tolist() == [S] * B and sm.tolist() == [S, B * L, 0, 0]
+    assert fr.cpu().tolist() == [ls] * B and na.cpu().tolist() == [ls] * B
+
+
+def test_verify_top1_reference_rule(cuda_lib):
+    B, V, ls = 3, 4096, [4, 9, 16]
+    L, seg, S = sum(ls), _seg(ls), 3
+    xt, _, d, _, _ = _verify_inputs(B, ls, V, 3.0, 4)
+    d[:, ::2] = xt.argmax(-1)[:, ::2]
+    match = torch.empty(B, L, dtype=torch.uint8, device=DEV); nm = torch.empty(B, S, dtype=torch.int32, device=DEV)
+    cuda_lib.verify_top1(xt.to(DEV), d.to(DEV), B, L, V, seg, match, nm)
+    ref = (xt.argmax(-1) == d)
+    assert torch.equal(match.cpu().bool(), ref)
+    assert nm.cpu().tolist() == [[int(ref[b, seg[j]:seg[j + 1]].sum()) for j in range(S)] for b in range(B)]
+
+
+# ------------------------------------------------------------------------------------------------ K5
+@pytest.mark.parametrize("pns", [P256, (1, 2, 3, 4), (1, 2, 3, 4, 6, 9, 13, 18, 24, 32)])
+def test_vq_next_input_vs_oracle(cuda_lib, pns):
+    from oracle.ref_model import RefVQ, phi_index
+    from sdvar_b200.weights import vqvae_state_dict
+    sd = {k: v for k, v in vqvae_state_dict(ch=32, patch_nums=pns).items() if k.startswith("quantize.")}
+    vq = RefVQ(sd, pns)
+    B, HW, K = 3, pns[-1], len(pns)
+    g = torch.Generator().manual_seed(0)
+    f_ref = torch.zeros(B, 32, HW, HW)
+    f_gpu = torch.zeros(B, 32, HW, HW, device=DEV)
+    cb = sd["quantize.embedding.weight"].to(DEV)
+    for si, pn in enumerate(pns):
+        idx = torch.randint(0, 4096, (B, pn * pn), generator=g)
+        f_ref, nm_ref = vq.next_input(si, f_ref, idx)           # F.interpolate path = the reference's own ops
+        k = phi_index(si, K, 4)
+        pn2 = pns[si + 1] if si + 1 < K else 0
+        nm = torch.empty(B, 32, max(pn2, 1), max(pn2, 1), device=DEV)
+        cuda_lib.vq_next_input(idx.to(DEV), B, pn, HW, pn2, 32, cb, sd[f"quantize.quant_resi.qresi_ls.{k}.weight"].to(DEV).contiguous(),
+                               sd[f"quantize.quant_resi.qresi_ls.{k}.bias"].to(DEV), f_gpu, nm if pn2 else None)
+        torch.cuda.synchronize()
+        # fp32 tolerance: |f_hat| ~ O(1..10) after 10 stages; bicubic/conv re-association ~1e-6 relative
+        assert torch.allclose(f_gpu.cpu(), f_ref, rtol=1e-5, atol=2e-5), si
+        if pn2:
+            assert torch.allclose(nm.cpu(), nm_ref, rtol=1e-5, atol=2e-5), si
+        f_gpu.copy_(f_ref)     # keep both sides on identical state so errors do not compound
+
+
+def test_stage_input_maps_vs_oracle(cuda_lib):
+    from oracle.ref_model import RefVAR
+    from sdvar_b200.weights import var_state_dict
+    pns = (1, 2, 3, 4)
+    sd = var_state_dict(2, patch_nums=pns)
+    o = RefVAR(sd, pns)
+    B, C = 3, o.C
+    lab = torch.tensor([1, 5, 999])
+    cond = o.cond(lab)
+    x_ref = o.first_map(cond)
+    x = torch.zeros(2 * B, 1, C, device=DEV)
+    cuda_lib.first_map(cond.to(DEV), 2 * B, 1, C, sd["pos_start"].to(DEV), o.lvl_pos[0, :1].contiguous().to(DEV), x, 1, 0)
+    assert torch.allclose(x.cpu(), x_ref, atol=1e-6)
+    si = 3
+    nm = hashed("nm", 0, (B, 32, 4, 4), 1.0)
+    x_ref = o.embed_map(si, nm)
+    l = 16
+    # write at a token offset inside a wider buffer (verify-window layout)
+    x = torch.zeros(2 * B, 9 + l, C, device=DEV)
+    cuda_lib.embed_next_map(nm.to(DEV), B, l, 32, C, sd["word_embed.weight"].to(DEV), sd["word_embed.bias"].to(DEV),
+                            o.lvl_pos[0, o.begins[si]:o.ends[si]].contiguous().to(DEV), x, 9 + l, 9)
+    assert torch.allclose(x.cpu()[:, 9:], x_ref, atol=1e-5)
+    assert float(x[:, :9].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------- transformer pieces
+@pytest.mark.parametrize("M,C,tpi", [(7, 1024, 7), (130, 1920, 13), (64, 2304, 1)])
+def test_ln_modulate(cuda_lib, M, C, tpi):
+    imgs = (M + tpi - 1) // tpi
+    x = hashed("ln.x", 0, (M, C), 2.0) + 0.3
+    mod = hashed("ln.m", 0, (imgs, 6 * C), 0.5)
+    ref = torch.nn.functional.layer_norm(x, (C,), eps=1e-6) * (1 + mod[:, 2 * C:3 * C].repeat_interleave(tpi, 0)[:M]) \
+        + mod[:, 4 * C:5 * C].repeat_interleave(tpi, 0)[:M]
+    out = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    m = mod.to(DEV)
+    cuda_lib.ln_modulate(x.to(DEV), M, C, tpi, m.data_ptr() + 2 * C * 4, m.data_ptr() + 4 * C * 4, 6 * C, 1e-6, out)
+    # bf16 output: half an ulp of bf16 is 2^-9 relative
+    assert torch.allclose(out.float().cpu(), ref, rtol=2 ** -8, atol=1e-3)
+
+
+def _gemm_ref(A, W):
+    return A.float() @ W.float().t()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 512), (300, 1920, 1920), (1, 4096, 1024), (2048, 7680, 1920),
+                                   (4000, 1024, 4096)])
+def test_gemm_f32_bias(cuda_lib, M, N, K):
+    A = hashed("g.A", 0, (M, K), 1.0, dtype=torch.bfloat16)
+    W = hashed("g.W", 1, (N, K), 1.0 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = hashed("g.b", 2, (N,), 0.5)
+    ref = _gemm_ref(A, W) + bias
+    out = torch.full((M, N), float("nan"), device=DEV)
+    e = cuda_lib.GemmEpilogue(epilogue=cuda_lib.EPI_F32, bias=bias.to(DEV).data_ptr(), out_f32=out.data_ptr(), ldo=N)
+    b_dev = bias.to(DEV); e.bias = b_dev.data_ptr()
+    cuda_lib.gemm_bf16(A.to(DEV), K, W.to(DEV), K, M, N, K, e)
+    torch.cuda.synchronize()
+    # bf16 products are exact in fp32; only the accumulation order differs from the fp32 reference
+    assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_bf16_gelu_and_residual(cuda_lib):
+    M, N, K, tpi = 390, 512, 256, 13
+    imgs = M // tpi
+    A = hashed("g2.A", 0, (M, K), 1.0, dtype=torch.bfloat16)
+    W = hashed("g2.W", 1, (N, K), 1.0 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = hashed("g2.b", 2, (N,), 0.5)
+    acc = _gemm_ref(A, W) + bias
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), bias.to(DEV)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    cuda_lib.gemm_bf16(Ad, K, Wd, K, M, N, K, cuda_lib.GemmEpilogue(epilogue=cuda_lib.EPI_BF16, bias=bd.data_ptr(), out_bf16=out.data_ptr(), ldo=N))
+    assert torch.allclose(out.float().cpu(), acc, rtol=2 ** -8, atol=1e-3)
+    cuda_lib.gemm_bf16(Ad, K, Wd, K, M, N, K, cuda_lib.GemmEpilogue(epilogue=cuda_lib.EPI_GELU_BF16, bias=bd.data_ptr(), out_bf16=out.data_ptr(), ldo=N))
+    # tanh.approx.f32 has ~2^-11 relative error, below bf16 resolution
+    assert torch.allclose(out.float().cpu(), torch.nn.functional.gelu(acc, approximate="tanh"), rtol=2 ** -7, atol=2e-3)
+    gate = hashed("g2.g", 3, (imgs, 6 * N), 1.0)
+    x0 = hashed("g2.x", 4, (M, N), 1.0)
+    x = x0.to(DEV)
+    gd = gate.to(DEV)
+    cuda_lib.gemm_bf16(Ad, K, Wd, K, M, N, K, cuda_lib.GemmEpilogue(epilogue=cuda_lib.EPI_RESID_F32, bias=bd.data_ptr(), out_f32=x.data_ptr(), ldo=N,
+                                                                 gate=gd.data_ptr() + N * 4, ld_gate=6 * N, tokens_per_img=tpi))
+    ref = x0 + acc * gate[:, N:2 * N].repeat_interleave(tpi, 0)
+    assert torch.allclose(x.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+def _attn_case(cuda_lib, imgs, H, ls_window, kv_off, l2norm, seed):
+    """QKV epilogue + attention against a plain fp32 torch restatement of basic_var.py:93-117."""
+    C = H * 64
+    Lq = sum(ls_window)
+    seg = _seg(ls_window)
+    Lmax = kv_off + Lq + 3
+    Lmax_pad = (Lmax + 7) // 8 * 8
+    M = imgs * Lq
+    xm = hashed("a.x", seed, (M, C), 1.0, dtype=torch.bfloat16)
+    Wqkv = hashed("a.W", seed, (3 * C, C), 1.0 / math.sqrt(C), dtype=torch.bfloat16)
+    bias = hashed("a.b", seed, (3 * C,), 0.3); bias[C:2 * C] = 0
+    smul = math.log(4.0) + hashed("a.s", seed, (H,), 0.5); smul[0] = 6.0    # one head hits the clamp at log(100)
+    # prefix already in the cache
+    kpre = torch.nn.functional.normalize(hashed("a.kp", seed, (imgs, H, kv_off, 64), 1.0), dim=-1) if l2norm else hashed("a.kp", seed, (imgs, H, kv_off, 64), 1.0)
+    vpre = hashed("a.vp", seed, (imgs, H, kv_off, 64), 1.0)
+    kc = torch.zeros(imgs, H, Lmax, 64, dtype=torch.bfloat16, device=DEV)
+    vc = torch.zeros(imgs, H, 64, Lmax_pad, dtype=torch.bfloat16, device=DEV)
+    kc[:, :, :kv_off] = kpre.to(DEV).bfloat16()
+    vc[:, :, :, :kv_off] = vpre.transpose(2, 3).to(DEV).bfloat16()
+    q = torch.zeros(imgs, H, Lq, 64, dtype=torch.bfloat16, device=DEV)
+    bd, sd_ = bias.to(DEV), smul.to(DEV)
+    e = cuda_lib.GemmEpilogue(epilogue=cuda_lib.EPI_QKV, bias=bd.data_ptr(), q_out=q.data_ptr(), k_cache=kc.data_ptr(), vT_cache=vc.data_ptr(),
+                              scale_mul=sd_.data_ptr(), H=H, Lq=Lq, Lmax=Lmax, Lmax_pad=Lmax_pad, kv_off=kv_off, l2norm=int(l2norm))
+    cuda_lib.gemm_bf16(xm.to(DEV), C, Wqkv.to(DEV), C, M, 3 * C, C, e)
+    scale = 1.0 if l2norm else 0.25 / 8.0
+    out = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    cuda_lib.attention(q, kc, vc, imgs, H, Lq, Lmax, Lmax_pad, kv_off, seg, scale, out)
+    torch.cuda.synchronize()
+    # ---- reference ----
+    qkv = (_gemm_ref(xm, Wqkv) + bias).view(imgs, Lq, 3, H, 64).permute(2, 0, 3, 1, 4)
+    qr, kr, vr = qkv[0], qkv[1], qkv[2]
+    if l2norm:
+        qr = torch.nn.functional.normalize(qr, dim=-1) * smul.clamp_max(math.log(100)).exp().view(1, H, 1, 1)
+        kr = torch.nn.functional.normalize(kr, dim=-1)
+    assert torch.allclose(q.float().cpu(), qr, rtol=2 ** -7, atol=2e-3)
+    assert torch.allclose(kc[:, :, kv_off:kv_off + Lq].float().cpu(), kr, rtol=2 ** -7, atol=2e-3)
+    assert torch.allclose(vc[:, :, :, kv_off:kv_off + Lq].float().cpu(), vr.transpose(2, 3), rtol=2 ** -7, atol=2e-3)
+    # attention reference on the bf16-rounded q/k/v the kernel itself consumed
+    qb = q.float().cpu()
+    kb = kc[:, :, :kv_off + Lq].float().cpu()
+    vb = vc[:, :, :, :kv_off + Lq].float().cpu().transpose(2, 3)
+    stage_of_q = torch.repeat_interleave(torch.arange(len(ls_window)), torch.tensor(ls_window))
+    limit = kv_off + torch.tensor(seg[1:])[stage_of_q]
+    mask = torch.arange(kv_off + Lq).view(1, -1) < limit.view(-1, 1)
+    s = (qb @ kb.transpose(-1, -2)) * scale
+    s = s.masked_fill(~mask, float("-inf"))
+    ref = (s.softmax(-1) @ vb).transpose(1, 2).reshape(M, C)
+    # P is rounded to bf16 before P@V (rel 2^-9 per term) and the output is bf16
+    assert torch.allclose(out.float().cpu(), ref, rtol=2 ** -6, atol=4e-3), float((out.float().cpu() - ref).abs().max())
+
+
+@pytest.mark.parametrize("imgs,H,ls,kv_off,l2", [(2, 2, [1], 0, True), (4, 3, [16], 14, True), (2, 16, [169], 255, True),
+                                                 (2, 4, [256], 424, True), (3, 2, [100, 169], 155, True),
+                                                 (2, 2, [4, 9, 16, 25], 1, False), (2, 20, [36, 64], 55, True)])
+def test_qkv_epilogue_and_attention(cuda_lib, imgs, H, ls, kv_off, l2):
+    _attn_case(cuda_lib, imgs, H, ls, kv_off, l2, 0)
