@@ -48,8 +48,9 @@ int sdvar_num_sms(int device);
 
 /* ---- K3: fused logits epilogue --------------------------------------------------------------
  * replaces models/var.py:199-202 (CFG mix) + models/helpers.py:6-19 (sample_with_top_k_top_p_).
- * rows are (b,pos), b<B, pos<L; cond logits at row b*L+pos and uncond logits at row (B+b)*L+pos of
- * logits_2BLV (fp32, V % 1024 == 0, V <= 8192).  seg_begin_host[S+1] partitions [0,L) into stages;
+ * rows are (b,pos), b<B, pos<L; cond logits at row b*in_ld+in_off+pos and uncond logits at row
+ * (B+b)*in_ld+in_off+pos of logits_2BLV (fp32, V % 1024 == 0, V <= 8192): in_ld/in_off select one stage's slice
+ * of a multi-stage verify window (in_ld=L, in_off=0 for a dense (2B,L,V) tensor).  Outputs are dense (B,L,..).  seg_begin_host[S+1] partitions [0,L) into stages;
  * stage j uses t1[j]=fl32(1+t_j), t2[j]=fl32(t_j), t_j = cfg*si/(K-1):  x = cond*t1 - uncond*t2.
  * top_k<=0 disables top-k; one_minus_top_p<0 disables top-p (else it is fl32(1-top_p)).
  * noise (B*L,V) is the pre-drawn Exp(1) tensor torch.multinomial would draw; NULL => no sampling
@@ -57,7 +58,8 @@ int sdvar_num_sms(int device);
  * with removed entries set to -inf (the reference masks them in place); prob_out (B,L) the sampled
  * token's probability under the filtered distribution.  Arithmetic is bit-exact to
  * oracle/spec_c/sdvar_spec.c:sdvar_spec_sample. */
-int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L, int V, const int* seg_begin_host, int S,
+int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L, int in_ld, int in_off, int V,
+                               const int* seg_begin_host, int S,
                                const float* t1_host, const float* t2_host, int top_k, float one_minus_top_p,
                                const float* noise, long long* idx_out, float* mixed_out, float* prob_out,
                                void* stream);
@@ -187,7 +189,10 @@ typedef struct {
   int S;                    /* window stages */
   int seg_begin[SDVAR_MAX_SEG + 1];
   float* x;                 /* (imgs*Lq, C) fp32 residual stream, in/out */
-  const float* ada;         /* (depth, imgs, 6C) fp32: gamma1,gamma2,scale1,scale2,shift1,shift2 per block */
+  const float* ada;         /* adaLN rows [gamma1 gamma2 scale1 scale2 shift1 shift2] (6C fp32) of block i, image r at
+                               ada + i*ada_block_stride + r*ada_img_stride (strides in floats) */
+  long long ada_block_stride;
+  long long ada_img_stride;
   const float* head_mod;    /* (imgs, 2C) fp32: scale, shift of AdaLNBeforeHead */
   sdvar_bf16* k_cache[SDVAR_MAX_DEPTH];
   sdvar_bf16* vT_cache[SDVAR_MAX_DEPTH];

@@ -52,7 +52,8 @@ class VarWeights(C.Structure):
 class Pass(C.Structure):
     _fields_ = [("imgs", C.c_int), ("Lq", C.c_int), ("Lmax", C.c_int), ("Lmax_pad", C.c_int), ("kv_off", C.c_int),
                 ("S", C.c_int), ("seg_begin", C.c_int * (MAX_SEG + 1)),
-                ("x", C.c_void_p), ("ada", C.c_void_p), ("head_mod", C.c_void_p),
+                ("x", C.c_void_p), ("ada", C.c_void_p), ("ada_block_stride", C.c_longlong), ("ada_img_stride", C.c_longlong),
+                ("head_mod", C.c_void_p),
                 ("k_cache", C.c_void_p * MAX_DEPTH), ("vT_cache", C.c_void_p * MAX_DEPTH),
                 ("xm", C.c_void_p), ("q", C.c_void_p), ("attn", C.c_void_p), ("hidden", C.c_void_p), ("logits", C.c_void_p)]
 
@@ -103,8 +104,8 @@ def launch_count() -> int:
 
 # ---- thin typed wrappers (argument meaning: include/sdvar_b200.h) ---------------------------------
 def sample_cfg_topk_topp(logits_2BLV, B, L, V, seg_begin, t1, t2, top_k, one_minus_top_p, noise, idx_out, mixed_out,
-                         prob_out):
-    _check(lib().sdvar_sample_cfg_topk_topp(ptr(logits_2BLV), B, L, V, _iarr(seg_begin), len(seg_begin) - 1, _farr(t1),
+                         prob_out, in_ld=None, in_off=0):
+    _check(lib().sdvar_sample_cfg_topk_topp(ptr(logits_2BLV), B, L, L if in_ld is None else in_ld, in_off, V, _iarr(seg_begin), len(seg_begin) - 1, _farr(t1),
                                             _farr(t2), int(top_k), C.c_float(one_minus_top_p), ptr(noise), ptr(idx_out),
                                             ptr(mixed_out), ptr(prob_out), stream_ptr()), "sdvar_sample_cfg_topk_topp")
 

@@ -17,11 +17,12 @@ extern "C" int sdvar_var_forward(const sdvar_var_weights* w, const sdvar_pass* p
   SDVAR_REQUIRE(ps->imgs > 0 && ps->Lq > 0 && ps->S >= 1 && ps->S <= SDVAR_MAX_SEG, "bad pass geometry");
   SDVAR_REQUIRE(ps->x && ps->ada && ps->xm && ps->q && ps->attn && ps->hidden, "NULL pass buffer");
   const int C = w->C, M = ps->imgs * ps->Lq;
-  const size_t ada_stride = (size_t)ps->imgs * 6 * C;
+  const int ldm = (int)ps->ada_img_stride;
+  SDVAR_REQUIRE(ps->ada_img_stride >= 6 * C && ps->ada_img_stride % 4 == 0 && ps->ada_block_stride % 4 == 0, "bad adaLN strides");
   for (int i = 0; i < w->depth; ++i) {
-    const float* ada = ps->ada + (size_t)i * ada_stride;  // rows: [gamma1 gamma2 scale1 scale2 shift1 shift2]
+    const float* ada = ps->ada + (size_t)i * ps->ada_block_stride;  // rows: [gamma1 gamma2 scale1 scale2 shift1 shift2]
     int rc;
-    if ((rc = sdvar_ln_modulate(ps->x, M, C, ps->Lq, ada + 2 * C, ada + 4 * C, 6 * C, w->eps, ps->xm, stream))) return rc;
+    if ((rc = sdvar_ln_modulate(ps->x, M, C, ps->Lq, ada + 2 * C, ada + 4 * C, ldm, w->eps, ps->xm, stream))) return rc;
     sdvar_gemm_epilogue e{};
     e.epilogue = SDVAR_EPI_QKV;
     e.bias = w->b_qkv[i];
@@ -36,9 +37,9 @@ extern "C" int sdvar_var_forward(const sdvar_var_weights* w, const sdvar_pass* p
     r.epilogue = SDVAR_EPI_RESID_F32;
     r.bias = w->b_proj[i];
     r.out_f32 = ps->x; r.ldo = C;
-    r.gate = ada; r.ld_gate = 6 * C; r.tokens_per_img = ps->Lq;
+    r.gate = ada; r.ld_gate = ldm; r.tokens_per_img = ps->Lq;
     if ((rc = sdvar_gemm_bf16(ps->attn, C, w->w_proj[i], C, M, C, C, &r, stream))) return rc;
-    if ((rc = sdvar_ln_modulate(ps->x, M, C, ps->Lq, ada + 3 * C, ada + 5 * C, 6 * C, w->eps, ps->xm, stream))) return rc;
+    if ((rc = sdvar_ln_modulate(ps->x, M, C, ps->Lq, ada + 3 * C, ada + 5 * C, ldm, w->eps, ps->xm, stream))) return rc;
     sdvar_gemm_epilogue g{};
     g.epilogue = SDVAR_EPI_GELU_BF16;
     g.bias = w->b_fc1[i];

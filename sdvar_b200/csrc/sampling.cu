@@ -118,7 +118,7 @@ __device__ __forceinline__ unsigned long long pack_best(float r, int idx) {
 // ================================================================================================
 template <int NV>
 __global__ void __launch_bounds__(kThreads, 2)
-k3_sample_kernel(const float* __restrict__ logits, int B, int L, SegTable seg, int top_k, float thr,
+k3_sample_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int in_off, SegTable seg, int top_k, float thr,
                  const float* __restrict__ noise, long long* __restrict__ idx_out, float* __restrict__ mixed_out,
                  float* __restrict__ prob_out) {
   constexpr int V = NV * 1024;
@@ -131,8 +131,8 @@ k3_sample_kernel(const float* __restrict__ logits, int B, int L, SegTable seg, i
     const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
     const int j = seg_of(seg, pos);
     const float t1 = seg.t1[j], t2 = seg.t2[j];
-    const float4* pc = reinterpret_cast<const float4*>(logits + row * V);
-    const float4* pu = reinterpret_cast<const float4*>(logits + ((long long)(B + b) * L + pos) * V);
+    const float4* pc = reinterpret_cast<const float4*>(logits + ((long long)b * in_ld + in_off + pos) * V);
+    const float4* pu = reinterpret_cast<const float4*>(logits + ((long long)(B + b) * in_ld + in_off + pos) * V);
     float x[E];
     uint32_t key[E];
     {
@@ -451,12 +451,14 @@ static int row_grid(long long rows, int blocks_per_sm) {
 
 using namespace sdvar;
 
-extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L, int V, const int* seg_begin_host, int S,
+extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L, int in_ld, int in_off, int V,
+                                          const int* seg_begin_host, int S,
                                           const float* t1_host, const float* t2_host, int top_k, float one_minus_top_p,
                                           const float* noise, long long* idx_out, float* mixed_out, float* prob_out,
                                           void* stream) {
   if (int rc = check_arch()) return rc;
   SDVAR_REQUIRE(logits_2BLV && B > 0 && L > 0, "bad logits/B/L");
+  SDVAR_REQUIRE(in_off >= 0 && in_ld >= in_off + L, "bad row mapping in_ld=%d in_off=%d L=%d", in_ld, in_off, L);
   SDVAR_REQUIRE(V % 1024 == 0 && V >= 1024 && V <= 8192, "V=%d must be a multiple of 1024 in [1024,8192]", V);
   SDVAR_REQUIRE(((uintptr_t)logits_2BLV & 15) == 0 && ((uintptr_t)noise & 15) == 0 && ((uintptr_t)mixed_out & 15) == 0,
                 "row pointers must be 16-byte aligned");
@@ -468,7 +470,7 @@ extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L
   cudaStream_t st = (cudaStream_t)stream;
 #define SDVAR_K3(NV)                                                                                          \
   case NV:                                                                                                    \
-    k3_sample_kernel<NV><<<grid, kThreads, 0, st>>>(logits_2BLV, B, L, seg, top_k, one_minus_top_p, noise,   \
+    k3_sample_kernel<NV><<<grid, kThreads, 0, st>>>(logits_2BLV, B, L, in_ld, in_off, seg, top_k, one_minus_top_p, noise,   \
                                                     idx_out, mixed_out, prob_out);                           \
     break;
   switch (V / 1024) {

@@ -1,0 +1,512 @@
+"""VAR and SDVAR with the reference's Python API (reference models/var.py), executed by libsdvar_b200.
+
+* ``VAR`` keeps the reference's constructor, parameter names/shapes (``var_d*.pth`` loads with
+  ``strict=True``), ``autoregressive_infer_cfg`` (models/var.py:128-215), ``forward`` (:217-259) and
+  ``get_logits`` (:119-125).  The modules below only HOLD parameters; all arithmetic is done by the CUDA
+  engine (``sdvar_b200.engine.VarEngine``).  There is no CPU path: calling inference on a CPU model raises.
+* ``SDVAR`` keeps ``sdvar_autoregressive_infer_cfg_parallel_v1`` (:1285-1383), ``..._sd_test3`` (:605-865) and
+  the step methods (:871-1282), with the reference's defects D1-D11 resolved as specified in
+  DESIGN.md "loop spec".  The reference's top-1/50% rule is kept as ``accept_rule='reference'``; the
+  north-star rule ``u < min(1, p/q)`` + residual resample is ``accept_rule='speculative'`` (default).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _cabi
+from ..engine import DeviceNoise, SingleGeneratorNoise, VarEngine
+from .vqvae import VQVAE
+from .quant import VectorQuantizer2
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameter holders (names = checkpoint surface)
+# ---------------------------------------------------------------------------------------------------
+class _AttnParams(nn.Module):
+    def __init__(self, C: int, H: int, l2: bool):
+        super().__init__()
+        if l2:
+            self.scale_mul_1H11 = nn.Parameter(torch.full((1, H, 1, 1), 4.0).log())
+        self.mat_qkv = nn.Linear(C, 3 * C, bias=False)
+        self.q_bias, self.v_bias = nn.Parameter(torch.zeros(C)), nn.Parameter(torch.zeros(C))
+        self.register_buffer("zero_k_bias", torch.zeros(C))
+        self.proj = nn.Linear(C, C)
+
+
+class _FfnParams(nn.Module):
+    def __init__(self, C: int, hidden: int):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(C, hidden), nn.Linear(hidden, C)
+
+
+class _BlockParams(nn.Module):
+    def __init__(self, C: int, D: int, H: int, mlp_ratio: float, shared_aln: bool, l2: bool):
+        super().__init__()
+        self.attn = _AttnParams(C, H, l2)
+        self.ffn = _FfnParams(C, round(C * mlp_ratio))
+        self.shared_aln = shared_aln
+        if shared_aln:
+            self.ada_gss = nn.Parameter(torch.randn(1, 1, 6, C) / C ** 0.5)
+        else:
+            self.ada_lin = nn.Sequential(nn.SiLU(), nn.Linear(D, 6 * C))
+
+
+class _HeadNorm(nn.Module):
+    def __init__(self, C: int, D: int):
+        super().__init__()
+        self.ada_lin = nn.Sequential(nn.SiLU(), nn.Linear(D, 2 * C))
+
+
+def _trunc(t: torch.Tensor, std: float):
+    nn.init.trunc_normal_(t, mean=0.0, std=std)
+
+
+class VAR(nn.Module):
+    def __init__(self, vae_local: VQVAE, num_classes=1000, depth=16, embed_dim=1024, num_heads=16, mlp_ratio=4.0,
+                 drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0, norm_eps=1e-6, shared_aln=False, cond_drop_rate=0.1,
+                 attn_l2_norm=False, patch_nums=(1, 2, 3, 4, 5, 6, 8, 10, 13, 16), flash_if_available=True,
+                 fused_if_available=True):
+        super().__init__()
+        assert embed_dim % num_heads == 0 and embed_dim // num_heads == 64, "the attention kernel is built for head_dim 64"
+        assert mlp_ratio == 4.0
+        self.Cvae, self.V = vae_local.Cvae, vae_local.vocab_size
+        self.depth, self.C, self.D, self.num_heads = depth, embed_dim, embed_dim, num_heads
+        self.cond_drop_rate, self.norm_eps = cond_drop_rate, norm_eps
+        self.shared_aln, self.attn_l2_norm = shared_aln, attn_l2_norm
+        self.prog_si = -1
+        self.patch_nums: Tuple[int, ...] = tuple(patch_nums)
+        self.ls = [pn * pn for pn in self.patch_nums]
+        self.ends = [int(e) for e in np.cumsum(self.ls)]
+        self.begins = [0] + self.ends[:-1]
+        self.begin_ends = list(zip(self.begins, self.ends))
+        self.L, self.first_l = self.ends[-1], self.ls[0]
+        self.num_stages_minus_1 = len(self.patch_nums) - 1
+        self.num_classes = num_classes
+        self.rng: Optional[torch.Generator] = None   # created on the model's device on first use (var.py:50)
+        # the VQVAE is deliberately kept out of .modules()/.state_dict(), like the reference's tuple proxy (var.py:54-55)
+        self.vae_proxy: Tuple[VQVAE] = (vae_local,)
+        self.vae_quant_proxy: Tuple[VectorQuantizer2] = (vae_local.quantize,)
+
+        init_std = math.sqrt(1 / self.C / 3)
+        self.word_embed = nn.Linear(self.Cvae, self.C)
+        self.class_emb = nn.Embedding(num_classes + 1, self.C)
+        self.pos_start = nn.Parameter(torch.empty(1, self.first_l, self.C))
+        self.pos_1LC = nn.Parameter(torch.empty(1, self.L, self.C))
+        self.lvl_embed = nn.Embedding(len(self.patch_nums), self.C)
+        for t in (self.class_emb.weight, self.pos_start, self.pos_1LC, self.lvl_embed.weight):
+            _trunc(t.data, init_std)
+        if shared_aln:
+            self.shared_ada_lin = nn.Sequential(nn.SiLU(), nn.Linear(self.D, 6 * self.C))
+        else:
+            self.shared_ada_lin = nn.Identity()
+        self.blocks = nn.ModuleList([_BlockParams(self.C, self.D, num_heads, mlp_ratio, shared_aln, attn_l2_norm) for _ in range(depth)])
+        lvl = torch.cat([torch.full((l,), i, dtype=torch.int64) for i, l in enumerate(self.ls)]).view(1, self.L)
+        self.register_buffer("lvl_1L", lvl)
+        d = lvl.view(1, self.L, 1)
+        # kept only because it is part of the checkpoint surface; the kernels take the stage table instead
+        self.register_buffer("attn_bias_for_masking", torch.where(d >= d.transpose(1, 2), 0.0, -torch.inf).reshape(1, 1, self.L, self.L).contiguous())
+        self.head_nm = _HeadNorm(self.C, self.D)
+        self.head = nn.Linear(self.C, self.V)
+        self._engine = VarEngine(self)
+
+    # ------------------------------------------------------------------ init (models/var.py:261-311)
+    def init_weights(self, init_adaln=0.5, init_adaln_gamma=1e-5, init_head=0.02, init_std=0.02, conv_std_or_gain=0.02):
+        if init_std < 0:
+            init_std = (1 / self.C / 3) ** 0.5
+        for mod in self.modules():
+            if isinstance(mod, nn.Linear):
+                _trunc(mod.weight.data, init_std)
+                if mod.bias is not None:
+                    mod.bias.data.zero_()
+            elif isinstance(mod, nn.Embedding):
+                _trunc(mod.weight.data, init_std)
+        if init_head >= 0:
+            self.head.weight.data.mul_(init_head)
+            self.head.bias.data.zero_()
+        self.head_nm.ada_lin[-1].weight.data.mul_(init_adaln)
+        self.head_nm.ada_lin[-1].bias.data.zero_()
+        for blk in self.blocks:
+            blk.attn.proj.weight.data.div_(math.sqrt(2 * self.depth))
+            blk.ffn.fc2.weight.data.div_(math.sqrt(2 * self.depth))
+            if self.shared_aln:
+                blk.ada_gss.data[:, :, 2:].mul_(init_adaln)
+                blk.ada_gss.data[:, :, :2].mul_(init_adaln_gamma)
+            else:
+                blk.ada_lin[-1].weight.data[2 * self.C:].mul_(init_adaln)
+                blk.ada_lin[-1].weight.data[:2 * self.C].mul_(init_adaln_gamma)
+                blk.ada_lin[-1].bias.data.zero_()
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def device(self):
+        return self.pos_1LC.device
+
+    def _rng(self, g_seed: Optional[int]) -> Optional[torch.Generator]:
+        if g_seed is None:
+            return None
+        if self.rng is None or self.rng.device != self.device:
+            self.rng = torch.Generator(device=self.device)
+        self.rng.manual_seed(g_seed)
+        return self.rng
+
+    def _labels(self, B: int, label_B, rng) -> torch.Tensor:
+        """models/var.py:147-150"""
+        if label_B is None:
+            prob = torch.full((1, self.num_classes), 1.0 / self.num_classes, device=self.device)
+            return torch.multinomial(prob, num_samples=B, replacement=True, generator=rng).reshape(B)
+        if isinstance(label_B, int):
+            return torch.full((B,), self.num_classes if label_B < 0 else label_B, device=self.device, dtype=torch.int64)
+        return label_B.to(self.device)
+
+    def _cfg_scalars(self, cfg: float, stages: Sequence[int]):
+        K1 = self.num_stages_minus_1
+        t = [cfg * (si / K1) for si in stages]
+        return [float(np.float32(1 + x)) for x in t], [float(np.float32(x)) for x in t]
+
+    def _sample_stage(self, logits_2BLV, B, si, cfg, top_k, top_p, noise, in_ld=None, in_off=0, want_mixed=False):
+        """K3 on one stage: returns (idx (B,l) int64 or None, mixed (B,l,V) or None)."""
+        l, V = self.ls[si], self.V
+        t1, t2 = self._cfg_scalars(cfg, [si])
+        idx = torch.empty(B, l, dtype=torch.int64, device=self.device) if noise is not None else None
+        mixed = torch.empty(B, l, V, dtype=torch.float32, device=self.device) if want_mixed else None
+        thr = float(np.float32(1.0 - top_p)) if top_p > 0 else -1.0
+        _cabi.sample_cfg_topk_topp(logits_2BLV, B, l, V, [0, l], t1, t2, top_k, thr, noise, idx, mixed, None, in_ld=in_ld, in_off=in_off)
+        return idx, mixed
+
+    def get_logits(self, h_BLC: torch.Tensor, cond_BD: torch.Tensor) -> torch.Tensor:
+        """head(head_nm(h, cond)) in fp32 out (models/var.py:119-125): LN-modulate kernel + tcgen05 GEMM."""
+        e = self._engine
+        e.pack()
+        n, L, C = h_BLC.shape
+        silu = torch.empty(n, C, dtype=torch.bfloat16, device=self.device)
+        _cabi.silu_bf16(cond_BD.float().contiguous(), silu)
+        mod = torch.empty(n, 2 * C, device=self.device)
+        E = _cabi.GemmEpilogue
+        _cabi.gemm_bf16(silu, C, e.w_headnm, C, n, 2 * C, C, E(epilogue=_cabi.EPI_F32, bias=e.b_headnm.data_ptr(), out_f32=mod.data_ptr(), ldo=2 * C))
+        xm = torch.empty(n * L, C, dtype=torch.bfloat16, device=self.device)
+        _cabi.ln_modulate(h_BLC.float().contiguous().view(n * L, C), n * L, C, L, mod.data_ptr(), mod.data_ptr() + 4 * C, 2 * C, self.norm_eps, xm)
+        out = torch.empty(n * L, self.V, device=self.device)
+        _cabi.gemm_bf16(xm, C, e.w_head, C, n * L, self.V, C, E(epilogue=_cabi.EPI_F32, bias=e.b_head.data_ptr(), out_f32=out.data_ptr(), ldo=self.V))
+        return out.view(n, L, self.V)
+
+    # ------------------------------------------------------------------ baseline loop (models/var.py:128-215)
+    @torch.no_grad()
+    def autoregressive_infer_cfg(self, B: int, label_B: Optional[Union[int, torch.LongTensor]], g_seed: Optional[int] = None,
+                                 cfg=1.5, top_k=0, top_p=0.0, more_smooth=False, noise=None, return_tokens=False,
+                                 record: Optional[dict] = None) -> torch.Tensor:
+        """Returns the reconstructed image (B,3,H,W) in [0,1].  ``noise`` (optional) is a provider object with
+        ``exponential(stream, rows, V)`` used by parity tests to inject pre-drawn Exp(1) noise; by default the
+        model's generator is used exactly as torch.multinomial would use it."""
+        rng = self._rng(g_seed)
+        label_B = self._labels(B, label_B, rng)
+        noise = noise or SingleGeneratorNoise(rng, self.device)
+        vq, e = self.vae_quant_proxy[0], self._engine
+        e.begin(B, label_B)
+        K = len(self.patch_nums)
+        f_hat = torch.zeros(B, self.Cvae, self.patch_nums[-1], self.patch_nums[-1], device=self.device)
+        next_map, idxs = None, []
+        for si in range(K):
+            l = self.ls[si]
+            if si == 0:
+                e.put_first_map(l)
+            else:
+                e.put_embed_map(si, next_map, l)
+            logits = e.forward([si])
+            n = noise.exponential("target", B * l, self.V)
+            if record is not None:
+                record.setdefault("logits", []).append(logits.clone()); record.setdefault("noise", []).append(n)
+            if not more_smooth:
+                idx, _ = self._sample_stage(logits, B, si, cfg, top_k, top_p, n)
+                f_hat, next_map = vq.next_input_from_idx(si, f_hat, idx)
+            else:  # visualisation-only branch (models/var.py:206-208), torch ops on the kernel's filtered logits
+                idx, mixed = self._sample_stage(logits, B, si, cfg, top_k, top_p, n, want_mixed=True)
+                ratio = si / self.num_stages_minus_1
+                gum = -torch.empty_like(mixed).exponential_(generator=rng).log()
+                y = ((mixed * (1 + ratio) + gum) / max(0.27 * (1 - ratio * 0.95), 0.005)).softmax(-1)
+                h = (y @ vq.embedding.weight.unsqueeze(0)).transpose(1, 2).reshape(B, self.Cvae, self.patch_nums[si], self.patch_nums[si])
+                f_hat, next_map = vq.get_next_autoregressive_input(si, K, f_hat, h.contiguous())
+            idxs.append(idx)
+        img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5)
+        return (img, idxs, f_hat) if return_tokens else img
+
+    # ------------------------------------------------------------------ teacher-forced (models/var.py:217-259)
+    @torch.no_grad()
+    def forward(self, label_B: torch.LongTensor, x_BLCv_wo_first_l: torch.Tensor) -> torch.Tensor:
+        """All-stage block-causal pass; returns logits (B, L, V).  Runs as one verify-style window over every stage.
+        The reference drops labels at cond_drop_rate even in eval (var.py:226, not gated on training); training is
+        out of scope here, so no label is dropped."""
+        B = x_BLCv_wo_first_l.shape[0]
+        e = self._engine
+        e.begin(B, label_B, max_window_tokens=self.L)
+        K = len(self.patch_nums)
+        e.put_first_map(self.L, 0)
+        for si in range(1, K):
+            nm = x_BLCv_wo_first_l[:, self.begins[si] - self.first_l:self.ends[si] - self.first_l].float().transpose(1, 2).contiguous()
+            e.put_embed_map(si, nm, self.L, self.begins[si])
+        logits = e.forward(list(range(K)))
+        return logits[:B].clone()
+
+
+# ---------------------------------------------------------------------------------------------------
+class SDVARInferenceState:
+    """State of one speculative generation (reference: inner class at models/var.py:912-945)."""
+
+    def __init__(self, B, gamma, patch_nums, cfg, noise):
+        self.B, self.gamma, self.patch_nums, self.cfg, self.noise = B, gamma, patch_nums, cfg, noise
+        self.current_stage, self.total_stages = 0, len(patch_nums)
+        self.accept_count = self.reject_count = self.target_calls = self.draft_stage_calls = self.rounds = 0
+        self.top_k, self.top_p, self.more_smooth = 0, 0.0, False
+        self.f_hat = None             # accepted f_hat (B,Cvae,HW,HW)
+        self.next_map = None          # accepted stage input for current_stage (None for stage 0)
+        self.final_idx: List[torch.Tensor] = []
+        # per-round scratch
+        self.maps, self.snaps, self.mixed_d, self.out_idx = [], [], [], []
+        self.advance: List[int] = []
+        self.stage_tokens = [0] * len(patch_nums)
+        self.stage_accept_tokens = [0] * len(patch_nums)
+
+    # reference-compatible aliases
+    @property
+    def draft_f_hat(self):
+        return self.f_hat
+
+    @property
+    def target_f_hat(self):
+        return self.f_hat
+
+    def stats(self) -> dict:
+        acc = sum(self.stage_accept_tokens)
+        return dict(rounds=self.rounds, target_passes=self.target_calls, draft_stages=self.draft_stage_calls,
+                    accepted_tokens=acc, rejected_tokens=sum(self.stage_tokens) - acc, advance=list(self.advance),
+                    stage_accept_tokens=list(self.stage_accept_tokens), stage_tokens=list(self.stage_tokens))
+
+
+class SDVAR(nn.Module):
+    def __init__(self, draft_model: VAR, target_model: VAR, similarity_thresh: float = 0.8):
+        super().__init__()
+        self.draft_model, self.target_model, self.similarity_thresh = draft_model, target_model, similarity_thresh
+        assert draft_model.patch_nums == target_model.patch_nums, "draft and target must share the token pyramid"
+        # The reference precomputes two dense LxL masks with O(L^2) python loops here (var.py:548-578, ~7 s) and
+        # hard-codes the 256 px pyramid (D11).  The kernels take the stage table of whichever pyramid the models use.
+        self.last_stats: Optional[dict] = None
+
+    # models/var.py:580-601
+    def init_param(self, model: VAR, B: int, label_B):
+        e = model._engine
+        e.pack()
+        sos = cond_BD = e.class_emb[torch.cat((label_B, torch.full_like(label_B, model.num_classes)), dim=0)]
+        lvl_pos = e.lvl_pos.unsqueeze(0)
+        first_token_map = sos.unsqueeze(1).expand(2 * B, model.first_l, -1) + e.pos_start.unsqueeze(0) + lvl_pos[:, :model.first_l]
+        first_f_hat = sos.new_zeros(B, model.Cvae, model.patch_nums[-1], model.patch_nums[-1])
+        return sos, cond_BD, cond_BD, lvl_pos, first_token_map, first_f_hat
+
+    # ------------------------------------------------------------------ hand-over variant (models/var.py:605-865)
+    @torch.no_grad()
+    def sdvar_autoregressive_infer_cfg_sd_test3(self, B: int, label_B, g_seed: Optional[int] = None, cfg: float = 1.5,
+                                                top_k: int = 0, top_p: float = 0.0, more_smooth: bool = False,
+                                                entry_num: int = 10, sd_mask: int = 0, noise=None, return_tokens=False):
+        """Draft runs stages [0,entry_num), the target runs [entry_num,K) from the draft's f_hat.  With sd_mask=0 the
+        target starts with an EMPTY KV cache and never sees the drafted prefix (var.py:817-825) -- reproduced as is.
+        sd_mask 1..5 run the prefix through the blocks and then discard the result (var.py:809-811); that branch has
+        no defined semantics and is refused."""
+        if sd_mask != 0:
+            raise NotImplementedError("sd_mask != 0 discards the masked pass in the reference (models/var.py:809-811); not supported")
+        assert not more_smooth, "more_smooth is only wired into autoregressive_infer_cfg"
+        D, T = self.draft_model, self.target_model
+        rng = T._rng(g_seed)
+        label_B = T._labels(B, label_B, rng)
+        noise = noise or SingleGeneratorNoise(rng, T.device)
+        vq = T.vae_quant_proxy[0]
+        K = len(T.patch_nums)
+        f_hat = torch.zeros(B, T.Cvae, T.patch_nums[-1], T.patch_nums[-1], device=T.device)
+        next_map, idxs = None, []
+        for model, lo, hi in ((D, 0, min(entry_num, K)), (T, min(entry_num, K), K)):
+            if lo >= hi:
+                continue
+            e = model._engine
+            e.begin(B, label_B)
+            for si in range(lo, hi):
+                l = model.ls[si]
+                e.put_first_map(l) if si == 0 else e.put_embed_map(si, next_map, l)
+                logits = e.forward([si], check_position=False)
+                idx, _ = model._sample_stage(logits, B, si, cfg, top_k, top_p, noise.exponential("target", B * l, model.V))
+                f_hat, next_map = vq.next_input_from_idx(si, f_hat, idx)
+                idxs.append(idx)
+        img = T.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5)
+        return (img, idxs, f_hat) if return_tokens else img
+
+    # ------------------------------------------------------------------ draft -> verify loop (models/var.py:871-1383)
+    def _initialize_inference_state(self, B: int, label_B, g_seed: Optional[int], cfg: float, gamma: int, noise=None):
+        D, T = self.draft_model, self.target_model
+        rng = T._rng(g_seed)
+        label_B = T._labels(B, label_B, rng)
+        state = SDVARInferenceState(B, gamma, T.patch_nums, cfg, noise or DeviceNoise(g_seed, T.device))
+        state.label_B = label_B
+        K = len(T.patch_nums)
+        win = max(sum(T.ls[s:s + gamma]) for s in range(K))
+        D._engine.begin(B, label_B)
+        T._engine.begin(B, label_B, max_window_tokens=win)
+        state.f_hat = torch.zeros(B, T.Cvae, T.patch_nums[-1], T.patch_nums[-1], device=T.device)
+        dev = T.device
+        state.ws = torch.zeros(4, dtype=torch.int32, device=dev)
+        return state
+
+    def draft_generate_batch(self, state: SDVARInferenceState, B: int) -> List[torch.Tensor]:
+        """Draft g = min(gamma, K - stage) stages incrementally (models/var.py:949-1024).  Each stage's input is
+        area_down(f_hat) of the previous DRAFTED stage (fixes D2), stage 0 is the sos map (D3); the draft's masked
+        mixed logits, f_hat snapshots and next maps are kept for verification and rollback."""
+        D = self.draft_model
+        e, vq = D._engine, D.vae_quant_proxy[0]
+        g = min(state.gamma, state.total_stages - state.current_stage)
+        state.maps, state.snaps, state.mixed_d, draft_tokens = [state.next_map], [], [], []
+        if g <= 0:
+            return draft_tokens
+        fh = state.f_hat.clone()
+        for j in range(g):
+            si = state.current_stage + j
+            l = D.ls[si]
+            e.put_first_map(l) if si == 0 else e.put_embed_map(si, state.maps[j], l)
+            logits = e.forward([si])
+            n = state.noise.exponential("draft", B * l, D.V)
+            idx, mixed = D._sample_stage(logits, B, si, state.cfg, state.top_k, state.top_p, n, want_mixed=True)
+            fh, nm = vq.next_input_from_idx(si, fh, idx)
+            draft_tokens.append(idx); state.mixed_d.append(mixed); state.snaps.append(fh.clone())
+            state.maps.append(nm if si != state.total_stages - 1 else None)
+            state.draft_stage_calls += 1
+        return draft_tokens
+
+    def target_verify_batch(self, draft_tokens: List[torch.Tensor], state: SDVARInferenceState, B: int):
+        """ONE block-causal target pass over the g drafted stages on top of the KV cache of accepted stages
+        (models/var.py:1026-1158 intent; fixes D1,D5,D6): returns ([mixed+filtered target logits (B,l,V) per stage], g)."""
+        if not draft_tokens:
+            return [], 0
+        T = self.target_model
+        e = T._engine
+        g = len(draft_tokens)
+        stages = list(range(state.current_stage, state.current_stage + g))
+        Lw = sum(T.ls[s] for s in stages)
+        off = 0
+        for j, si in enumerate(stages):
+            e.put_first_map(Lw, off) if si == 0 else e.put_embed_map(si, state.maps[j], Lw, off)
+            off += T.ls[si]
+        logits = e.forward(stages)
+        state.target_calls += 1
+        out, off = [], 0
+        for si in stages:
+            _, mixed = T._sample_stage(logits, B, si, state.cfg, state.top_k, state.top_p, None, in_ld=Lw, in_off=off, want_mixed=True)
+            out.append(mixed)
+            off += T.ls[si]
+        return out, g
+
+    def speculative_token_matching(self, draft_tokens, target_logits, state: SDVARInferenceState, B: int) -> int:
+        """K4 per stage: accept u*q[d] < p[d], residual resample on reject, first-reject scan.  Returns the number of
+        stages to commit: a = min(#leading stages with no reject in any image + 1, g); the last committed stage keeps the
+        accepted draft tokens plus the target's repairs."""
+        T = self.target_model
+        g, dev = len(draft_tokens), T.device
+        summ = torch.empty(g, 4, dtype=torch.int32, device=dev)
+        state.out_idx = []
+        for j in range(g):
+            l = T.ls[state.current_stage + j]
+            u = state.noise.uniform("u", B * l)
+            nr = state.noise.exponential("resample", B * l, T.V)
+            out = torch.empty(B, l, dtype=torch.int64, device=dev)
+            acc = torch.empty(B, l, dtype=torch.uint8, device=dev)
+            fr = torch.empty(B, 1, dtype=torch.int32, device=dev); na = torch.empty(B, 1, dtype=torch.int32, device=dev)
+            st = torch.empty(B, dtype=torch.int32, device=dev)
+            _cabi.verify_accept_resample(target_logits[j], state.mixed_d[j], draft_tokens[j], u, nr, B, l, T.V, [0, l], out, acc,
+                                         None, None, fr, na, st, summ[j], state.ws)
+            state.out_idx.append(out)
+        s = summ.cpu()      # the one host sync of the round
+        n_ok = 0
+        for j in range(g):   # stages after the first failing one were conditioned on unrepaired tokens: not counted
+            si = state.current_stage + j
+            state.stage_tokens[si] += B * T.ls[si]
+            state.stage_accept_tokens[si] += int(s[j, 1])
+            if int(s[j, 2]) != 0:
+                break
+            n_ok += 1
+        return min(n_ok + 1, g)
+
+    def basic_token_matching(self, draft_tokens, target_logits, state: SDVARInferenceState, B: int) -> int:
+        """Reference rule (models/var.py:1160-1227): stage accepted iff the batch-mean top-1 match rate >= 0.5, stop at
+        the first rejected stage.  Departure (D8): the rejected stage is repaired by sampling it from the target's
+        distribution instead of breaking out of the loop with a truncated image."""
+        T = self.target_model
+        g, dev = len(draft_tokens), T.device
+        nm = torch.empty(g, B, dtype=torch.int32, device=dev)
+        for j in range(g):
+            l = T.ls[state.current_stage + j]
+            match = torch.empty(B, l, dtype=torch.uint8, device=dev)
+            _cabi.verify_top1(target_logits[j], draft_tokens[j], B, l, T.V, [0, l], match, nm[j].view(B, 1))
+        counts = nm.cpu().sum(dim=1).tolist()
+        n_ok, state.out_idx = 0, []
+        for j in range(g):
+            si = state.current_stage + j
+            l = T.ls[si]
+            rate = counts[j] / float(B * l)
+            if j == n_ok:
+                state.stage_tokens[si] += B * l
+                if rate >= 0.5:
+                    n_ok += 1
+                    state.stage_accept_tokens[si] += counts[j]
+        for j in range(g):
+            l = T.ls[state.current_stage + j]
+            u = state.noise.uniform("u", B * l)                      # drawn to keep the stream positions rule-independent
+            nr = state.noise.exponential("resample", B * l, T.V)
+            if j < n_ok:
+                state.out_idx.append(draft_tokens[j])
+            else:
+                # target_logits[j] is already mixed+filtered: sample it with K3 as x = x*1 - 0*0
+                out = torch.empty(B, l, dtype=torch.int64, device=dev)
+                both = torch.cat((target_logits[j], torch.zeros_like(target_logits[j])), 0)
+                _cabi.sample_cfg_topk_topp(both, B, l, T.V, [0, l], [1.0], [0.0], 0, -1.0, nr, out, None, None)
+                state.out_idx.append(out)
+        return min(n_ok + 1, g)
+
+    def update_state_with_accepted_tokens(self, draft_tokens, accept_length: int, state: SDVARInferenceState, B: int):
+        """Commit ``accept_length`` stages (models/var.py:1245-1282): f_hat = snapshot after the last unmodified stage +
+        the final tokens of the last committed stage (fixes the double add D7); both KV caches roll back to the end of
+        the last committed stage (D4)."""
+        if accept_length <= 0:
+            return
+        T, D = self.target_model, self.draft_model
+        vq = T.vae_quant_proxy[0]
+        s, a = state.current_stage, accept_length
+        for j in range(a - 1):
+            state.final_idx.append(draft_tokens[j])
+        state.final_idx.append(state.out_idx[a - 1])
+        base = state.snaps[a - 2].clone() if a >= 2 else state.f_hat
+        state.f_hat, nm = vq.next_input_from_idx(s + a - 1, base, state.out_idx[a - 1])
+        state.next_map = nm if s + a < state.total_stages else None
+        D._engine.kv_truncate(D.ends[s + a - 1])
+        T._engine.kv_truncate(T.ends[s + a - 1])
+
+    @torch.no_grad()
+    def sdvar_autoregressive_infer_cfg_parallel_v1(self, B: int, label_B=None, g_seed: Optional[int] = None, cfg: float = 1.5,
+                                                   gamma: int = 2, top_k: int = 0, top_p: float = 0.0, more_smooth: bool = False,
+                                                   accept_rule: str = "speculative", noise=None, return_tokens: bool = False):
+        """while stage < K: draft g stages -> one target pass -> verify -> commit a prefix (models/var.py:1285-1383).
+        Returns the image (B,3,H,W) in [0,1]; acceptance statistics are left in ``self.last_stats``."""
+        assert not more_smooth, "more_smooth is only wired into autoregressive_infer_cfg"
+        assert accept_rule in ("speculative", "reference")
+        state = self._initialize_inference_state(B, label_B, g_seed, cfg, gamma, noise)
+        state.top_k, state.top_p, state.more_smooth = top_k, top_p, more_smooth
+        match = self.speculative_token_matching if accept_rule == "speculative" else self.basic_token_matching
+        while state.current_stage < state.total_stages:
+            draft_tokens = self.draft_generate_batch(state, B)
+            target_logits, _ = self.target_verify_batch(draft_tokens, state, B)
+            accept_length = match(draft_tokens, target_logits, state, B)
+            self.update_state_with_accepted_tokens(draft_tokens, accept_length, state, B)
+            state.accept_count += accept_length
+            state.current_stage += accept_length
+            state.rounds += 1
+            state.advance.append(accept_length)
+        self.last_stats = state.stats()
+        img = self.target_model.vae_proxy[0].fhat_to_img(state.f_hat).add_(1).mul_(0.5)
+        return (img, state.final_idx, state.f_hat) if return_tokens else img

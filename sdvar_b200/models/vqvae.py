@@ -1,0 +1,168 @@
+"""VQVAE, inference side: quantizer (K5 kernels) + decoder.
+
+The decoder (``fhat_to_img``, reference models/vqvae.py:62-63 + models/basic_vae.py:163-226) is NOT one of the
+four north-star kernel families; it is the boundary right after the path and runs here through
+PyTorch/cuDNN in bf16 channels-last as library code.  Parameter names follow the reference checkpoint
+(``decoder.*``, ``post_quant_conv.*``, ``quantize.*``); encode-side tensors (``encoder.*``, ``quant_conv.*``) of a
+real ``vae_ch160v4096z32.pth`` are accepted and ignored by ``load_state_dict``.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .quant import VectorQuantizer2
+
+
+def _gn(c: int) -> nn.GroupNorm:
+    return nn.GroupNorm(32, c, eps=1e-6, affine=True)
+
+
+class _Res(nn.Module):
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.norm1, self.conv1 = _gn(cin), nn.Conv2d(cin, cout, 3, padding=1)
+        self.norm2, self.conv2 = _gn(cout), nn.Conv2d(cout, cout, 3, padding=1)
+        if cin != cout:
+            self.nin_shortcut = nn.Conv2d(cin, cout, 1)
+
+    def forward(self, x):
+        h = self.conv2(F.silu(self.norm2(self.conv1(F.silu(self.norm1(x))))))
+        return (self.nin_shortcut(x) if hasattr(self, "nin_shortcut") else x) + h
+
+
+class _SpatialAttn(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+        self.norm, self.qkv, self.proj_out = _gn(c), nn.Conv2d(c, 3 * c, 1), nn.Conv2d(c, c, 1)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        q, k, v = self.qkv(self.norm(x)).reshape(B, 3, C, H * W).unbind(1)
+        o = F.scaled_dot_product_attention(q.transpose(1, 2).unsqueeze(1), k.transpose(1, 2).unsqueeze(1),
+                                           v.transpose(1, 2).unsqueeze(1), scale=C ** -0.5)   # softmax(q k^T / sqrt(C)) v
+        return x + self.proj_out(o.squeeze(1).transpose(1, 2).reshape(B, C, H, W))
+
+
+class _Up(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class _Level(nn.Module):
+    def __init__(self, cin, cout, n, with_attn, with_up):
+        super().__init__()
+        self.block = nn.ModuleList([_Res(cin if i == 0 else cout, cout) for i in range(n)])
+        self.attn = nn.ModuleList([_SpatialAttn(cout) for _ in range(n)] if with_attn else [])
+        if with_up:
+            self.upsample = _Up(cout)
+
+    def forward(self, h):
+        for i, b in enumerate(self.block):
+            h = b(h)
+            if len(self.attn):
+                h = self.attn[i](h)
+        return self.upsample(h) if hasattr(self, "upsample") else h
+
+
+class _Mid(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.block_1, self.attn_1, self.block_2 = _Res(c, c), _SpatialAttn(c), _Res(c, c)
+
+    def forward(self, h):
+        return self.block_2(self.attn_1(self.block_1(h)))
+
+
+class Decoder(nn.Module):
+    def __init__(self, ch=160, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, in_channels=3, z_channels=32):
+        super().__init__()
+        n = len(ch_mult)
+        c = ch * ch_mult[-1]
+        self.conv_in = nn.Conv2d(z_channels, c, 3, padding=1)
+        self.mid = _Mid(c)
+        levels = []
+        for lv in reversed(range(n)):
+            cout = ch * ch_mult[lv]
+            levels.insert(0, _Level(c, cout, num_res_blocks + 1, with_attn=(lv == n - 1), with_up=(lv != 0)))
+            c = cout
+        self.up = nn.ModuleList(levels)
+        self.norm_out, self.conv_out = _gn(c), nn.Conv2d(c, in_channels, 3, padding=1)
+
+    def forward(self, z):
+        h = self.mid(self.conv_in(z))
+        for lv in reversed(range(len(self.up))):
+            h = self.up[lv](h)
+        return self.conv_out(F.silu(self.norm_out(h)))
+
+
+class VQVAE(nn.Module):
+    def __init__(self, vocab_size=4096, z_channels=32, ch=128, dropout=0.0, beta=0.25, using_znorm=False, quant_conv_ks=3,
+                 quant_resi=0.5, share_quant_resi=4, default_qresi_counts=0, v_patch_nums=(1, 2, 3, 4, 5, 6, 8, 10, 13, 16),
+                 test_mode=True, decoder_dtype=torch.bfloat16):
+        super().__init__()
+        self.test_mode, self.V, self.Cvae, self.vocab_size = test_mode, vocab_size, z_channels, vocab_size
+        self.decoder = Decoder(ch=ch, z_channels=z_channels)
+        self.downsample = 16
+        self.quantize = VectorQuantizer2(vocab_size=vocab_size, Cvae=z_channels, using_znorm=using_znorm, beta=beta,
+                                         default_qresi_counts=default_qresi_counts, v_patch_nums=v_patch_nums,
+                                         quant_resi=quant_resi, share_quant_resi=share_quant_resi)
+        self.post_quant_conv = nn.Conv2d(z_channels, z_channels, quant_conv_ks, padding=quant_conv_ks // 2)
+        self.decoder_dtype = decoder_dtype
+        self._dec_cache = None
+        if test_mode:
+            self.eval()
+            for p in self.parameters():
+                p.requires_grad_(False)
+
+    def _decoder_exec(self):
+        """bf16 channels-last copy of (post_quant_conv, decoder), refreshed when the fp32 master weights change."""
+        ps = list(self.decoder.parameters()) + list(self.post_quant_conv.parameters())
+        key = (str(ps[0].device), self.decoder_dtype, sum(p._version for p in ps))
+        if self._dec_cache is None or self._dec_cache[0] != key:
+            import copy
+            mods = nn.Sequential(copy.deepcopy(self.post_quant_conv), copy.deepcopy(self.decoder))
+            mods = mods.to(dtype=self.decoder_dtype).to(memory_format=torch.channels_last).eval()
+            self._dec_cache = (key, mods)
+        return self._dec_cache[1]
+
+    @torch.no_grad()
+    def fhat_to_img(self, f_hat: torch.Tensor) -> torch.Tensor:
+        """decoder(post_quant_conv(f_hat)).clamp(-1,1)  (models/vqvae.py:62-63), fp32 result."""
+        if self.decoder_dtype == torch.float32 or not f_hat.is_cuda:
+            return self.decoder(self.post_quant_conv(f_hat.float())).clamp_(-1, 1)
+        mods = self._decoder_exec()
+        x = f_hat.to(self.decoder_dtype).contiguous(memory_format=torch.channels_last)
+        return mods(x).float().clamp_(-1, 1)
+
+    def idxBl_to_img(self, ms_idx_Bl: List[torch.Tensor], same_shape: bool = True, last_one: bool = False):
+        """models/vqvae.py:69-76: decode token pyramids (same_shape=True only)."""
+        assert same_shape, "same_shape=False is the reference's experimental branch and not supported"
+        B, HW = ms_idx_Bl[0].shape[0], self.quantize.v_patch_nums[-1]
+        f_hat = torch.zeros(B, self.Cvae, HW, HW, device=ms_idx_Bl[0].device, dtype=torch.float32)
+        outs = []
+        for si, idx in enumerate(ms_idx_Bl):
+            self.quantize.next_input_from_idx(si, f_hat, idx.contiguous())
+            if not last_one:
+                outs.append(self.fhat_to_img(f_hat))
+        return self.fhat_to_img(f_hat) if last_one else outs
+
+    def img_to_idxBl(self, *a, **k):
+        raise NotImplementedError("encode side (Encoder + nearest-code search) is SURVEY.md 8f #3: not built yet")
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("VQVAE.forward is VAE training: out of scope")
+
+    def load_state_dict(self, state_dict: Dict[str, Any], strict=True, assign=False):
+        sd = {k: v for k, v in state_dict.items() if not k.startswith(("encoder.", "quant_conv."))}
+        if "quantize.ema_vocab_hit_SV" in sd and sd["quantize.ema_vocab_hit_SV"].shape != self.quantize.ema_vocab_hit_SV.shape:
+            sd["quantize.ema_vocab_hit_SV"] = self.quantize.ema_vocab_hit_SV
+        self._dec_cache = None
+        return super().load_state_dict(sd, strict=strict, assign=assign)
