@@ -205,6 +205,14 @@ typedef struct {
 
 int sdvar_var_forward(const sdvar_var_weights* w_host, const sdvar_pass* pass_host, void* stream);
 
+/* Optional per-family device timing for bench.py's roofline leg (off by default, zero cost when off).  After
+ * sdvar_profile_begin() every entry point brackets its launches with a cudaEvent pair on the launch stream;
+ * sdvar_profile_end() synchronises the device and returns, per family, the summed milliseconds, the summed
+ * ALGORITHMIC work (FLOPs for GEMM/ATTN, bytes for the others, as defined in DESIGN.md) and the launch count. */
+#define SDVAR_PROFILE_FAMILIES 8 /* 0 GEMM, 1 ATTN, 2 LN, 3 SAMPLE, 4 VERIFY, 5 VQ, 6 EMBED, 7 MISC */
+int sdvar_profile_begin(void);
+int sdvar_profile_end(double* ms, double* work, long long* launches);
+
 /* number of kernels the library has launched since load (gpu_launches accounting in bench.py) */
 long long sdvar_launch_count(void);
 

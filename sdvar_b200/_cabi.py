@@ -23,8 +23,9 @@ EXPORTS = [
     "sdvar_abi_version", "sdvar_last_error", "sdvar_arch_check", "sdvar_num_sms", "sdvar_launch_count",
     "sdvar_sample_cfg_topk_topp", "sdvar_verify_accept_resample", "sdvar_verify_top1", "sdvar_vq_next_input",
     "sdvar_embed_next_map", "sdvar_first_map", "sdvar_ln_modulate", "sdvar_silu_bf16", "sdvar_f32_to_bf16",
-    "sdvar_gemm_bf16", "sdvar_attention", "sdvar_var_forward",
+    "sdvar_gemm_bf16", "sdvar_attention", "sdvar_var_forward", "sdvar_profile_begin", "sdvar_profile_end",
 ]
+PROFILE_FAMILIES = ("gemm", "attention", "ln_modulate", "sample", "verify", "vq", "embed", "misc")
 
 
 class SdvarError(RuntimeError):
@@ -163,3 +164,15 @@ def attention(q, k_cache, vT_cache, imgs, H, Lq, Lmax, Lmax_pad, kv_off, seg_beg
 
 def var_forward(w: VarWeights, p: Pass):
     _check(lib().sdvar_var_forward(C.byref(w), C.byref(p), stream_ptr()), "sdvar_var_forward")
+
+
+def profile_begin():
+    _check(lib().sdvar_profile_begin(), "sdvar_profile_begin")
+
+
+def profile_end() -> dict:
+    """{family: (ms, algorithmic work [FLOP for gemm/attention, bytes otherwise], launches)}"""
+    n = len(PROFILE_FAMILIES)
+    ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
+    _check(lib().sdvar_profile_end(ms, work, cnt), "sdvar_profile_end")
+    return {PROFILE_FAMILIES[i]: (ms[i], work[i], int(cnt[i])) for i in range(n)}

@@ -1,6 +1,7 @@
 // api.cu -- library-level entry points: version, error string, arch check, launch accounting.
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -33,7 +34,52 @@ int check_arch() {
   return cached_rc;
 }
 
+// ---- profiling ----------------------------------------------------------------------------------------
+struct ProfRec { cudaEvent_t a, b; int family; double work; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+ProfileScope::ProfileScope(cudaStream_t s, int family, double work) : st(s), slot(-1) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r;
+  r.family = family;
+  r.work = work;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+}
+ProfileScope::~ProfileScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].b, st);
+}
+
 }  // namespace sdvar
+
+extern "C" int sdvar_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(sdvar::g_prof_mu);
+  for (auto& r : sdvar::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  sdvar::g_prof.clear();
+  sdvar::g_prof_on.store(1);
+  return SDVAR_OK;
+}
+// ms[f], work[f], launches[f] for f < SDVAR_PROFILE_FAMILIES; synchronises the device
+extern "C" int sdvar_profile_end(double* ms, double* work, long long* launches) {
+  sdvar::g_prof_on.store(0);
+  if (cudaDeviceSynchronize() != cudaSuccess) { sdvar::set_error("cudaDeviceSynchronize failed in sdvar_profile_end"); return SDVAR_ERR_CUDA; }
+  std::lock_guard<std::mutex> lk(sdvar::g_prof_mu);
+  for (int f = 0; f < sdvar::FAM_COUNT; ++f) { ms[f] = 0; work[f] = 0; launches[f] = 0; }
+  for (auto& r : sdvar::g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.family] += t; work[r.family] += r.work; launches[r.family] += 1; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  sdvar::g_prof.clear();
+  return SDVAR_OK;
+}
 
 extern "C" int sdvar_abi_version(void) { return SDVAR_ABI_VERSION; }
 extern "C" const char* sdvar_last_error(void) { return sdvar::g_err; }

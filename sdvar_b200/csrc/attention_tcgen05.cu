@@ -274,6 +274,9 @@ extern "C" int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, c
     SDVAR_CUDA(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::kSmemBytes));
     attr_set = true;
   }
+  double visible = 0;  // sum over query rows of visible keys
+  for (int j = 0; j < S; ++j) visible += (double)(seg_begin_host[j + 1] - seg_begin_host[j]) * (kv_off + seg_begin_host[j + 1]);
+  ProfileScope prof((cudaStream_t)stream, FAM_ATTN, 4.0 * 64.0 * visible * imgs * H);
   dim3 grid((Lq + attn::BQ - 1) / attn::BQ, H, imgs);
   attn::attention_kernel<<<grid, attn::kThreads, attn::kSmemBytes, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   SDVAR_LAUNCH_CHECK();

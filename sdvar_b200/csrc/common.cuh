@@ -42,6 +42,16 @@ int check_arch();  // SDVAR_OK iff the current device is sm_100
     sdvar::count_launch();                                                                     \
   } while (0)
 
+// ---- optional per-family device timing (bench.py's roofline leg).  Disabled by default: zero overhead on the
+// product path.  When enabled every entry point brackets its launches with a cudaEvent pair on the launch stream.
+enum Family { FAM_GEMM = 0, FAM_ATTN = 1, FAM_LN = 2, FAM_SAMPLE = 3, FAM_VERIFY = 4, FAM_VQ = 5, FAM_EMBED = 6, FAM_MISC = 7, FAM_COUNT = 8 };
+struct ProfileScope {
+  ProfileScope(cudaStream_t st, int family, double work);
+  ~ProfileScope();
+  cudaStream_t st;
+  int slot;
+};
+
 struct SegTable {
   int S;
   int begin[SDVAR_MAX_SEG + 1];

@@ -76,6 +76,7 @@ extern "C" int sdvar_ln_modulate(const float* x, int M, int C, int tokens_per_im
                 "alignment");
   const size_t smem = (size_t)kLnWarps * C * sizeof(float);
   SDVAR_REQUIRE(smem <= 48 * 1024, "C=%d too large for ln_modulate", C);
+  ProfileScope prof((cudaStream_t)stream, FAM_LN, (double)M * C * 6.0);
   ln_modulate_kernel<<<(M + kLnWarps - 1) / kLnWarps, kLnWarps * 32, smem, (cudaStream_t)stream>>>(
       x, M, C, tokens_per_img, scale, shift, ld_mod, eps, reinterpret_cast<__nv_bfloat16*>(out));
   SDVAR_LAUNCH_CHECK();

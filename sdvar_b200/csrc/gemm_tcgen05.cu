@@ -339,6 +339,7 @@ extern "C" int sdvar_gemm_bf16(const sdvar_bf16* A, int lda, const sdvar_bf16* W
     if (int rc = make_tmap_bf16(&tmB, W, 2, dimsB, strB, boxB)) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  ProfileScope prof(st, FAM_GEMM, 2.0 * M * (double)N * K);
   switch (e->epilogue) {
     case SDVAR_EPI_F32: return gemm::launch<SDVAR_EPI_F32>(tmA, tmB, M, N, K, ep, st);
     case SDVAR_EPI_BF16: return gemm::launch<SDVAR_EPI_BF16>(tmA, tmB, M, N, K, ep, st);

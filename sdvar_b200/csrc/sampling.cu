@@ -468,6 +468,7 @@ extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L
   const long long rows = (long long)B * L;
   const int grid = row_grid(rows, 2);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfileScope prof(st, FAM_SAMPLE, (double)rows * (8.0 * V + (noise ? 4.0 * V + 8.0 : 0.0) + (mixed_out ? 4.0 * V : 0.0)));
 #define SDVAR_K3(NV)                                                                                          \
   case NV:                                                                                                    \
     k3_sample_kernel<NV><<<grid, kThreads, 0, st>>>(logits_2BLV, B, L, in_ld, in_off, seg, top_k, one_minus_top_p, noise,   \
@@ -498,6 +499,7 @@ extern "C" int sdvar_verify_accept_resample(const float* xt, const float* xd, co
   SegTable seg;
   if (int rc = fill_seg(seg, seg_begin_host, S, L, nullptr, nullptr)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfileScope prof(st, FAM_VERIFY, (double)B * L * (8.0 * V + 17.0));
   k4_init_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(first_reject, n_accept, B, seg);
   SDVAR_LAUNCH_CHECK();
   const int grid = row_grid((long long)B * L, 2);

@@ -217,6 +217,7 @@ extern "C" int sdvar_vq_next_input(const long long* idx_Bl, int B, int pn, int H
     SDVAR_CUDA(cudaFuncSetAttribute(vq_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VqSmem)));
     attr_set = true;
   }
+  ProfileScope prof(st, FAM_VQ, (double)B * (2.0 * Cvae * HW * HW * 4 + 8.0 * pn * pn + 4.0 * Cvae * pn_next * pn_next));
   vq_accumulate_kernel<<<dim3(HW, B), 256, sizeof(VqSmem), st>>>(idx_Bl, pn, HW, codebook, phi_w, phi_b, f_hat);
   SDVAR_LAUNCH_CHECK();
   if (pn_next > 0) {
@@ -234,6 +235,7 @@ extern "C" int sdvar_embed_next_map(const float* next_map, int B, int l, int Cva
   SDVAR_REQUIRE(Cvae == kC, "Cvae=%d unsupported (32)", Cvae);
   SDVAR_REQUIRE(B > 0 && l > 0 && C > 0 && ldx_tokens >= tok_off + l, "bad geometry");
   SDVAR_REQUIRE(((uintptr_t)W_we & 15) == 0, "W_we must be 16-byte aligned");
+  ProfileScope prof((cudaStream_t)stream, FAM_EMBED, (double)B * l * (4.0 * Cvae + 8.0 * C));
   embed_next_map_kernel<<<dim3((l + kEmbTok - 1) / kEmbTok, B), 256, 0, (cudaStream_t)stream>>>(
       next_map, B, l, C, W_we, b_we, lvl_pos, x, ldx_tokens, tok_off);
   SDVAR_LAUNCH_CHECK();
