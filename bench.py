@@ -172,7 +172,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from sdvar_b200 import _cabi
+    from sdvar_b200 import _cabi, parallel
     from sdvar_b200.models import build_vae_var_speculative_decoding
     from sdvar_b200.weights import var_state_dict, vqvae_state_dict
 
@@ -185,8 +185,6 @@ def main():
     lab_host = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(rank)).pin_memory()
     lab_dev = lab_host.to(dev)
     img_host = torch.empty(B, 3, 256, 256, dtype=torch.float32).pin_memory()
-    gathered = torch.empty(world * B, 3, 256, 256, device=dev) if world > 1 else None
-    stats_acc = {"rounds": 0, "target_passes": 0, "draft_stages": 0, "accepted_tokens": 0, "rejected_tokens": 0}
 
     def step(i: int, e2e: bool):
         lab = lab_host.to(dev, non_blocking=True) if e2e else lab_dev
@@ -194,9 +192,8 @@ def main():
                                                            top_k=args.top_k, top_p=args.top_p, accept_rule=args.accept_rule)
         st = sd.last_stats
         if world > 1:   # the path's only collectives: images + acceptance counters
-            dist.all_gather_into_tensor(gathered, img)
-            c = torch.tensor([st[k] for k in stats_acc], device=dev, dtype=torch.int64)
-            dist.all_reduce(c)
+            parallel.gather_images(img)
+            parallel.reduce_stats(st, dev)
         if e2e:
             img_host.copy_(img, non_blocking=True)
         return st
@@ -209,6 +206,7 @@ def main():
             dist.barrier()
         sampler = ClockSampler(local)
         sampler.start()
+        torch.cuda.profiler.start()      # ncu --profile-from-start off captures exactly the timed region
         l0 = _cabi.launch_count()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -218,6 +216,7 @@ def main():
             last = step(args.warmup + i, e2e)
         b.record()
         torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         ms = a.elapsed_time(b)
         launches = _cabi.launch_count() - l0
         clocks = sampler.stop()

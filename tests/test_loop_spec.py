@@ -1,0 +1,112 @@
+"""CPU tests of the draft->verify loop SPEC (oracle.ref_model.sd_generate, PARITY UNPINNED by the reference) and of the
+data-parallel plumbing (gloo, world_size 2)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle.ref_model import RefVAR, RefVQ, ReplayNoise, sd_generate
+from sdvar_b200.weights import var_state_dict, vqvae_state_dict
+
+P4 = (1, 2, 3, 4)
+KW = dict(gamma_bias=0.5, init_head=1.0)
+
+
+class _Rename:
+    def __init__(self, inner): self.inner = inner
+    def exponential(self, stream, rows, V): return self.inner.exponential("draft", rows, V)
+    def uniform(self, stream, rows): return self.inner.uniform(stream, rows)
+
+
+def _models():
+    vq = RefVQ(vqvae_state_dict(ch=32, patch_nums=P4), P4)
+    d = RefVAR(var_state_dict(2, patch_nums=P4, seed=1, tag="draft", **KW), P4)
+    t = RefVAR(var_state_dict(3, patch_nums=P4, seed=2, tag="target", **KW), P4)
+    return vq, d, t
+
+
+@pytest.mark.parametrize("gamma", [1, 2, 4])
+def test_draft_equal_target_accepts_everything_and_equals_baseline(gamma):
+    vq, d, _ = _models()
+    d2 = RefVAR(var_state_dict(2, patch_nums=P4, seed=1, tag="draft", **KW), P4)
+    B, lab = 2, torch.tensor([4, 5])
+    f, idxs, st = sd_generate(d, d2, vq, B, lab, ReplayNoise(2), cfg=1.5, gamma=gamma, top_k=900, top_p=0.96)
+    # window pass vs incremental pass differ by fp32 re-association (1e-7): p/q may differ in the last ulp, which can
+    # reject a token only if u*q lands within that ulp of p -- not with these seeds
+    assert st["rejected_tokens"] == 0 and sum(st["advance"]) == 4 and st["rounds"] == -(-4 // gamma)
+    noise = _Rename(ReplayNoise(2))
+    nl = [noise.exponential("target", B * l, 4096) for l in d.ls]
+    fb, ib = d.autoregressive_infer_cfg(vq, B, lab, cfg=1.5, top_k=900, top_p=0.96, noise=nl)
+    assert all(torch.equal(a, b) for a, b in zip(idxs, ib)) and torch.allclose(f, fb)
+
+
+@pytest.mark.parametrize("rule", ["speculative", "reference"])
+def test_loop_invariants_with_rejections(rule):
+    vq, d, t = _models()
+    B, lab = 3, torch.tensor([1, 2, 3])
+    f, idxs, st = sd_generate(d, t, vq, B, lab, ReplayNoise(7), cfg=1.5, gamma=2, accept_rule=rule)
+    assert [i.shape for i in idxs] == [(B, l) for l in d.ls]
+    assert sum(st["advance"]) == 4 and st["target_passes"] == st["rounds"] and all(1 <= a <= 2 for a in st["advance"])
+    fr = torch.zeros(B, 32, 4, 4)
+    for si, ix in enumerate(idxs):
+        fr, _ = vq.next_input(si, fr, ix)
+    assert torch.allclose(f, fr, atol=1e-6)                       # f_hat == VQ(final tokens): no double add (D7)
+    assert d.kv_len() == 0 and t.kv_len() == 0                    # caches released
+
+
+def test_window_pass_equals_incremental_pass():
+    """pin P3 on the oracle: one block-causal pass over g stages == g KV-cached stage passes"""
+    vq, _, t = _models()
+    B, lab = 2, torch.tensor([9, 10])
+    cond = t.cond(lab)
+    xs = [t.first_map(cond)] + [t.embed_map(si, torch.randn(B, 32, P4[si], P4[si], generator=torch.Generator().manual_seed(si))) for si in (1, 2, 3)]
+    t.kv_caching(True)
+    inc = [t.get_logits(t.blocks(x, cond, None), cond) for x in xs]
+    t.kv_caching(True)
+    a = t.forward_window(0, xs[:2], cond)
+    b = t.forward_window(2, xs[2:], cond)
+    for got, want in zip(a + b, inc):
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    t.kv_caching(False)
+
+
+# ---------------------------------------------------------------------------------------------- DP plumbing, gloo
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sdvar_b200 import parallel
+    G = 5                                                        # ragged: 3 + 2
+    labels = torch.arange(100, 100 + G)
+    mine = parallel.shard_labels(labels)
+    img = mine.float().view(-1, 1, 1, 1).expand(-1, 3, 2, 2).contiguous()
+    allimg = parallel.gather_images(img, global_batch=G)
+    stats = parallel.reduce_stats(dict(rounds=10, target_passes=10, draft_stages=19, accepted_tokens=100 * (rank + 1), rejected_tokens=rank), "cpu")
+    even = parallel.gather_images(torch.full((2, 3, 2, 2), float(rank)))
+    q.put((rank, mine.tolist(), allimg[:, 0, 0, 0].tolist(), stats, even[:, 0, 0, 0].tolist(), parallel.rank_seed(7)))
+    dist.destroy_process_group()
+
+
+def test_dp_sharding_gather_and_stats_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(30) for p in ps]
+    assert res[0][1] == [100, 101, 102] and res[1][1] == [103, 104]
+    for r in res:
+        assert r[2] == [100.0, 101.0, 102.0, 103.0, 104.0]
+        assert r[3] == dict(rounds=20, target_passes=20, draft_stages=38, accepted_tokens=300, rejected_tokens=1)
+        assert r[4] == [0.0, 0.0, 1.0, 1.0]
+    assert res[0][5] == 7 and res[1][5] == 8
+
+
+def test_shard_range_partitions_exactly():
+    from sdvar_b200.parallel import shard_range
+    for G in (1, 7, 64, 512):
+        for w in (1, 2, 4, 8):
+            r = [shard_range(G, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == G and all(a[1] == b[0] for a, b in zip(r, r[1:]))
