@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
+#include "gemm_epilogue.cuh"
+#include <stdlib.h>
 
 namespace sdvar {
 
@@ -29,18 +31,6 @@ constexpr int kTmemCols = kAccStages * BN;  // 256
 constexpr int kGroupM = 16;
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * (A_BYTES + B_BYTES) + 256 /*barriers*/;
 
-struct Epi {
-  const float* bias;
-  float* out_f32;
-  __nv_bfloat16* out_bf16;
-  int ldo;
-  const float* gate;
-  int ld_gate, tokens_per_img;
-  __nv_bfloat16 *q_out, *k_cache, *vT_cache;
-  const float* scale_mul;
-  int H, Lq, Lmax, Lmax_pad, kv_off, l2norm, C;
-};
-
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb, int& nb) {
   const int per_group = kGroupM * num_n;
   const int g = t / per_group;
@@ -49,119 +39,6 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb
   const int r = t - g * per_group;
   mb = first_m + r % gsz;
   nb = r / gsz;
-}
-
-__device__ __forceinline__ float gelu_tanh(float x) {
-  // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3)))  (nn.GELU(approximate='tanh'), models/basic_var.py:40)
-  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  return 0.5f * x * (1.0f + t);
-}
-
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    d[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                      pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-}
-
-template <int EPI>
-__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row, int col_base, int M, int N, const Epi& ep) {
-  if constexpr (EPI == SDVAR_EPI_QKV) {
-    // 64-column groups = one attention head of one of q / k / v
-#pragma unroll 1
-    for (int g0 = 0; g0 < BN; g0 += 64) {
-      uint32_t r0[32], r1[32];
-      ptx::tmem_ld_32x32(taddr + g0, r0);
-      ptx::tmem_ld_32x32(taddr + g0 + 32, r1);
-      ptx::tmem_ld_wait();
-      const int col0 = col_base + g0;
-      if (row < M && col0 < N) {
-        float v[64];
-        const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = __ldg(b4 + q), bc = __ldg(b4 + 8 + q);
-          v[4 * q] = __uint_as_float(r0[4 * q]) + bb.x; v[4 * q + 1] = __uint_as_float(r0[4 * q + 1]) + bb.y;
-          v[4 * q + 2] = __uint_as_float(r0[4 * q + 2]) + bb.z; v[4 * q + 3] = __uint_as_float(r0[4 * q + 3]) + bb.w;
-          v[32 + 4 * q] = __uint_as_float(r1[4 * q]) + bc.x; v[32 + 4 * q + 1] = __uint_as_float(r1[4 * q + 1]) + bc.y;
-          v[32 + 4 * q + 2] = __uint_as_float(r1[4 * q + 2]) + bc.z; v[32 + 4 * q + 3] = __uint_as_float(r1[4 * q + 3]) + bc.w;
-        }
-        const int sect = col0 / ep.C, h = (col0 - sect * ep.C) >> 6;
-        if (sect < 2 && ep.l2norm) {
-          float ss = 0.0f;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) ss += v[i] * v[i];
-          float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (models/basic_var.py:103-104)
-          if (sect == 0) inv *= __expf(fminf(__ldg(ep.scale_mul + h), 4.605170185988092f));  // clamp_max(log 100).exp()
-#pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] *= inv;
-        }
-        const int img = row / ep.Lq, t = row - img * ep.Lq;
-        if (sect < 2) {
-          __nv_bfloat16* dst = (sect == 0)
-              ? ep.q_out + (((size_t)img * ep.H + h) * ep.Lq + t) * 64
-              : ep.k_cache + (((size_t)img * ep.H + h) * ep.Lmax + ep.kv_off + t) * 64;
-          uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            d[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-        } else {
-          __nv_bfloat16* dst = ep.vT_cache + ((size_t)img * ep.H + h) * 64 * ep.Lmax_pad + ep.kv_off + t;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) dst[(size_t)i * ep.Lmax_pad] = __float2bfloat16_rn(v[i]);
-        }
-      }
-    }
-  } else {
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(taddr + c0, r);
-      ptx::tmem_ld_wait();
-      const int col0 = col_base + c0;
-      if (row < M && col0 < N) {
-        float v[32];
-        if (ep.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bb = __ldg(b4 + q);
-            v[4 * q] = __uint_as_float(r[4 * q]) + bb.x; v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb.y;
-            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb.z; v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        }
-        if constexpr (EPI == SDVAR_EPI_F32) {
-          float4* d = reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo + col0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else if constexpr (EPI == SDVAR_EPI_BF16) {
-          store_bf16x32(ep.out_bf16 + (size_t)row * ep.ldo + col0, v);
-        } else if constexpr (EPI == SDVAR_EPI_GELU_BF16) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
-          store_bf16x32(ep.out_bf16 + (size_t)row * ep.ldo + col0, v);
-        } else if constexpr (EPI == SDVAR_EPI_RESID_F32) {
-          const int img = row / ep.tokens_per_img;
-          const float4* g4 = reinterpret_cast<const float4*>(ep.gate + (size_t)img * ep.ld_gate + col0);
-          float4* d = reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo + col0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 g = __ldg(g4 + q);
-            float4 o = d[q];
-            o.x += v[4 * q] * g.x; o.y += v[4 * q + 1] * g.y; o.z += v[4 * q + 2] * g.z; o.w += v[4 * q + 3] * g.w;
-            d[q] = o;
-          }
-        }
-      }
-    }
-  }
 }
 
 template <int EPI>
@@ -246,10 +123,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int mb, nb;
       tile_coords(t, num_m, num_n, mb, nb);
+      EpiPre pre;
+      epilogue_prefetch<EPI>(pre, mb * BM + ew * 32 + lane, nb * BN, M, N, ep);
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
-      epilogue_tile<EPI>(taddr, mb * BM + ew * 32 + lane, nb * BN, M, N, ep);
+      epilogue_tile<EPI, BN>(taddr, mb * BM + ew * 32 + lane, nb * BN, M, N, ep, pre);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[as]);
@@ -279,6 +158,21 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, 
 }
 
 }  // namespace gemm
+}  // namespace sdvar
+
+namespace sdvar {
+namespace gemm2 {
+int launch_pair(int epilogue, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const gemm::Epi& ep, cudaStream_t st);
+}
+// 0 = automatic, 1 = force the 1-CTA kernel, 2 = force the CTA-pair kernel (SDVAR_GEMM env, for A/B measurements)
+static int gemm_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SDVAR_GEMM");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode;
+}
 }  // namespace sdvar
 
 using namespace sdvar;
@@ -329,6 +223,12 @@ extern "C" int sdvar_gemm_bf16(const sdvar_bf16* A, int lda, const sdvar_bf16* W
     default:
       SDVAR_REQUIRE(false, "unknown epilogue %d", e->epilogue);
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfileScope prof(st, FAM_GEMM, 2.0 * M * (double)N * K);
+  // CTA pairs (256x256 tiles) once there are enough tiles to fill 74 clusters; small M stays on 128x128 tiles
+  const int mode = gemm_mode();
+  const long long pair_tiles = (long long)((M + 255) / 256) * ((N + 255) / 256);
+  if (mode == 2 || (mode == 0 && pair_tiles >= 74)) return gemm2::launch_pair(e->epilogue, A, lda, W, ldw, M, N, K, ep, st);
   CUtensorMap tmA, tmB;
   {
     const uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}, strA[1] = {(uint64_t)lda * 2};
@@ -338,8 +238,6 @@ extern "C" int sdvar_gemm_bf16(const sdvar_bf16* A, int lda, const sdvar_bf16* W
     const uint32_t boxB[2] = {(uint32_t)gemm::BK, (uint32_t)gemm::BN};
     if (int rc = make_tmap_bf16(&tmB, W, 2, dimsB, strB, boxB)) return rc;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  ProfileScope prof(st, FAM_GEMM, 2.0 * M * (double)N * K);
   switch (e->epilogue) {
     case SDVAR_EPI_F32: return gemm::launch<SDVAR_EPI_F32>(tmA, tmB, M, N, K, ep, st);
     case SDVAR_EPI_BF16: return gemm::launch<SDVAR_EPI_BF16>(tmA, tmB, M, N, K, ep, st);
