@@ -157,10 +157,13 @@ int sdvar_gemm_bf16(const sdvar_bf16* A, int lda, const sdvar_bf16* W, int ldw, 
  * q (imgs,H,Lq,64) bf16; k_cache (imgs,H,Lmax,64); vT_cache (imgs,H,64,Lmax_pad); out (imgs*Lq, H*64)
  * bf16.  Query token t of the launch belongs to window stage j (seg_begin_host over [0,Lq)) and sees
  * keys [0, kv_off + seg_begin[j+1]) -- block-causal inside the window, everything before it
- * (models/var.py:108-113; incremental decode is S=1).  softmax scale `scale` (1.0 with l2 norm). */
+ * (models/var.py:108-113; incremental decode is S=1).  softmax scale `scale` (1.0 with l2 norm).
+ * logit_bound_log (device, [H], may be NULL): when given, the caller guarantees |q.k| <= exp(min(logit_bound_log[h], ln 100)) <= 40
+ * for every head (true for l2-normalised attention, where it is the scale_mul parameter): the kernel then uses that bound
+ * as the softmax reference point and runs the one-pass ping-pong variant; NULL selects the general two-pass kernel. */
 int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, const sdvar_bf16* vT_cache, int imgs, int H,
                     int Lq, int Lmax, int Lmax_pad, int kv_off, const int* seg_begin_host, int S, float scale,
-                    sdvar_bf16* out, void* stream);
+                    const float* logit_bound_log, sdvar_bf16* out, void* stream);
 
 /* ---- whole transformer pass (the launch sequence of one stage / one verify window) -----------
  * Device-pointer table of one VAR model in the engine's packed layout (bf16 weights, fp32 vectors).
@@ -179,6 +182,7 @@ typedef struct {
   const float* b_fc2[SDVAR_MAX_DEPTH];
   const sdvar_bf16* w_head;                   /* (V, C) */
   const float* b_head;
+  int attn_fixed_max;                         /* 1: l2norm and exp(min(scale_mul, ln 100)) <= 40 for every head (one-pass attention) */
 } sdvar_var_weights;
 
 typedef struct {

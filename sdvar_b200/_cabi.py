@@ -47,7 +47,7 @@ class VarWeights(C.Structure):
                 ("w_proj", C.c_void_p * MAX_DEPTH), ("b_proj", C.c_void_p * MAX_DEPTH),
                 ("w_fc1", C.c_void_p * MAX_DEPTH), ("b_fc1", C.c_void_p * MAX_DEPTH),
                 ("w_fc2", C.c_void_p * MAX_DEPTH), ("b_fc2", C.c_void_p * MAX_DEPTH),
-                ("w_head", C.c_void_p), ("b_head", C.c_void_p)]
+                ("w_head", C.c_void_p), ("b_head", C.c_void_p), ("attn_fixed_max", C.c_int)]
 
 
 class Pass(C.Structure):
@@ -156,9 +156,9 @@ def gemm_bf16(A, lda, W, ldw, M, N, K, epi: GemmEpilogue):
     _check(lib().sdvar_gemm_bf16(ptr(A), lda, ptr(W), ldw, M, N, K, C.byref(epi), stream_ptr()), "sdvar_gemm_bf16")
 
 
-def attention(q, k_cache, vT_cache, imgs, H, Lq, Lmax, Lmax_pad, kv_off, seg_begin, scale, out):
+def attention(q, k_cache, vT_cache, imgs, H, Lq, Lmax, Lmax_pad, kv_off, seg_begin, scale, out, logit_bound_log=None):
     _check(lib().sdvar_attention(ptr(q), ptr(k_cache), ptr(vT_cache), imgs, H, Lq, Lmax, Lmax_pad, kv_off,
-                                 _iarr(seg_begin), len(seg_begin) - 1, C.c_float(scale), ptr(out), stream_ptr()),
+                                 _iarr(seg_begin), len(seg_begin) - 1, C.c_float(scale), ptr(logit_bound_log), ptr(out), stream_ptr()),
            "sdvar_attention")
 
 

@@ -239,11 +239,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }  // namespace attn
 }  // namespace sdvar
 
+namespace sdvar {
+namespace attn2 {
+int launch_onepass(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, int imgs, int H, int Lq, int kv_off,
+                   const int* seg_begin_host, int S, float scale, const float* scale_mul, __nv_bfloat16* out, cudaStream_t st);
+}
+}  // namespace sdvar
+
 using namespace sdvar;
 
 extern "C" int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, const sdvar_bf16* vT_cache, int imgs, int H,
                                int Lq, int Lmax, int Lmax_pad, int kv_off, const int* seg_begin_host, int S, float scale,
-                               sdvar_bf16* out, void* stream) {
+                               const float* logit_bound_log, sdvar_bf16* out, void* stream) {
   if (int rc = check_arch()) return rc;
   SDVAR_REQUIRE(q && k_cache && vT_cache && out, "NULL argument");
   SDVAR_REQUIRE(imgs > 0 && H > 0 && Lq > 0 && kv_off >= 0 && kv_off + Lq <= Lmax && Lmax <= Lmax_pad, "bad geometry");
@@ -269,14 +276,17 @@ extern "C" int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, c
     const uint32_t bv[3] = {64, 64, 1};
     if (int rc = make_tmap_bf16(&tmV, vT_cache, 3, dv, sv, bv)) return rc;
   }
+  double visible = 0;  // sum over query rows of visible keys
+  for (int j = 0; j < S; ++j) visible += (double)(seg_begin_host[j + 1] - seg_begin_host[j]) * (kv_off + seg_begin_host[j + 1]);
+  ProfileScope prof((cudaStream_t)stream, FAM_ATTN, 4.0 * 64.0 * visible * imgs * H);
+  if (logit_bound_log != nullptr)
+    return attn2::launch_onepass(tmQ, tmK, tmV, imgs, H, Lq, kv_off, seg_begin_host, S, scale, logit_bound_log,
+                                 reinterpret_cast<__nv_bfloat16*>(out), (cudaStream_t)stream);
   static bool attr_set = false;
   if (!attr_set) {
     SDVAR_CUDA(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::kSmemBytes));
     attr_set = true;
   }
-  double visible = 0;  // sum over query rows of visible keys
-  for (int j = 0; j < S; ++j) visible += (double)(seg_begin_host[j + 1] - seg_begin_host[j]) * (kv_off + seg_begin_host[j + 1]);
-  ProfileScope prof((cudaStream_t)stream, FAM_ATTN, 4.0 * 64.0 * visible * imgs * H);
   dim3 grid((Lq + attn::BQ - 1) / attn::BQ, H, imgs);
   attn::attention_kernel<<<grid, attn::kThreads, attn::kSmemBytes, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   SDVAR_LAUNCH_CHECK();

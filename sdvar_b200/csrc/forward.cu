@@ -31,7 +31,8 @@ extern "C" int sdvar_var_forward(const sdvar_var_weights* w, const sdvar_pass* p
     e.H = w->H; e.Lq = ps->Lq; e.Lmax = ps->Lmax; e.Lmax_pad = ps->Lmax_pad; e.kv_off = ps->kv_off; e.l2norm = w->l2norm;
     if ((rc = sdvar_gemm_bf16(ps->xm, C, w->w_qkv[i], C, M, 3 * C, C, &e, stream))) return rc;
     if ((rc = sdvar_attention(ps->q, ps->k_cache[i], ps->vT_cache[i], ps->imgs, w->H, ps->Lq, ps->Lmax, ps->Lmax_pad,
-                              ps->kv_off, ps->seg_begin, ps->S, w->attn_scale, ps->attn, stream)))
+                              ps->kv_off, ps->seg_begin, ps->S, w->attn_scale,
+                              (w->attn_fixed_max && w->l2norm) ? w->scale_mul[i] : nullptr, ps->attn, stream)))
       return rc;
     sdvar_gemm_epilogue r{};
     r.epilogue = SDVAR_EPI_RESID_F32;

@@ -80,6 +80,11 @@ class VarEngine:
         self.lvl_pos = f32(m.lvl_embed.weight[m.lvl_1L[0]] + m.pos_1LC[0])              # (L, C)  var.py:164
         self.pos_start = f32(m.pos_start[0])                                              # (first_l, C)
         self.class_emb = f32(m.class_emb.weight)
+        # one-pass attention needs the logit bound exp(min(scale_mul, ln 100)) <= 40 on every head (attention2_tcgen05.cu)
+        w.attn_fixed_max = 0
+        if m.attn_l2_norm:
+            smax = max(float(blk.attn.scale_mul_1H11.detach().max()) for blk in m.blocks)
+            w.attn_fixed_max = int(math.exp(min(smax, math.log(100.0))) <= 40.0)
         self.weights = w
         self._packed_key = key
 

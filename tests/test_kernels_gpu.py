@@ -252,7 +252,7 @@ def test_gemm_bf16_gelu_and_residual(cuda_lib):
     assert torch.allclose(x.cpu(), ref, rtol=1e-4, atol=1e-4)
 
 
-def _attn_case(cuda_lib, imgs, H, ls_window, kv_off, l2norm, seed):
+def _attn_case(cuda_lib, imgs, H, ls_window, kv_off, l2norm, seed, clamp_head=False):
     """QKV epilogue + attention against a plain fp32 torch restatement of basic_var.py:93-117."""
     C = H * 64
     Lq = sum(ls_window)
@@ -263,7 +263,9 @@ def _attn_case(cuda_lib, imgs, H, ls_window, kv_off, l2norm, seed):
     xm = hashed("a.x", seed, (M, C), 1.0, dtype=torch.bfloat16)
     Wqkv = hashed("a.W", seed, (3 * C, C), 1.0 / math.sqrt(C), dtype=torch.bfloat16)
     bias = hashed("a.b", seed, (3 * C,), 0.3); bias[C:2 * C] = 0
-    smul = math.log(4.0) + hashed("a.s", seed, (H,), 0.5); smul[0] = 6.0    # one head hits the clamp at log(100)
+    smul = math.log(4.0) + hashed("a.s", seed, (H,), 0.5)
+    if clamp_head:
+        smul[0] = 6.0    # one head hits the clamp at log(100) (forces the two-pass kernel)
     # prefix already in the cache
     kpre = torch.nn.functional.normalize(hashed("a.kp", seed, (imgs, H, kv_off, 64), 1.0), dim=-1) if l2norm else hashed("a.kp", seed, (imgs, H, kv_off, 64), 1.0)
     vpre = hashed("a.vp", seed, (imgs, H, kv_off, 64), 1.0)
@@ -279,6 +281,10 @@ def _attn_case(cuda_lib, imgs, H, ls_window, kv_off, l2norm, seed):
     scale = 1.0 if l2norm else 0.25 / 8.0
     out = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
     cuda_lib.attention(q, kc, vc, imgs, H, Lq, Lmax, Lmax_pad, kv_off, seg, scale, out)
+    out1 = None
+    if l2norm and float(smul.clamp_max(math.log(100)).exp().max()) <= 40:    # one-pass ping-pong variant
+        out1 = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+        cuda_lib.attention(q, kc, vc, imgs, H, Lq, Lmax, Lmax_pad, kv_off, seg, scale, out1, logit_bound_log=sd_)
     torch.cuda.synchronize()
     # ---- reference ----
     qkv = (_gemm_ref(xm, Wqkv) + bias).view(imgs, Lq, 3, H, 64).permute(2, 0, 3, 1, 4)
@@ -301,6 +307,8 @@ def _attn_case(cuda_lib, imgs, H, ls_window, kv_off, l2norm, seed):
     ref = (s.softmax(-1) @ vb).transpose(1, 2).reshape(M, C)
     # P is rounded to bf16 before P@V (rel 2^-9 per term) and the output is bf16
     assert torch.allclose(out.float().cpu(), ref, rtol=2 ** -6, atol=4e-3), float((out.float().cpu() - ref).abs().max())
+    if out1 is not None:
+        assert torch.allclose(out1.float().cpu(), ref, rtol=2 ** -6, atol=4e-3), float((out1.float().cpu() - ref).abs().max())
 
 
 @pytest.mark.parametrize("imgs,H,ls,kv_off,l2", [(2, 2, [1], 0, True), (4, 3, [16], 14, True), (2, 16, [169], 255, True),
@@ -308,3 +316,4 @@ def _attn_case(cuda_lib, imgs, H, ls_window, kv_off, l2norm, seed):
                                                  (2, 2, [4, 9, 16, 25], 1, False), (2, 20, [36, 64], 55, True)])
 def test_qkv_epilogue_and_attention(cuda_lib, imgs, H, ls, kv_off, l2):
     _attn_case(cuda_lib, imgs, H, ls, kv_off, l2, 0)
+    _attn_case(cuda_lib, imgs, H, ls, kv_off, l2, 1, clamp_head=True)

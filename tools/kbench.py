@@ -20,7 +20,7 @@ from sdvar_b200 import _cabi  # noqa: E402
 DEV = "cuda"
 P256 = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)
 LS = [p * p for p in P256]
-SEG = [0] + list(np.cumsum(LS))
+SEG = [0] + [int(v) for v in np.cumsum(LS)]
 
 
 def peaks():
@@ -80,13 +80,14 @@ def bench_attn(out):
             for stages in ([9], [8], [6], [3], [8, 9]):
                 ls = [LS[s] for s in stages]
                 Lq, kv_off = sum(ls), SEG[stages[0]]
-                seg = [0] + list(np.cumsum(ls))
+                seg = [0] + [int(v) for v in np.cumsum(ls)]
                 Lmax, Lp = 680, 680
                 q = torch.randn(imgs, H, Lq, 64, device=DEV).bfloat16()
                 kc = torch.nn.functional.normalize(torch.randn(imgs, H, Lmax, 64, device=DEV), dim=-1).bfloat16()
                 vc = torch.randn(imgs, H, 64, Lp, device=DEV).bfloat16()
                 o = torch.empty(imgs * Lq, H * 64, device=DEV, dtype=torch.bfloat16)
-                ms = timeit(lambda: _cabi.attention(q, kc, vc, imgs, H, Lq, Lmax, Lp, kv_off, seg, 1.0, o))
+                sm = torch.full((H,), math.log(4.0), device=DEV)
+                ms = timeit(lambda: _cabi.attention(q, kc, vc, imgs, H, Lq, Lmax, Lp, kv_off, [int(v) for v in seg], 1.0, o, logit_bound_log=sm))
                 vis = sum(l * (kv_off + e) for l, e in zip(ls, seg[1:]))
                 fl = 4.0 * 64 * vis * imgs * H
                 rows.append(dict(model=name, stages=stages, ms=ms, tflops=fl / ms / 1e9))
