@@ -241,7 +241,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 namespace sdvar {
 namespace attn2 {
-int launch_onepass(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, int imgs, int H, int Lq, int kv_off,
+int launch_onepass(const void* q, const void* k_cache, const void* vT_cache, int imgs, int H, int Lq, int Lmax, int Lmax_pad, int kv_off,
                    const int* seg_begin_host, int S, float scale, const float* scale_mul, __nv_bfloat16* out, cudaStream_t st);
 }
 }  // namespace sdvar
@@ -264,6 +264,12 @@ extern "C" int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, c
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.seg.S = S;
   for (int j = 0; j <= S; ++j) p.seg.begin[j] = seg_begin_host[j];
+  double visible = 0;  // sum over query rows of visible keys
+  for (int j = 0; j < S; ++j) visible += (double)(seg_begin_host[j + 1] - seg_begin_host[j]) * (kv_off + seg_begin_host[j + 1]);
+  ProfileScope prof((cudaStream_t)stream, FAM_ATTN, 4.0 * 64.0 * visible * imgs * H);
+  if (logit_bound_log != nullptr)
+    return attn2::launch_onepass(q, k_cache, vT_cache, imgs, H, Lq, Lmax, Lmax_pad, kv_off, seg_begin_host, S, scale, logit_bound_log,
+                                 reinterpret_cast<__nv_bfloat16*>(out), (cudaStream_t)stream);
   CUtensorMap tmQ, tmK, tmV;
   {
     const uint64_t dq[3] = {64, (uint64_t)Lq, (uint64_t)imgs * H}, sq[2] = {128, (uint64_t)Lq * 128};
@@ -276,12 +282,6 @@ extern "C" int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, c
     const uint32_t bv[3] = {64, 64, 1};
     if (int rc = make_tmap_bf16(&tmV, vT_cache, 3, dv, sv, bv)) return rc;
   }
-  double visible = 0;  // sum over query rows of visible keys
-  for (int j = 0; j < S; ++j) visible += (double)(seg_begin_host[j + 1] - seg_begin_host[j]) * (kv_off + seg_begin_host[j + 1]);
-  ProfileScope prof((cudaStream_t)stream, FAM_ATTN, 4.0 * 64.0 * visible * imgs * H);
-  if (logit_bound_log != nullptr)
-    return attn2::launch_onepass(tmQ, tmK, tmV, imgs, H, Lq, kv_off, seg_begin_host, S, scale, logit_bound_log,
-                                 reinterpret_cast<__nv_bfloat16*>(out), (cudaStream_t)stream);
   static bool attr_set = false;
   if (!attr_set) {
     SDVAR_CUDA(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::kSmemBytes));
