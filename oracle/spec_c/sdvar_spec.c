@@ -53,8 +53,8 @@ float sdvar_spec_expf(float x) {
   p = fmaf(p, r, 0.5f);
   p = fmaf(p, r, 1.0f);
   p = fmaf(p, r, 1.0f);
+  /* 2^n in two steps (exact, then rounded once if the result is denormal): identical to one multiplication by 2^n */
   const int ni = (int)n;
-  if (ni >= -126) return p * u2f((uint32_t)(ni + 127) << 23);
   return (p * u2f((uint32_t)(ni + 100 + 127) << 23)) * u2f((uint32_t)(-100 + 127) << 23);
 }
 

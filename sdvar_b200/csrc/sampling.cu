@@ -15,12 +15,14 @@ namespace sdvar {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
-// exp(x), bit-identical to sdvar_spec_expf
+// exp(x) for x <= 0, bit-identical to sdvar_spec_expf.  Branch-free so the 16-32 independent exponentials of a thread
+// interleave: the input is clamped at -104 (the spec returns 0 below it) and the power-of-two scaling is always done in two
+// exact-or-once-rounded steps (2^(n+100) then 2^-100), which rounds identically to a single multiplication by 2^n.
 __device__ __forceinline__ float spec_expf(float x) {
-  if (x < -104.0f) return 0.0f;
-  const float t = __fmul_rn(x, 1.44269504088896340736f);
+  const float xc = fmaxf(x, -104.0f);
+  const float t = __fmul_rn(xc, 1.44269504088896340736f);
   const float n = rintf(t);
-  float r = __fmaf_rn(n, -0.693145751953125f, x);
+  float r = __fmaf_rn(n, -0.693145751953125f, xc);
   r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
   float p = 1.0f / 5040.0f;
   p = __fmaf_rn(p, r, 1.0f / 720.0f);
@@ -30,9 +32,9 @@ __device__ __forceinline__ float spec_expf(float x) {
   p = __fmaf_rn(p, r, 0.5f);
   p = __fmaf_rn(p, r, 1.0f);
   p = __fmaf_rn(p, r, 1.0f);
-  const int ni = (int)n;
-  if (ni >= -126) return __fmul_rn(p, u2f((uint32_t)(ni + 127) << 23));
-  return __fmul_rn(__fmul_rn(p, u2f((uint32_t)(ni + 100 + 127) << 23)), u2f((uint32_t)(-100 + 127) << 23));
+  const int ni = (int)n;   // in [-151, 0]
+  const float v = __fmul_rn(__fmul_rn(p, u2f((uint32_t)(ni + 100 + 127) << 23)), u2f((uint32_t)(-100 + 127) << 23));
+  return (x < -104.0f) ? 0.0f : v;
 }
 
 // ---- block reductions.  `slot` alternates between two smem buffers so one barrier per reduction suffices.
@@ -250,88 +252,145 @@ __global__ void k4_init_kernel(int* first_reject, int* n_accept, int B, SegTable
   }
 }
 
+// K4 v2: the two logit rows of a token (2 x V fp32 = 32 KiB) are staged in shared memory by 1-D bulk TMA copies
+// (cp.async.bulk + mbarrier), double-buffered so row i+1 streams in while row i is processed; several CTAs per SM keep
+// >= 96 KiB in flight per SM.  The accept path touches each value once (max, exp, sum: nothing is kept in registers);
+// only a rejected row re-reads its staged logits to rebuild p and q for the residual resample.  Same arithmetic and
+// reduction order as v1, i.e. bit-exact to oracle/spec_c/sdvar_spec.c.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init1(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_par(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "K4_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra K4_DONE;\n"
+      "bra K4_WAIT;\n"
+      "K4_DONE:\n"
+      "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 template <int NV>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, const long long* __restrict__ draft_idx,
                  const float* __restrict__ u, const float* __restrict__ noise, int B, int L, SegTable seg,
                  long long* __restrict__ out_idx, unsigned char* __restrict__ accept, float* __restrict__ p_d_out,
                  float* __restrict__ q_d_out, int* first_reject, int* n_accept, int* accepted_stages, int* summary,
                  int* counter) {
   constexpr int V = NV * 1024;
-  constexpr int E = NV * 4;
+  extern __shared__ __align__(128) unsigned char k4_smem[];
+  float* stage_buf = reinterpret_cast<float*>(k4_smem);                    // [2][2][V]
+  uint64_t* full = reinterpret_cast<uint64_t*>(k4_smem + 2 * 2 * V * 4);   // [2]
   __shared__ RedSmem sm;
   __shared__ int s_last;
   int slot = 0;
   const int tid = threadIdx.x;
   const long long rows = (long long)B * L;
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+  if (tid == 0) {
+    mbar_init1(&full[0]);
+    mbar_init1(&full[1]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((long long)blockIdx.x < rows) {
+      mbar_expect(&full[0], 2 * V * 4);
+      bulk_g2s(stage_buf, xt + (long long)blockIdx.x * V, V * 4, &full[0]);
+      bulk_g2s(stage_buf + V, xd + (long long)blockIdx.x * V, V * 4, &full[0]);
+    }
+  }
+  __syncthreads();
+  uint32_t k = 0;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x, ++k) {
+    const uint32_t st = k & 1;
+    // prefetch the next row into the other stage (all reads of that stage finished before the barrier closing iteration k-1)
+    const long long nrow = row + gridDim.x;
+    if (tid == 0 && nrow < rows) {
+      mbar_expect(&full[st ^ 1], 2 * V * 4);
+      bulk_g2s(stage_buf + (st ^ 1) * 2 * V, xt + nrow * V, V * 4, &full[st ^ 1]);
+      bulk_g2s(stage_buf + (st ^ 1) * 2 * V + V, xd + nrow * V, V * 4, &full[st ^ 1]);
+    }
     const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
     const int j = seg_of(seg, pos);
-    const float4* pt = reinterpret_cast<const float4*>(xt + row * V);
-    const float4* pd = reinterpret_cast<const float4*>(xd + row * V);
-    float et[E], ed[E];
-    {
-      float4 a[NV], c[NV];
-#pragma unroll
-      for (int i = 0; i < NV; ++i) { a[i] = ldg_stream(pt + i * kThreads + tid); c[i] = ldg_stream(pd + i * kThreads + tid); }
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        et[4 * i] = a[i].x; et[4 * i + 1] = a[i].y; et[4 * i + 2] = a[i].z; et[4 * i + 3] = a[i].w;
-        ed[4 * i] = c[i].x; ed[4 * i + 1] = c[i].y; ed[4 * i + 2] = c[i].z; ed[4 * i + 3] = c[i].w;
-      }
-    }
     const int d = (int)draft_idx[row];
     const float uu = u[row];
-    uint32_t kt = 0, kd = 0;
+    mbar_wait_par(&full[st], (k >> 1) & 1);
+    const float4* st4 = reinterpret_cast<const float4*>(stage_buf + st * 2 * V);
+    const float4* sd4 = st4 + V / 4;
+    // pass 1: row maxima (order-independent)
+    float mt = -INFINITY, md = -INFINITY;
 #pragma unroll
-    for (int e = 0; e < E; ++e) { kt = max(kt, fkey(et[e])); kd = max(kd, fkey(ed[e])); }
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = st4[i * kThreads + tid], c = sd4[i * kThreads + tid];
+      mt = fmaxf(fmaxf(mt, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
+      md = fmaxf(fmaxf(md, fmaxf(c.x, c.y)), fmaxf(c.z, c.w));
+    }
+    uint32_t kt = fkey(mt), kd = fkey(md);
     block_max_u32x2(kt, kd, sm, slot);
-    const float mt = fkey_inv(kt), md = fkey_inv(kd);
+    mt = fkey_inv(kt);
+    md = fkey_inv(kd);
+    // pass 2: canonical exp sums; the owner of element d keeps its two exponentials
     float zt = 0.0f, zd = 0.0f;
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      et[e] = spec_expf(__fsub_rn(et[e], mt));
-      ed[e] = spec_expf(__fsub_rn(ed[e], md));
-      zt = __fadd_rn(zt, et[e]);
-      zd = __fadd_rn(zd, ed[e]);
-    }
-    block_sum2(zt, zd, sm, slot);  // zt, zd now hold Zt, Zd
-    // the owner of element d evaluates the accept test (flag/pq are rewritten only after two more
-    // block barriers of the next row, so a single buffer is race-free)
-    const int fs = 0;
-    {
-      const int fd = d >> 2;
-      if ((fd & (kThreads - 1)) == tid) {
-        float etd = 0.0f, edd = 0.0f;
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = st4[i * kThreads + tid], c = sd4[i * kThreads + tid];
+      const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (4 * (i * kThreads + tid) + c == d) { etd = et[4 * i + c]; edd = ed[4 * i + c]; }
-        const float pdv = __fdiv_rn(etd, zt), qdv = __fdiv_rn(edd, zd);
-        sm.flag[fs] = (__fmul_rn(uu, qdv) < pdv) ? 1 : 0;
-        sm.pq[fs][0] = pdv;
-        sm.pq[fs][1] = qdv;
+      for (int q = 0; q < 4; ++q) {
+        zt = __fadd_rn(zt, spec_expf(__fsub_rn(av[q], mt)));
+        zd = __fadd_rn(zd, spec_expf(__fsub_rn(cv[q], md)));
       }
     }
-    __syncthreads();
-    const int acc = sm.flag[fs];
-    const float pdv = sm.pq[fs][0], qdv = sm.pq[fs][1];
+    block_sum2(zt, zd, sm, slot);  // zt, zd now hold Zt, Zd
+    // the owner of element d evaluates the accept test and publishes the per-token outputs itself
+    const bool owner = ((d >> 2) & (kThreads - 1)) == tid;
+    int rej = 0;
+    if (owner) {
+      const float* rt = stage_buf + st * 2 * V;
+      const float pdv = __fdiv_rn(spec_expf(__fsub_rn(rt[d], mt)), zt), qdv = __fdiv_rn(spec_expf(__fsub_rn(rt[V + d], md)), zd);
+      rej = (__fmul_rn(uu, qdv) < pdv) ? 0 : 1;
+      accept[row] = (unsigned char)(rej ^ 1);
+      if (p_d_out) p_d_out[row] = pdv;
+      if (q_d_out) q_d_out[row] = qdv;
+      if (!rej) {
+        out_idx[row] = d;
+        atomicAdd(&n_accept[b * seg.S + j], 1);
+      } else {
+        atomicMin(&first_reject[b * seg.S + j], pos - seg.begin[j]);
+      }
+    }
+    const int acc = __syncthreads_or(rej) ? 0 : 1;
     int out = d;
-    if (!acc) {  // block-uniform
+    if (!acc) {  // block-uniform: residual resample from the staged logits
       const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
       float4 nz[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) nz[i] = ldg_stream(pn + i * kThreads + tid);
+      float pv[NV * 4], rv[NV * 4];
       int anyp = 0;
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const float pv = __fdiv_rn(et[e], zt);
-        float rv = __fsub_rn(pv, __fdiv_rn(ed[e], zd));
-        rv = rv > 0.0f ? rv : 0.0f;
-        anyp |= (rv > 0.0f) ? 1 : 0;
-        ed[e] = rv;   // residual
-        et[e] = pv;   // target probability
+      for (int i = 0; i < NV; ++i) {
+        const float4 a = st4[i * kThreads + tid], c = sd4[i * kThreads + tid];
+        const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float p1 = __fdiv_rn(spec_expf(__fsub_rn(av[q], mt)), zt);
+          float r1 = __fsub_rn(p1, __fdiv_rn(spec_expf(__fsub_rn(cv[q], md)), zd));
+          r1 = r1 > 0.0f ? r1 : 0.0f;
+          anyp |= (r1 > 0.0f) ? 1 : 0;
+          pv[4 * i + q] = p1;
+          rv[4 * i + q] = r1;
+        }
       }
       anyp = __syncthreads_or(anyp);
       float best = -1.0f;
@@ -340,24 +399,18 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
       for (int i = 0; i < NV; ++i) {
         const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float num = anyp ? ed[4 * i + c] : et[4 * i + c];
-          const float r = __fdiv_rn(num, nn[c]);
-          if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; }
+        for (int q = 0; q < 4; ++q) {
+          const float r = __fdiv_rn(anyp ? rv[4 * i + q] : pv[4 * i + q], nn[q]);
+          if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + q; }
         }
       }
       const unsigned long long w = block_max_u64(pack_best(best, bi), sm, slot);
       out = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
       if (out == 0x7FFFFFFF) out = 0;
+      if (tid == 0) out_idx[row] = out;
     }
-    if (tid == 0) {
-      out_idx[row] = out;
-      accept[row] = (unsigned char)acc;
-      if (p_d_out) p_d_out[row] = pdv;
-      if (q_d_out) q_d_out[row] = qdv;
-      if (acc) atomicAdd(&n_accept[b * seg.S + j], 1);
-      else atomicMin(&first_reject[b * seg.S + j], pos - seg.begin[j]);
-    }
+    // (no trailing barrier: the last shared-memory reads of stage st are always followed by a block reduction barrier
+    //  before the next iteration's prefetch can target that stage)
   }
   // ---- last CTA finalises the per-image / batch scan (integer atomics => deterministic) ----
   __threadfence();
@@ -502,13 +555,21 @@ extern "C" int sdvar_verify_accept_resample(const float* xt, const float* xd, co
   ProfileScope prof(st, FAM_VERIFY, (double)B * L * (8.0 * V + 17.0));
   k4_init_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(first_reject, n_accept, B, seg);
   SDVAR_LAUNCH_CHECK();
-  const int grid = row_grid((long long)B * L, 2);
+  const size_t k4_smem = (size_t)2 * 2 * V * 4 + 64;          // two stages x (target row + draft row) + mbarriers
+  const int per_sm = (int)((220 * 1024) / (k4_smem + 1024)) < 3 ? (int)((220 * 1024) / (k4_smem + 1024)) : 3;
+  SDVAR_REQUIRE(per_sm >= 1, "V=%d rows do not fit the shared-memory ring", V);
+  const int grid = row_grid((long long)B * L, per_sm);
 #define SDVAR_K4(NV)                                                                                               \
-  case NV:                                                                                                         \
-    k4_verify_kernel<NV><<<grid, kThreads, 0, st>>>(xt, xd, draft_idx, u, noise, B, L, seg, out_idx, accept,      \
-                                                    p_d_out, q_d_out, first_reject, n_accept, accepted_stages,    \
-                                                    summary, workspace);                                           \
-    break;
+  case NV: {                                                                                                       \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      SDVAR_CUDA(cudaFuncSetAttribute(k4_verify_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem)); \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    k4_verify_kernel<NV><<<grid, kThreads, k4_smem, st>>>(xt, xd, draft_idx, u, noise, B, L, seg, out_idx, accept, \
+                                                          p_d_out, q_d_out, first_reject, n_accept, accepted_stages, \
+                                                          summary, workspace);                                     \
+  } break;
   switch (V / 1024) {
     SDVAR_K4(1) SDVAR_K4(2) SDVAR_K4(4) SDVAR_K4(8)
     default:
