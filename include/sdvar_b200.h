@@ -165,6 +165,12 @@ int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, const sdvar_
                     int Lq, int Lmax, int Lmax_pad, int kv_off, const int* seg_begin_host, int S, float scale,
                     const float* logit_bound_log, sdvar_bf16* out, void* stream);
 
+/* ---- decoder boundary ------------------------------------------------------------
+ * GroupNorm(32 groups, eps, affine) optionally followed by SiLU on channels-last bf16 activations (reference
+ * models/basic_vae.py:18-19, 57-59).  x, y: (N, H*W, C) with C contiguous; y may alias x.  scratch: N*128*64 floats. */
+int sdvar_groupnorm_silu_nhwc(const sdvar_bf16* x, int N, int HW, int C, const float* gamma, const float* beta, float eps,
+                              int silu, sdvar_bf16* y, float* scratch, void* stream);
+
 /* ---- whole transformer pass (the launch sequence of one stage / one verify window) -----------
  * Device-pointer table of one VAR model in the engine's packed layout (bf16 weights, fp32 vectors).
  * Replaces the python block loop models/var.py:195-197 / :973-976 / :1051-1055. */

@@ -24,6 +24,7 @@ EXPORTS = [
     "sdvar_sample_cfg_topk_topp", "sdvar_verify_accept_resample", "sdvar_verify_top1", "sdvar_vq_next_input",
     "sdvar_embed_next_map", "sdvar_first_map", "sdvar_ln_modulate", "sdvar_silu_bf16", "sdvar_f32_to_bf16",
     "sdvar_gemm_bf16", "sdvar_attention", "sdvar_var_forward", "sdvar_profile_begin", "sdvar_profile_end",
+    "sdvar_groupnorm_silu_nhwc",
 ]
 PROFILE_FAMILIES = ("gemm", "attention", "ln_modulate", "sample", "verify", "vq", "embed", "misc")
 
@@ -176,3 +177,8 @@ def profile_end() -> dict:
     ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
     _check(lib().sdvar_profile_end(ms, work, cnt), "sdvar_profile_end")
     return {PROFILE_FAMILIES[i]: (ms[i], work[i], int(cnt[i])) for i in range(n)}
+
+
+def groupnorm_silu_nhwc(x, N, HW, Cc, gamma, beta, eps, silu, y, scratch):
+    _check(lib().sdvar_groupnorm_silu_nhwc(C.c_void_p(x.data_ptr()), N, HW, Cc, ptr(gamma), ptr(beta), C.c_float(eps), int(silu),
+                                           C.c_void_p(y.data_ptr()), ptr(scratch), stream_ptr()), "sdvar_groupnorm_silu_nhwc")

@@ -34,6 +34,17 @@ int check_arch() {
   return cached_rc;
 }
 
+int sm_count() {
+  static thread_local int dev_cached = -1, sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != dev_cached) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    dev_cached = dev;
+  }
+  return sms;
+}
+
 // ---- profiling ----------------------------------------------------------------------------------------
 struct ProfRec { cudaEvent_t a, b; int family; double work; };
 static std::mutex g_prof_mu;

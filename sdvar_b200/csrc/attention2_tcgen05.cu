@@ -369,9 +369,7 @@ int launch_onepass(const void* q, const void* k_cache, const void* vT_cache, int
     SDVAR_CUDA(cudaFuncSetAttribute(attention_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int grid = p.n_items < sms ? p.n_items : sms;
   attention_onepass_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmQ, tmK, tmV, p);
   SDVAR_LAUNCH_CHECK();

@@ -14,6 +14,7 @@ namespace sdvar {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_arch();  // SDVAR_OK iff the current device is sm_100
+int sm_count();    // multiprocessor count of the current device (cached per thread)
 
 #define SDVAR_REQUIRE(cond, ...)                     \
   do {                                               \

@@ -206,9 +206,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, 
     SDVAR_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int clusters = tiles < sms / 2 ? tiles : sms / 2;
   gemm2_kernel<EPI><<<2 * clusters, kThreads, kSmemBytes, st>>>(tmA, tmB, M, N, K, ep);

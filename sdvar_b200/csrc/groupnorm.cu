@@ -1,0 +1,131 @@
+// groupnorm.cu -- GroupNorm(32 groups, eps, affine) [+ SiLU] on channels-last bf16 activations, for the VQVAE decoder that
+// turns the path's f_hat into pixels (reference models/basic_vae.py:18-19 `Normalize`, :57-59 `F.silu(norm(x))`).
+//
+// The decoder is the boundary right after the hot path; its convolutions stay on cuDNN for now, but PyTorch's
+// GroupNorm falls back to NCHW copies for channels-last bf16 (63 ms + 60 ms of layout copies per 64-image batch, measured), so
+// this HBM-bound piece is done here: two passes over the tensor (statistics, then normalise+SiLU), 16-byte vector accesses,
+// deterministic two-stage reduction (per-block partials, summed in a fixed order by every consumer).
+#include "common.cuh"
+
+namespace sdvar {
+
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxC = 1024;
+
+// partial[(n*nblk + blk)*2*32 + g*2 + {0,1}] = sum / sum of squares over this block's pixels
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pix_per_blk, float* __restrict__ partial) {
+  __shared__ float s_sum[32], s_sq[32];
+  const int n = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int vec_per_pix = C >> 3;                 // 8 channels (16 bytes) per vector
+  const int cg = C >> 5;                          // channels per group
+  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int p0 = blk * pix_per_blk, p1 = min(p0 + pix_per_blk, HW);
+  const long long base = (long long)n * HW * C;
+  const int total = (p1 - p0) * vec_per_pix;
+  // blockDim.x is a multiple of vec_per_pix (host guarantees it), so a thread keeps one fixed 8-channel vector index and
+  // accumulates its 8 channels in registers over all its pixels; groups are combined once at the end
+  float acc_s[8], acc_q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { acc_s[k] = 0.f; acc_q[k] = 0.f; }
+  const int v = threadIdx.x % vec_per_pix;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pix = p0 + i / vec_per_pix;
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + base + (long long)pix * C + v * 8);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(h[k]);
+      acc_s[2 * k] += f.x; acc_q[2 * k] += f.x * f.x;
+      acc_s[2 * k + 1] += f.y; acc_q[2 * k + 1] += f.y * f.y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int g = (v * 8 + k) / cg;
+    atomicAdd(&s_sum[g], acc_s[k]);
+    atomicAdd(&s_sq[g], acc_q[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float* o = partial + ((long long)n * nblk + blk) * 64;
+    o[2 * threadIdx.x] = s_sum[threadIdx.x];
+    o[2 * threadIdx.x + 1] = s_sq[threadIdx.x];
+  }
+}
+
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pix_per_blk, int nblk_stats, const float* __restrict__ partial,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu, __nv_bfloat16* __restrict__ y) {
+  __shared__ float s_mean[32], s_rstd[32];
+  __shared__ float s_a[kGnMaxC], s_b[kGnMaxC];    // per-channel scale / shift: y = x*a + b
+  const int n = blockIdx.y, blk = blockIdx.x;
+  const int cg = C >> 5, vec_per_pix = C >> 3;
+  if (threadIdx.x < 32) {
+    float s = 0.f, q = 0.f;
+    const float* pp = partial + (long long)n * nblk_stats * 64 + 2 * threadIdx.x;
+    for (int b = 0; b < nblk_stats; ++b) { s += pp[b * 64]; q += pp[b * 64 + 1]; }   // fixed order => deterministic
+    const float cnt = (float)HW * (float)cg;
+    const float mean = s / cnt;
+    const float var = fmaxf(q / cnt - mean * mean, 0.f);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kGnThreads) {
+    const int g = c / cg;
+    const float a = s_rstd[g] * gamma[c];
+    s_a[c] = a;
+    s_b[c] = beta[c] - s_mean[g] * a;
+  }
+  __syncthreads();
+  const int p0 = blk * pix_per_blk, p1 = min(p0 + pix_per_blk, HW);
+  const long long base = (long long)n * HW * C;
+  const int total = (p1 - p0) * vec_per_pix;
+  for (int i = threadIdx.x; i < total; i += kGnThreads) {
+    const int pix = p0 + i / vec_per_pix, v = i % vec_per_pix;
+    const long long off = base + (long long)pix * C + v * 8;
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + off);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(h[k]);
+      float y0 = f.x * s_a[v * 8 + 2 * k] + s_b[v * 8 + 2 * k];
+      float y1 = f.y * s_a[v * 8 + 2 * k + 1] + s_b[v * 8 + 2 * k + 1];
+      if (silu) { y0 = y0 / (1.0f + __expf(-y0)); y1 = y1 / (1.0f + __expf(-y1)); }
+      o[k] = pack_bf16x2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(y + off) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace sdvar
+
+using namespace sdvar;
+
+// x, y: (N, H*W, C) channels-last bf16 (y may alias x); gamma/beta fp32 [C]; scratch >= N*nblk*64 floats with
+// nblk = min(ceil(HW/32), 128).  32 groups (reference Normalize), C % 32 == 0, C % 8 == 0, C <= 1024.
+extern "C" int sdvar_groupnorm_silu_nhwc(const sdvar_bf16* x, int N, int HW, int C, const float* gamma, const float* beta, float eps,
+                                         int silu, sdvar_bf16* y, float* scratch, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(x && y && gamma && beta && scratch, "NULL argument");
+  SDVAR_REQUIRE(N > 0 && HW > 0 && C % 32 == 0 && C % 8 == 0 && C <= kGnMaxC, "bad geometry N=%d HW=%d C=%d", N, HW, C);
+  SDVAR_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "16-byte alignment");
+  int nblk = (HW + 31) / 32;
+  if (nblk > 128) nblk = 128;
+  const int ppb = (HW + nblk - 1) / nblk;
+  nblk = (HW + ppb - 1) / ppb;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfileScope prof(st, FAM_MISC, (double)N * HW * C * 2.0 * 3.0);
+  const int vpp = C >> 3;
+  SDVAR_REQUIRE(vpp <= kGnThreads, "C too large");
+  const int stat_threads = (kGnThreads / vpp) * vpp;
+  gn_stats_kernel<<<dim3(nblk, N), stat_threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), HW, C, ppb, scratch);
+  SDVAR_LAUNCH_CHECK();
+  gn_apply_kernel<<<dim3(nblk, N), kGnThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), HW, C, ppb, nblk, scratch, gamma, beta, eps,
+                                                       silu, reinterpret_cast<__nv_bfloat16*>(y));
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}

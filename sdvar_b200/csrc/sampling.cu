@@ -493,9 +493,7 @@ static int fill_seg(SegTable& seg, const int* seg_begin_host, int S, int L, cons
 }
 
 static int row_grid(long long rows, int blocks_per_sm) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const long long g = (long long)sms * blocks_per_sm;
   return (int)(rows < g ? rows : g);
 }

@@ -21,6 +21,28 @@ def _gn(c: int) -> nn.GroupNorm:
     return nn.GroupNorm(32, c, eps=1e-6, affine=True)
 
 
+_GN_SCRATCH = {}
+
+
+def _gn_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool) -> torch.Tensor:
+    """GroupNorm (+SiLU).  On the device path (bf16, channels-last) this is the fused libsdvar kernel: PyTorch's GroupNorm
+    round-trips channels-last bf16 through NCHW copies (measured 120 ms of a 140 ms decode of 64 images)."""
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) \
+            and x.shape[1] % 32 == 0 and norm.num_groups == 32:
+        from .. import _cabi
+        N, C, H, W = x.shape
+        if getattr(norm, "_w32", None) is None or norm._w32.device != x.device:
+            norm._w32, norm._b32 = norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous()
+        key = (x.device, N)
+        if key not in _GN_SCRATCH:
+            _GN_SCRATCH[key] = torch.empty(N * 128 * 64, device=x.device, dtype=torch.float32)
+        y = torch.empty_like(x)
+        _cabi.groupnorm_silu_nhwc(x, N, H * W, C, norm._w32, norm._b32, norm.eps, silu, y, _GN_SCRATCH[key])
+        return y
+    y = norm(x)
+    return F.silu(y) if silu else y
+
+
 class _Res(nn.Module):
     def __init__(self, cin: int, cout: int):
         super().__init__()
@@ -30,7 +52,7 @@ class _Res(nn.Module):
             self.nin_shortcut = nn.Conv2d(cin, cout, 1)
 
     def forward(self, x):
-        h = self.conv2(F.silu(self.norm2(self.conv1(F.silu(self.norm1(x))))))
+        h = self.conv2(_gn_act(self.norm2, self.conv1(_gn_act(self.norm1, x, True)), True))
         return (self.nin_shortcut(x) if hasattr(self, "nin_shortcut") else x) + h
 
 
@@ -41,7 +63,7 @@ class _SpatialAttn(nn.Module):
 
     def forward(self, x):
         B, C, H, W = x.shape
-        q, k, v = self.qkv(self.norm(x)).reshape(B, 3, C, H * W).unbind(1)
+        q, k, v = self.qkv(_gn_act(self.norm, x, False)).reshape(B, 3, C, H * W).unbind(1)
         o = F.scaled_dot_product_attention(q.transpose(1, 2).unsqueeze(1), k.transpose(1, 2).unsqueeze(1),
                                            v.transpose(1, 2).unsqueeze(1), scale=C ** -0.5)   # softmax(q k^T / sqrt(C)) v
         return x + self.proj_out(o.squeeze(1).transpose(1, 2).reshape(B, C, H, W))
@@ -100,7 +122,7 @@ class Decoder(nn.Module):
         h = self.mid(self.conv_in(z))
         for lv in reversed(range(len(self.up))):
             h = self.up[lv](h)
-        return self.conv_out(F.silu(self.norm_out(h)))
+        return self.conv_out(_gn_act(self.norm_out, h, True))
 
 
 class VQVAE(nn.Module):

@@ -317,3 +317,19 @@ def _attn_case(cuda_lib, imgs, H, ls_window, kv_off, l2norm, seed, clamp_head=Fa
 def test_qkv_epilogue_and_attention(cuda_lib, imgs, H, ls, kv_off, l2):
     _attn_case(cuda_lib, imgs, H, ls, kv_off, l2, 0)
     _attn_case(cuda_lib, imgs, H, ls, kv_off, l2, 1, clamp_head=True)
+
+
+@pytest.mark.parametrize("N,C,H,silu", [(2, 160, 32, True), (3, 320, 16, True), (2, 640, 16, False), (1, 32, 8, True)])
+def test_groupnorm_silu_nhwc_vs_torch(cuda_lib, N, C, H, silu):
+    """decoder boundary: fused GroupNorm(32)+SiLU on channels-last bf16 vs torch fp32 on the same bf16 input"""
+    x = (hashed("gn.x", 0, (N, C, H, H), 1.5) + 0.4).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    g = (1.0 + hashed("gn.g", 1, (C,), 0.2)).to(DEV)
+    b = hashed("gn.b", 2, (C,), 0.2).to(DEV)
+    ref = torch.nn.functional.group_norm(x.float(), 32, g, b, eps=1e-6)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    y = torch.empty_like(x)
+    scratch = torch.empty(N * 128 * 64, device=DEV)
+    cuda_lib.groupnorm_silu_nhwc(x, N, H * H, C, g, b, 1e-6, silu, y, scratch)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.allclose(y.float(), ref, rtol=2 ** -7, atol=1e-2), float((y.float() - ref).abs().max())
