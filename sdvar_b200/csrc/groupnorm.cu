@@ -41,11 +41,20 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pix_per_
       acc_s[2 * k + 1] += f.y; acc_q[2 * k + 1] += f.y * f.y;
     }
   }
+  // deterministic block reduction: per-thread channel partials go to shared memory, then 64 threads (32 groups x {sum, sumsq})
+  // each add up their group's channels over the threads that own them, in a fixed order
+  __shared__ float s_part[16][kGnThreads];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int g = (v * 8 + k) / cg;
-    atomicAdd(&s_sum[g], acc_s[k]);
-    atomicAdd(&s_sq[g], acc_q[k]);
+  for (int k = 0; k < 8; ++k) { s_part[k][threadIdx.x] = acc_s[k]; s_part[8 + k][threadIdx.x] = acc_q[k]; }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    float tsum = 0.f;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      const int vv = c >> 3, kk = (c & 7) + which * 8;
+      for (int t = vv; t < (int)blockDim.x; t += vec_per_pix) tsum += s_part[kk][t];
+    }
+    if (which == 0) s_sum[g] = tsum; else s_sq[g] = tsum;
   }
   __syncthreads();
   if (threadIdx.x < 32) {
