@@ -207,3 +207,26 @@ def test_sd_loop_invariants_after_rejections(cuda_lib, rule, gamma):
     for i in range(t.depth):
         assert torch.equal(k_loop[i][:, :, :t.L], e.k_cache[i][:, :, :t.L]), i
         assert torch.equal(v_loop[i][:, :, :, :t.L], e.v_cache[i][:, :, :, :t.L]), i
+
+
+def test_512px_pyramid_shared_aln_target_sd_loop(cuda_lib):
+    """BASELINE.json configs[3] shape at toy depth: 512 px pyramid (patch_nums up to 32, L=2240), target with shared adaLN
+    (the d36 layout), draft without (fixes D10/D11).  Invariants as above + teacher-forced logits vs the oracle."""
+    from oracle.ref_model import RefVAR, RefVQ, ReplayNoise
+    P512 = (1, 2, 3, 4, 6, 9, 13, 18, 24, 32)
+    vae, d, t, sd, sds = _build(P512, 2, 2, shared_t=True, gamma_bias=0.5, init_head=1.0)
+    B, lab = 2, torch.tensor([10, 20], device=DEV)
+    img, idxs, f_hat = sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, gamma=2, cfg=1.5, top_k=900, top_p=0.96,
+                                                                     noise=ReplayNoise(4, DEV), return_tokens=True)
+    K = len(P512)
+    assert img.shape == (B, 3, 512, 512) and bool(torch.isfinite(img).all())
+    assert sum(sd.last_stats["advance"]) == K and [i.shape[1] for i in idxs] == t.ls and t.L == 2240
+    vq = RefVQ(sds["vae"], P512)
+    x_in, f_ref = _teacher_input(vq, [i.cpu() for i in idxs])
+    f_ref, _ = vq.next_input(K - 1, f_ref, idxs[-1].cpu())
+    assert torch.allclose(f_hat.cpu(), f_ref, rtol=1e-4, atol=1e-4)
+    got = t(lab, x_in.to(DEV)).cpu()
+    ref = RefVAR(sds["t"], P512, mm="bf16").forward_teacher(lab.cpu(), x_in)
+    scale = float(ref.abs().max())
+    err = (got - ref).abs()
+    assert float(err.max()) < 8e-3 * scale and float(err.mean()) < 1e-3 * scale, (float(err.max()), float(err.mean()), scale)
