@@ -102,8 +102,11 @@ def verify_tokens(xt_NV, xd_NV, draft_idx_N, u_N, noise_NV):
     """Per token: p=softmax(xt), q=softmax(xd); accept iff u*q[d] < p[d]; on reject
     out = argmax(max(0,p-q)/noise) (if the residual is identically 0: argmax(p/noise)).
     Returns (out_idx int64 (N,), accept bool (N,), p_d, q_d)."""
-    p = xt_NV.softmax(dim=-1)
-    q = xd_NV.softmax(dim=-1)
+    # exp * (1/Z), the association the C spec / kernel use (one division per row)
+    et = (xt_NV - xt_NV.amax(dim=-1, keepdim=True)).exp()
+    ed = (xd_NV - xd_NV.amax(dim=-1, keepdim=True)).exp()
+    p = et * (1.0 / et.sum(dim=-1, keepdim=True))
+    q = ed * (1.0 / ed.sum(dim=-1, keepdim=True))
     ar = torch.arange(p.shape[0])
     p_d, q_d = p[ar, draft_idx_N], q[ar, draft_idx_N]
     accept = (u_N * q_d) < p_d

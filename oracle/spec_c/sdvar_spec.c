@@ -182,14 +182,16 @@ int sdvar_spec_verify(const float* xt, const float* xd, const long long* draft_i
       for (int v = 0; v < V; ++v) { et[v] = sdvar_spec_expf(t[v] - mt); ed[v] = sdvar_spec_expf(d[v] - md); }
       const float Zt = canon_sum(et, V, NULL, 0), Zd = canon_sum(ed, V, NULL, 0);
       const long long di = draft_idx[row];
-      const float pd = et[di] / Zt, qd = ed[di] / Zd;
+      /* probabilities are exp * (1/Z): one IEEE division per row, one multiplication per element */
+      const float iZt = 1.0f / Zt, iZd = 1.0f / Zd;
+      const float pd = et[di] * iZt, qd = ed[di] * iZd;
       const int acc = (u[row] * qd) < pd;
       long long o = di;
       if (!acc) {
         int anypos = 0;
         for (int v = 0; v < V; ++v) {
-          const float pv = et[v] / Zt;
-          float rv = pv - ed[v] / Zd;
+          const float pv = et[v] * iZt;
+          float rv = pv - ed[v] * iZd;
           rv = rv > 0.0f ? rv : 0.0f;
           r[v] = rv;
           anypos |= rv > 0.0f;
@@ -197,7 +199,7 @@ int sdvar_spec_verify(const float* xt, const float* xd, const long long* draft_i
         float best = -1.0f;
         o = 0;
         for (int v = 0; v < V; ++v) {
-          const float num = anypos ? r[v] : et[v] / Zt;
+          const float num = anypos ? r[v] : et[v] * iZt;
           const float q = num / noise[row * V + v];
           if (q > best) { best = q; o = v; }
         }

@@ -325,8 +325,8 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
     const int d = (int)draft_idx[row];
     const float uu = u[row];
     mbar_wait_par(&full[st], (k >> 1) & 1);
-    const float4* st4 = reinterpret_cast<const float4*>(stage_buf + st * 2 * V);
-    const float4* sd4 = st4 + V / 4;
+    float4* st4 = reinterpret_cast<float4*>(stage_buf + st * 2 * V);
+    float4* sd4 = st4 + V / 4;
     // pass 1: row maxima (order-independent)
     float mt = -INFINITY, md = -INFINITY;
 #pragma unroll
@@ -344,20 +344,27 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float4 a = st4[i * kThreads + tid], c = sd4[i * kThreads + tid];
-      const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+      float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        zt = __fadd_rn(zt, spec_expf(__fsub_rn(av[q], mt)));
-        zd = __fadd_rn(zd, spec_expf(__fsub_rn(cv[q], md)));
+        av[q] = spec_expf(__fsub_rn(av[q], mt));
+        cv[q] = spec_expf(__fsub_rn(cv[q], md));
+        zt = __fadd_rn(zt, av[q]);
+        zd = __fadd_rn(zd, cv[q]);
       }
+      // the exponentials replace the staged logits (each thread rewrites only the chunks it owns), so neither the accept
+      // test nor a residual resample has to exponentiate again
+      st4[i * kThreads + tid] = make_float4(av[0], av[1], av[2], av[3]);
+      sd4[i * kThreads + tid] = make_float4(cv[0], cv[1], cv[2], cv[3]);
     }
     block_sum2(zt, zd, sm, slot);  // zt, zd now hold Zt, Zd
+    const float izt = __fdiv_rn(1.0f, zt), izd = __fdiv_rn(1.0f, zd);
     // the owner of element d evaluates the accept test and publishes the per-token outputs itself
     const bool owner = ((d >> 2) & (kThreads - 1)) == tid;
     int rej = 0;
     if (owner) {
       const float* rt = stage_buf + st * 2 * V;
-      const float pdv = __fdiv_rn(spec_expf(__fsub_rn(rt[d], mt)), zt), qdv = __fdiv_rn(spec_expf(__fsub_rn(rt[V + d], md)), zd);
+      const float pdv = __fmul_rn(rt[d], izt), qdv = __fmul_rn(rt[V + d], izd);
       rej = (__fmul_rn(uu, qdv) < pdv) ? 0 : 1;
       accept[row] = (unsigned char)(rej ^ 1);
       if (p_d_out) p_d_out[row] = pdv;
@@ -384,8 +391,8 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
         const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float p1 = __fdiv_rn(spec_expf(__fsub_rn(av[q], mt)), zt);
-          float r1 = __fsub_rn(p1, __fdiv_rn(spec_expf(__fsub_rn(cv[q], md)), zd));
+          const float p1 = __fmul_rn(av[q], izt);
+          float r1 = __fsub_rn(p1, __fmul_rn(cv[q], izd));
           r1 = r1 > 0.0f ? r1 : 0.0f;
           anyp |= (r1 > 0.0f) ? 1 : 0;
           pv[4 * i + q] = p1;
