@@ -75,6 +75,20 @@ __device__ __forceinline__ float block_sum(float a, RedSmem& s, int& slot) {
   slot ^= 1;
   return a;
 }
+// canonical float sum and an integer count with a single barrier
+__device__ __forceinline__ void block_sum_fi(float& a, int& c, RedSmem& s, int& slot) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, off));
+  c = __reduce_add_sync(0xffffffffu, c);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s.f[slot][0][w] = a; s.i[slot][w] = c; }
+  __syncthreads();
+  a = s.f[slot][0][0];
+  c = s.i[slot][0];
+#pragma unroll
+  for (int k = 1; k < kWarps; ++k) { a = __fadd_rn(a, s.f[slot][0][k]); c += s.i[slot][k]; }
+  slot ^= 1;
+}
 __device__ __forceinline__ int block_sum_int(int c, RedSmem& s, int& slot) {
   c = __reduce_add_sync(0xffffffffu, c);
   const int w = threadIdx.x >> 5;
@@ -118,8 +132,11 @@ __device__ __forceinline__ unsigned long long pack_best(float r, int idx) {
 // ================================================================================================
 // K3
 // ================================================================================================
+// Register diet: a thread keeps only the order-preserving KEYS of its 4*NV mixed logits (the logit is the exact inverse of
+// its key) plus, during the top-p search, their probabilities; exponentials are recomputed (bit-identically) for the final
+// draw.  ~60 registers -> four 256-thread CTAs per SM, which is what hides the serial latency of the canonical reductions.
 template <int NV>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 4)
 k3_sample_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int in_off, SegTable seg, int top_k, float thr,
                  const float* __restrict__ noise, long long* __restrict__ idx_out, float* __restrict__ mixed_out,
                  float* __restrict__ prob_out) {
@@ -129,13 +146,13 @@ k3_sample_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int 
   int slot = 0;
   const int tid = threadIdx.x;
   const long long rows = (long long)B * L;
+  const uint32_t kneg = fkey(-INFINITY);
   for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
     const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
     const int j = seg_of(seg, pos);
     const float t1 = seg.t1[j], t2 = seg.t2[j];
     const float4* pc = reinterpret_cast<const float4*>(logits + ((long long)b * in_ld + in_off + pos) * V);
     const float4* pu = reinterpret_cast<const float4*>(logits + ((long long)(B + b) * in_ld + in_off + pos) * V);
-    float x[E];
     uint32_t key[E];
     {
       float4 a[NV], c[NV];
@@ -143,69 +160,90 @@ k3_sample_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int 
       for (int i = 0; i < NV; ++i) { a[i] = ldg_stream(pc + i * kThreads + tid); c[i] = ldg_stream(pu + i * kThreads + tid); }
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        x[4 * i + 0] = __fsub_rn(__fmul_rn(a[i].x, t1), __fmul_rn(c[i].x, t2));
-        x[4 * i + 1] = __fsub_rn(__fmul_rn(a[i].y, t1), __fmul_rn(c[i].y, t2));
-        x[4 * i + 2] = __fsub_rn(__fmul_rn(a[i].z, t1), __fmul_rn(c[i].z, t2));
-        x[4 * i + 3] = __fsub_rn(__fmul_rn(a[i].w, t1), __fmul_rn(c[i].w, t2));
+        key[4 * i + 0] = fkey(__fsub_rn(__fmul_rn(a[i].x, t1), __fmul_rn(c[i].x, t2)));
+        key[4 * i + 1] = fkey(__fsub_rn(__fmul_rn(a[i].y, t1), __fmul_rn(c[i].y, t2)));
+        key[4 * i + 2] = fkey(__fsub_rn(__fmul_rn(a[i].z, t1), __fmul_rn(c[i].z, t2)));
+        key[4 * i + 3] = fkey(__fsub_rn(__fmul_rn(a[i].w, t1), __fmul_rn(c[i].w, t2)));
       }
     }
-#pragma unroll
-    for (int e = 0; e < E; ++e) key[e] = fkey(x[e]);
 
-    // ---- top-k: K = key of the k-th largest (radix select, MSB first) ----
+    // ---- row max / min (exact, on keys) ----
+    uint32_t kmax = 0, kminc = 0;   // kminc = ~min
+#pragma unroll
+    for (int e = 0; e < E; ++e) { kmax = max(kmax, key[e]); kminc = max(kminc, ~key[e]); }
+    block_max_u32x2(kmax, kminc, sm, slot);
+    const float m = fkey_inv(kmax);
+
+    // ---- top-k: K = key of the k-th largest.  Midpoint bisection on the key VALUE range [min, max] with early exit:
+    // cL = #{key >= lo} (>= k) and cH = #{key >= hi} (< k) bracket the answer; once the bracket [lo,hi) holds exactly one key
+    // that key IS the k-th largest (one min-reduction fetches it); ~log2(V)+2 rounds instead of 32.  The result is the
+    // unique largest K with #{key >= K} >= k, i.e. exactly what the bit-serial search of the spec returns.
     if (top_k > 0 && top_k < V) {
-      uint32_t K = 0;
+      uint32_t lo = ~kminc, hi = kmax + 1u;
+      int cL = V, cH = 0;
 #pragma unroll 1
-      for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t tr = K | (1u << bit);
+      while (cL - cH > 1 && hi - lo > 1u) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
         int c = 0;
 #pragma unroll
-        for (int e = 0; e < E; ++e) c += (key[e] >= tr) ? 1 : 0;
-        if (block_sum_int(c, sm, slot) >= top_k) K = tr;
+        for (int e = 0; e < E; ++e) c += (key[e] >= mid) ? 1 : 0;
+        c = block_sum_int(c, sm, slot);
+        if (c >= top_k) { lo = mid; cL = c; } else { hi = mid; cH = c; }
       }
-      const uint32_t kneg = fkey(-INFINITY);
+      uint32_t K = lo;
+      if (cL - cH == 1 && hi - lo > 1u) {   // the smallest key that is still >= lo (min via max of the complement)
+        uint32_t mn = 0, z = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) mn = max(mn, (key[e] >= lo) ? ~key[e] : 0u);
+        block_max_u32x2(mn, z, sm, slot);
+        K = ~mn;
+      }
 #pragma unroll
       for (int e = 0; e < E; ++e)
-        if (key[e] < K) { x[e] = -INFINITY; key[e] = kneg; }
+        if (key[e] < K) key[e] = kneg;
     }
-
-    // ---- row max (exact, on keys) and exponentials ----
-    uint32_t kmax = 0, dummy = 0;
-#pragma unroll
-    for (int e = 0; e < E; ++e) kmax = max(kmax, key[e]);
-    block_max_u32x2(kmax, dummy, sm, slot);
-    const float m = fkey_inv(kmax);
-    float ex[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) ex[e] = spec_expf(__fsub_rn(x[e], m));
 
     // ---- top-p: remove v iff mass{key <= key_v} <= thr, never the max ----
     if (thr >= 0.0f) {
+      float p[E];
       float z = 0.0f;
 #pragma unroll
-      for (int e = 0; e < E; ++e) z = __fadd_rn(z, ex[e]);
+      for (int e = 0; e < E; ++e) { p[e] = spec_expf(__fsub_rn(fkey_inv(key[e]), m)); z = __fadd_rn(z, p[e]); }
       const float Z = block_sum(z, sm, slot);
-      float p[E];
+      float tot = 0.0f;
 #pragma unroll
-      for (int e = 0; e < E; ++e) p[e] = __fdiv_rn(ex[e], Z);
-      uint32_t K = 0;
+      for (int e = 0; e < E; ++e) { p[e] = __fdiv_rn(p[e], Z); tot = __fadd_rn(tot, p[e]); }
+      tot = block_sum(tot, sm, slot);      // canonical mass of the whole row = mass{key <= kmax}
+      // Midpoint bisection on the canonical masked mass with early exit: lo is good (mass{key<=lo} <= thr, nL = #{key<=lo}),
+      // hi is bad.  The mass only changes at key values, so once at most one key separates lo from hi no threshold in
+      // between can change the removed set {key <= lo}: the answer equals the spec's largest good threshold.
+      uint32_t lo = 0u, hi = kmax;
+      int nL = 0, nH = V;
+      if (tot <= thr) lo = kmax;           // everything is removable (the max itself is always kept)
 #pragma unroll 1
-      for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t tr = K | (1u << bit);
+      while (lo != kmax && nH - nL > 1 && hi - lo > 1u) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
         float a = 0.0f;
+        int c = 0;
 #pragma unroll
-        for (int e = 0; e < E; ++e) a = __fadd_rn(a, (key[e] <= tr) ? p[e] : 0.0f);
-        if (block_sum(a, sm, slot) <= thr) K = tr;
+        for (int e = 0; e < E; ++e) {
+          const bool in = key[e] <= mid;
+          a = __fadd_rn(a, in ? p[e] : 0.0f);
+          c += in ? 1 : 0;
+        }
+        block_sum_fi(a, c, sm, slot);
+        if (a <= thr) { lo = mid; nL = c; } else { hi = mid; nH = c; }
       }
 #pragma unroll
       for (int e = 0; e < E; ++e)
-        if (key[e] <= K && key[e] != kmax) { x[e] = -INFINITY; ex[e] = 0.0f; }
+        if (key[e] <= lo && key[e] != kmax) key[e] = kneg;
     }
 
     if (mixed_out != nullptr) {
       float4* po = reinterpret_cast<float4*>(mixed_out + row * V);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) stg_stream(po + i * kThreads + tid, make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]));
+      for (int i = 0; i < NV; ++i)
+        stg_stream(po + i * kThreads + tid, make_float4(fkey_inv(key[4 * i]), fkey_inv(key[4 * i + 1]), fkey_inv(key[4 * i + 2]), fkey_inv(key[4 * i + 3])));
     }
 
     if (noise != nullptr) {
@@ -213,9 +251,10 @@ k3_sample_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int 
       float4 nz[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) nz[i] = ldg_stream(pn + i * kThreads + tid);
+      float ex[E];
       float z = 0.0f;
 #pragma unroll
-      for (int e = 0; e < E; ++e) z = __fadd_rn(z, ex[e]);
+      for (int e = 0; e < E; ++e) { ex[e] = spec_expf(__fsub_rn(fkey_inv(key[e]), m)); z = __fadd_rn(z, ex[e]); }
       const float Z2 = block_sum(z, sm, slot);
       float best = -1.0f, bestp = 0.0f;
       int bi = 0x7FFFFFFF;
@@ -524,7 +563,7 @@ extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L
   SegTable seg;
   if (int rc = fill_seg(seg, seg_begin_host, S, L, t1_host, t2_host)) return rc;
   const long long rows = (long long)B * L;
-  const int grid = row_grid(rows, 2);
+  const int grid = row_grid(rows, 4);
   cudaStream_t st = (cudaStream_t)stream;
   ProfileScope prof(st, FAM_SAMPLE, (double)rows * (8.0 * V + (noise ? 4.0 * V + 8.0 : 0.0) + (mixed_out ? 4.0 * V : 0.0)));
 #define SDVAR_K3(NV)                                                                                          \
