@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 P256 = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)
+P512 = (1, 2, 3, 4, 6, 9, 13, 18, 24, 32)
 METRIC = "images/sec (d16->d30 SD, 256px)"
 
 
@@ -48,6 +49,8 @@ def parse():
     ap.add_argument("--top-k", type=int, default=900)
     ap.add_argument("--top-p", type=float, default=0.96)
     ap.add_argument("--accept-rule", default="speculative", choices=["speculative", "reference"])
+    ap.add_argument("--px", type=int, default=256, choices=[256, 512], help="256: patch_nums 1..16 (L=680); 512: 1..32 (L=2240)")
+    ap.add_argument("--shared-aln-target", action="store_true", help="target uses shared adaLN (the d36 layout, README.md:142-144)")
     ap.add_argument("--cpu-sample-images", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -125,7 +128,8 @@ def cpu_reference_run(args, n_images: int, steps: int, warmup: int, device_for_i
     cpu = lambda sd: {k: v.cpu() for k, v in sd.items()}
     vsd = cpu(vqvae_state_dict(ch=160, patch_nums=P256, device=device_for_init))
     d = RefVAR(cpu(var_state_dict(args.depth_draft, patch_nums=P256, seed=1, tag="draft", device=device_for_init)), P256)
-    t = RefVAR(cpu(var_state_dict(args.depth_target, patch_nums=P256, seed=2, tag="target", device=device_for_init)), P256)
+    t = RefVAR(cpu(var_state_dict(args.depth_target, patch_nums=P256, seed=2, tag="target", device=device_for_init,
+                                  shared_aln=args.shared_aln_target)), P256)
     vq, dec = RefVQ(vsd, P256), RefDecoder(vsd)
     lab = torch.randint(0, 1000, (n_images,), generator=torch.Generator().manual_seed(0))
     times = []
@@ -148,7 +152,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     has_cuda = torch.cuda.is_available()
-    workload = (f"SDVAR VAR-d{args.depth_draft} draft + VAR-d{args.depth_target} target, random-init, 256px, patch_nums 1..16, "
+    global P256
+    if args.px == 512:
+        P256 = P512          # every use below takes the selected pyramid
+    workload = (f"SDVAR VAR-d{args.depth_draft} draft + VAR-d{args.depth_target} target, random-init, {args.px}px, patch_nums 1..{P256[-1]}, "
                 f"batch {args.batch}/GPU, cfg={args.cfg}, top_k={args.top_k}, top_p={args.top_p}, gamma={args.gamma}, accept_rule={args.accept_rule}")
 
     if args.impl == "reference":
@@ -177,14 +184,16 @@ def main():
     from sdvar_b200.weights import var_state_dict, vqvae_state_dict
 
     torch.manual_seed(0)
-    vae, draft, target, sd = build_vae_var_speculative_decoding(dev, patch_nums=P256, depth_draft=args.depth_draft, depth_target=args.depth_target)
+    vae, draft, target, sd = build_vae_var_speculative_decoding(dev, patch_nums=P256, depth_draft=args.depth_draft, depth_target=args.depth_target,
+                                                                shared_aln_target=args.shared_aln_target)
     vae.load_state_dict(vqvae_state_dict(ch=160, patch_nums=P256, device=dev))
     draft.load_state_dict(var_state_dict(args.depth_draft, patch_nums=P256, seed=1, tag="draft", device=dev))
-    target.load_state_dict(var_state_dict(args.depth_target, patch_nums=P256, seed=2, tag="target", device=dev))
+    target.load_state_dict(var_state_dict(args.depth_target, patch_nums=P256, seed=2, tag="target", device=dev, shared_aln=args.shared_aln_target))
     B = args.batch
+    px = 16 * P256[-1]
     lab_host = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(rank)).pin_memory()
     lab_dev = lab_host.to(dev)
-    img_host = torch.empty(B, 3, 256, 256, dtype=torch.float32).pin_memory()
+    img_host = torch.empty(B, 3, px, px, dtype=torch.float32).pin_memory()
 
     def step(i: int, e2e: bool):
         lab = lab_host.to(dev, non_blocking=True) if e2e else lab_dev
@@ -241,7 +250,7 @@ def main():
                       "l2": "no flush: per-step working set (bf16 weights 4.6 GB + KV ring ~27 GB + logits) >> 126 MB L2",
                       "weights": "sdvar_b200.weights hashed init (seed 1 draft / 2 target / 0 vae)", "labels": "randint(0,1000) seed=rank"},
            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": B * 8,
-                   "d2h_bytes_per_step": B * 3 * 256 * 256 * 4},
+                   "d2h_bytes_per_step": B * 3 * px * px * 4},
            "gpu_launches": launches, "clocks": clocks,
            "accept_stats": {k: last_stats[k] for k in ("rounds", "target_passes", "draft_stages", "accepted_tokens", "rejected_tokens", "advance")}}
 
