@@ -250,19 +250,17 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
               if (__all_sync(0xffffffffu, nvalid >= 32)) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(ex2(fmaf(__uint_as_float(cur[i]), c, -mc)),
-                                                                  ex2(fmaf(__uint_as_float(cur[i + 1]), c, -mc)));
-                  l4[(i >> 1) & 3] += __low2float(b2) + __high2float(b2);
-                  pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+                  const float e0 = ex2(fmaf(__uint_as_float(cur[i]), c, -mc)), e1 = ex2(fmaf(__uint_as_float(cur[i + 1]), c, -mc));
+                  l4[(i >> 1) & 3] += e0 + e1;     // row sum in fp32 before rounding (rounding errors of P average out)
+                  pk[i >> 1] = pack_bf16x2(e0, e1);
                 }
               } else {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                   const float e0 = (i < nvalid) ? ex2(fmaf(__uint_as_float(cur[i]), c, -mc)) : 0.0f;
                   const float e1 = (i + 1 < nvalid) ? ex2(fmaf(__uint_as_float(cur[i + 1]), c, -mc)) : 0.0f;
-                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
-                  l4[(i >> 1) & 3] += __low2float(b2) + __high2float(b2);
-                  pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+                  l4[(i >> 1) & 3] += e0 + e1;
+                  pk[i >> 1] = pack_bf16x2(e0, e1);
                 }
               }
               if (cc == 0) ptx::mbar_wait(&p_empty[g], par ^ 1);   // PV of this group's previous tile has drained the P buffer
