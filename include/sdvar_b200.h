@@ -167,9 +167,17 @@ int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, const sdvar_
 
 /* ---- decoder boundary ------------------------------------------------------------
  * GroupNorm(32 groups, eps, affine) optionally followed by SiLU on channels-last bf16 activations (reference
- * models/basic_vae.py:18-19, 57-59).  x, y: (N, H*W, C) with C contiguous; y may alias x.  scratch: N*128*64 floats. */
-int sdvar_groupnorm_silu_nhwc(const sdvar_bf16* x, int N, int HW, int C, const float* gamma, const float* beta, float eps,
-                              int silu, sdvar_bf16* y, float* scratch, void* stream);
+ * models/basic_vae.py:18-19, 57-59).  x, y: (N, H*W, C) with C contiguous; y may alias x.  scratch: N*128*64 floats.
+ * pre_bias (nullable, fp32 [C]) is added to x before the statistics: the bias of the convolution that produced x, so that
+ * convolution can run bias-free (no separate bias pass over the activation). */
+int sdvar_groupnorm_silu_nhwc(const sdvar_bf16* x, const float* pre_bias, int N, int HW, int C, const float* gamma, const float* beta,
+                              float eps, int silu, sdvar_bf16* y, float* scratch, void* stream);
+/* out = h + bias[c] (+ res): conv bias + skip connection of a residual block (models/basic_vae.py:61) in one pass.
+ * rows = N*H*W pixels, C % 8 == 0, channels-last bf16; res may be NULL; out may alias h or res. */
+int sdvar_bias_residual_nhwc(const sdvar_bf16* h, const float* bias, const sdvar_bf16* res, long long rows, int C, sdvar_bf16* out,
+                             void* stream);
+/* nearest-neighbour 2x upsampling (models/basic_vae.py:31), channels-last bf16: x (N,H,W,C) -> y (N,2H,2W,C). */
+int sdvar_upsample2x_nhwc(const sdvar_bf16* x, int N, int H, int W, int C, sdvar_bf16* y, void* stream);
 
 /* ---- whole transformer pass (the launch sequence of one stage / one verify window) -----------
  * Device-pointer table of one VAR model in the engine's packed layout (bf16 weights, fp32 vectors).

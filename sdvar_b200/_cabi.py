@@ -24,7 +24,7 @@ EXPORTS = [
     "sdvar_sample_cfg_topk_topp", "sdvar_verify_accept_resample", "sdvar_verify_top1", "sdvar_vq_next_input",
     "sdvar_embed_next_map", "sdvar_first_map", "sdvar_ln_modulate", "sdvar_silu_bf16", "sdvar_f32_to_bf16",
     "sdvar_gemm_bf16", "sdvar_attention", "sdvar_var_forward", "sdvar_profile_begin", "sdvar_profile_end",
-    "sdvar_groupnorm_silu_nhwc",
+    "sdvar_groupnorm_silu_nhwc", "sdvar_bias_residual_nhwc", "sdvar_upsample2x_nhwc",
 ]
 PROFILE_FAMILIES = ("gemm", "attention", "ln_modulate", "sample", "verify", "vq", "embed", "misc")
 
@@ -179,6 +179,16 @@ def profile_end() -> dict:
     return {PROFILE_FAMILIES[i]: (ms[i], work[i], int(cnt[i])) for i in range(n)}
 
 
-def groupnorm_silu_nhwc(x, N, HW, Cc, gamma, beta, eps, silu, y, scratch):
-    _check(lib().sdvar_groupnorm_silu_nhwc(C.c_void_p(x.data_ptr()), N, HW, Cc, ptr(gamma), ptr(beta), C.c_float(eps), int(silu),
-                                           C.c_void_p(y.data_ptr()), ptr(scratch), stream_ptr()), "sdvar_groupnorm_silu_nhwc")
+def groupnorm_silu_nhwc(x, N, HW, Cc, gamma, beta, eps, silu, y, scratch, pre_bias=None):
+    _check(lib().sdvar_groupnorm_silu_nhwc(C.c_void_p(x.data_ptr()), ptr(pre_bias), N, HW, Cc, ptr(gamma), ptr(beta), C.c_float(eps),
+                                           int(silu), C.c_void_p(y.data_ptr()), ptr(scratch), stream_ptr()), "sdvar_groupnorm_silu_nhwc")
+
+
+def bias_residual_nhwc(h, bias, res, rows, Cc, out):
+    _check(lib().sdvar_bias_residual_nhwc(C.c_void_p(h.data_ptr()), ptr(bias), C.c_void_p(res.data_ptr() if res is not None else 0), C.c_longlong(rows), Cc,
+                                          C.c_void_p(out.data_ptr()), stream_ptr()), "sdvar_bias_residual_nhwc")
+
+
+def upsample2x_nhwc(x, N, H, W, Cc, y):
+    _check(lib().sdvar_upsample2x_nhwc(C.c_void_p(x.data_ptr()), N, H, W, Cc, C.c_void_p(y.data_ptr()), stream_ptr()),
+           "sdvar_upsample2x_nhwc")

@@ -35,20 +35,19 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
                       pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
 }
 
-// Residual epilogue: the fp32 residual tile and the gate row are known before the accumulator is ready, so the first
+// Residual epilogue: the fp32 residual tile is known before the accumulator is ready, so the first
 // 32-column chunk is loaded while the main loop of the tile is still running, and chunk c+1 is in flight while chunk c
 // is combined and stored (the proj GEMM, K = C, is otherwise epilogue-bound on these global round trips).
 struct EpiPre {
-  float4 x[8], g[8];
+  float4 x[8];
 };
 template <int EPI>
 __device__ __forceinline__ void epilogue_prefetch(EpiPre& pre, int row, int col_base, int M, int N, const Epi& ep) {
   if constexpr (EPI == SDVAR_EPI_RESID_F32) {
     if (row < M && col_base < N) {
-      const float4* g4 = reinterpret_cast<const float4*>(ep.gate + (size_t)(row / ep.tokens_per_img) * ep.ld_gate + col_base);
       const float4* x4 = reinterpret_cast<const float4*>(ep.out_f32 + (size_t)row * ep.ldo + col_base);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { pre.x[q] = x4[q]; pre.g[q] = __ldg(g4 + q); }
+      for (int q = 0; q < 8; ++q) pre.x[q] = x4[q];
     }
   }
 }
@@ -64,22 +63,22 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row, int col_b
       uint32_t r[32];
       ptx::tmem_ld_32x32(taddr + c * 32, r);
       const int col0 = col_base + c * 32, coln = col0 + 32;
-      float4 xn[8], gn[8];
+      float4 xn[8];
       if (c + 1 < BN / 32 && rv && coln < N) {
-        const float4* g4 = reinterpret_cast<const float4*>(grow + coln);
         const float4* x4 = reinterpret_cast<const float4*>(xrow + coln);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { xn[q] = x4[q]; gn[q] = __ldg(g4 + q); }
+        for (int q = 0; q < 8; ++q) xn[q] = x4[q];
       }
       ptx::tmem_ld_wait();
       if (rv && col0 < N) {
         float4* d = reinterpret_cast<float4*>(xrow + col0);
         const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+        const float4* g4 = reinterpret_cast<const float4*>(grow + col0);   // one gate row per image: warp-uniform, L1-resident
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 bb = ep.bias != nullptr ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 o = pre.x[q];
-          const float4 g = pre.g[q];
+          const float4 g = __ldg(g4 + q);
           o.x += (__uint_as_float(r[4 * q]) + bb.x) * g.x;
           o.y += (__uint_as_float(r[4 * q + 1]) + bb.y) * g.y;
           o.z += (__uint_as_float(r[4 * q + 2]) + bb.z) * g.z;
@@ -88,7 +87,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row, int col_b
         }
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { pre.x[q] = xn[q]; pre.g[q] = gn[q]; }
+      for (int q = 0; q < 8; ++q) pre.x[q] = xn[q];
     }
   } else if constexpr (EPI == SDVAR_EPI_QKV) {
     // 64-column groups = one attention head of one of q / k / v

@@ -14,7 +14,8 @@ constexpr int kGnMaxC = 1024;
 
 // partial[(n*nblk + blk)*2*32 + g*2 + {0,1}] = sum / sum of squares over this block's pixels
 __global__ void __launch_bounds__(kGnThreads)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pix_per_blk, float* __restrict__ partial) {
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ pre_bias, int HW, int C, int pix_per_blk,
+                float* __restrict__ partial) {
   __shared__ float s_sum[32], s_sq[32];
   const int n = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
   const int vec_per_pix = C >> 3;                 // 8 channels (16 bytes) per vector
@@ -30,13 +31,17 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pix_per_
 #pragma unroll
   for (int k = 0; k < 8; ++k) { acc_s[k] = 0.f; acc_q[k] = 0.f; }
   const int v = threadIdx.x % vec_per_pix;
+  float pb[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) pb[k] = pre_bias ? pre_bias[v * 8 + k] : 0.f;   // conv bias folded in: statistics of x + b
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int pix = p0 + i / vec_per_pix;
     const uint4 raw = *reinterpret_cast<const uint4*>(x + base + (long long)pix * C + v * 8);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 f = __bfloat1622float2(h[k]);
+      float2 f = __bfloat1622float2(h[k]);
+      f.x += pb[2 * k]; f.y += pb[2 * k + 1];
       acc_s[2 * k] += f.x; acc_q[2 * k] += f.x * f.x;
       acc_s[2 * k + 1] += f.y; acc_q[2 * k + 1] += f.y * f.y;
     }
@@ -65,7 +70,8 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pix_per_
 }
 
 __global__ void __launch_bounds__(kGnThreads)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pix_per_blk, int nblk_stats, const float* __restrict__ partial,
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ pre_bias, int HW, int C, int pix_per_blk, int nblk_stats,
+                const float* __restrict__ partial,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu, __nv_bfloat16* __restrict__ y) {
   __shared__ float s_mean[32], s_rstd[32];
   __shared__ float s_a[kGnMaxC], s_b[kGnMaxC];    // per-channel scale / shift: y = x*a + b
@@ -86,7 +92,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pix_per_
     const int g = c / cg;
     const float a = s_rstd[g] * gamma[c];
     s_a[c] = a;
-    s_b[c] = beta[c] - s_mean[g] * a;
+    s_b[c] = beta[c] + ((pre_bias ? pre_bias[c] : 0.f) - s_mean[g]) * a;
   }
   __syncthreads();
   const int p0 = blk * pix_per_blk, p1 = min(p0 + pix_per_blk, HW);
@@ -110,14 +116,58 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pix_per_
   }
 }
 
+// out = h + bias [+ res]: the tail of a residual block (conv2 bias + skip connection, reference models/basic_vae.py:61) in one
+// pass instead of cuDNN's separate bias kernel followed by an elementwise add.  One 16-byte vector (8 channels) per thread step.
+__global__ void __launch_bounds__(256)
+bias_residual_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res,
+                     long long nvec, int vec_per_pix, __nv_bfloat16* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const int v = (int)(i % vec_per_pix);
+    const uint4 a = reinterpret_cast<const uint4*>(h)[i];
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * v), b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * v + 1);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (res) r = reinterpret_cast<const uint4*>(res)[i];
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&r);
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = __bfloat1622float2(ha[k]), fr = __bfloat1622float2(hr[k]);
+      o[k] = pack_bf16x2(fa.x + bb[2 * k] + fr.x, fa.y + bb[2 * k + 1] + fr.y);
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// nearest-neighbour 2x upsampling, channels-last (reference models/basic_vae.py:31 F.interpolate(scale_factor=2, mode='nearest')):
+// each input vector is read once and written to its four output pixels.
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int H, int W, int vec_per_pix, long long nvec, __nv_bfloat16* __restrict__ y) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const int v = (int)(i % vec_per_pix);
+    const long long pix = i / vec_per_pix;
+    const int w = (int)(pix % W);
+    const long long nh = pix / W;            // n*H + h
+    const uint4 a = reinterpret_cast<const uint4*>(x)[i];
+    uint4* o = reinterpret_cast<uint4*>(y) + ((nh * 2) * (2 * W) + 2 * w) * vec_per_pix + v;
+    o[0] = a;
+    o[vec_per_pix] = a;
+    o[(long long)2 * W * vec_per_pix] = a;
+    o[(long long)2 * W * vec_per_pix + vec_per_pix] = a;
+  }
+}
+
 }  // namespace sdvar
 
 using namespace sdvar;
 
-// x, y: (N, H*W, C) channels-last bf16 (y may alias x); gamma/beta fp32 [C]; scratch >= N*nblk*64 floats with
+// x, y: (N, H*W, C) channels-last bf16 (y may alias x); pre_bias (nullable) fp32 [C] is added to x first; gamma/beta fp32 [C]; scratch >= N*nblk*64 floats with
 // nblk = min(ceil(HW/32), 128).  32 groups (reference Normalize), C % 32 == 0, C % 8 == 0, C <= 1024.
-extern "C" int sdvar_groupnorm_silu_nhwc(const sdvar_bf16* x, int N, int HW, int C, const float* gamma, const float* beta, float eps,
-                                         int silu, sdvar_bf16* y, float* scratch, void* stream) {
+extern "C" int sdvar_groupnorm_silu_nhwc(const sdvar_bf16* x, const float* pre_bias, int N, int HW, int C, const float* gamma,
+                                         const float* beta, float eps, int silu, sdvar_bf16* y, float* scratch, void* stream) {
   if (int rc = check_arch()) return rc;
   SDVAR_REQUIRE(x && y && gamma && beta && scratch, "NULL argument");
   SDVAR_REQUIRE(N > 0 && HW > 0 && C % 32 == 0 && C % 8 == 0 && C <= kGnMaxC, "bad geometry N=%d HW=%d C=%d", N, HW, C);
@@ -131,10 +181,49 @@ extern "C" int sdvar_groupnorm_silu_nhwc(const sdvar_bf16* x, int N, int HW, int
   const int vpp = C >> 3;
   SDVAR_REQUIRE(vpp <= kGnThreads, "C too large");
   const int stat_threads = (kGnThreads / vpp) * vpp;
-  gn_stats_kernel<<<dim3(nblk, N), stat_threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), HW, C, ppb, scratch);
+  gn_stats_kernel<<<dim3(nblk, N), stat_threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), pre_bias, HW, C, ppb, scratch);
   SDVAR_LAUNCH_CHECK();
-  gn_apply_kernel<<<dim3(nblk, N), kGnThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), HW, C, ppb, nblk, scratch, gamma, beta, eps,
+  gn_apply_kernel<<<dim3(nblk, N), kGnThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), pre_bias, HW, C, ppb, nblk, scratch, gamma, beta, eps,
                                                        silu, reinterpret_cast<__nv_bfloat16*>(y));
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
+
+// out[r, c] = h[r, c] + bias[c] (+ res[r, c]); rows = N*H*W pixels, channels-last bf16, C % 8 == 0; out may alias h or res.
+extern "C" int sdvar_bias_residual_nhwc(const sdvar_bf16* h, const float* bias, const sdvar_bf16* res, long long rows, int C,
+                                        sdvar_bf16* out, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(h && bias && out, "NULL argument");
+  SDVAR_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, "bad geometry rows=%lld C=%d", rows, C);
+  SDVAR_REQUIRE(((uintptr_t)h & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)res & 15) == 0 && ((uintptr_t)bias & 15) == 0,
+                "16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nvec = rows * (C >> 3);
+  ProfileScope prof(st, FAM_MISC, (double)nvec * 16.0 * (res ? 3.0 : 2.0));
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  bias_residual_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(h), bias,
+                                                         reinterpret_cast<const __nv_bfloat16*>(res), nvec, C >> 3,
+                                                         reinterpret_cast<__nv_bfloat16*>(out));
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
+
+// y (N, 2H, 2W, C) = nearest-neighbour 2x of x (N, H, W, C), channels-last bf16, C % 8 == 0; x and y must not overlap.
+extern "C" int sdvar_upsample2x_nhwc(const sdvar_bf16* x, int N, int H, int W, int C, sdvar_bf16* y, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(x && y && x != y, "NULL or aliased argument");
+  SDVAR_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad geometry N=%d H=%d W=%d C=%d", N, H, W, C);
+  SDVAR_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nvec = (long long)N * H * W * (C >> 3);
+  ProfileScope prof(st, FAM_MISC, (double)nvec * 16.0 * 5.0);
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  upsample2x_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), H, W, C >> 3, nvec,
+                                                      reinterpret_cast<__nv_bfloat16*>(y));
   SDVAR_LAUNCH_CHECK();
   return SDVAR_OK;
 }

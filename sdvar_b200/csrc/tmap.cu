@@ -18,8 +18,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int esize, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available (driver too old or no driver)");
@@ -40,8 +40,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     gstr[i] = strides_bytes[i];
     SDVAR_REQUIRE(strides_bytes[i] % 16 == 0, "TMA stride %llu not a multiple of 16 bytes", (unsigned long long)strides_bytes[i]);
   }
-  SDVAR_REQUIRE(box[0] * 2 == 128, "inner box must be 128 bytes for SWIZZLE_128B");
-  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+  SDVAR_REQUIRE((int)box[0] * esize == 128, "inner box must be 128 bytes for SWIZZLE_128B");
+  const CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -50,6 +50,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return SDVAR_ERR_CUDA;
   }
   return SDVAR_OK;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rank, dims, strides_bytes, box);
+}
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rank, dims, strides_bytes, box);
 }
 
 }  // namespace sdvar

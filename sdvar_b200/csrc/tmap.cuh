@@ -12,5 +12,8 @@ namespace sdvar {
 // strides_bytes[i] is the byte stride of dims[i+1].  box[0] must be 64 elements (=128 bytes).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// fp32 tensor, same conventions; box[0] must be 32 elements (=128 bytes).
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
 
 }  // namespace sdvar

@@ -2,7 +2,8 @@
 
 The decoder (``fhat_to_img``, reference models/vqvae.py:62-63 + models/basic_vae.py:163-226) is NOT one of the
 four north-star kernel families; it is the boundary right after the path and runs here through
-PyTorch/cuDNN in bf16 channels-last as library code.  Parameter names follow the reference checkpoint
+cuDNN convolutions (library code, bias-free) in bf16 channels-last; GroupNorm+SiLU, bias+skip adds and the 2x upsampling are
+libsdvar kernels.  Parameter names follow the reference checkpoint
 (``decoder.*``, ``post_quant_conv.*``, ``quantize.*``); encode-side tensors (``encoder.*``, ``quant_conv.*``) of a
 real ``vae_ch160v4096z32.pth`` are accepted and ignored by ``load_state_dict``.
 """
@@ -24,11 +25,42 @@ def _gn(c: int) -> nn.GroupNorm:
 _GN_SCRATCH = {}
 
 
-def _gn_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool) -> torch.Tensor:
-    """GroupNorm (+SiLU).  On the device path (bf16, channels-last) this is the fused libsdvar kernel: PyTorch's GroupNorm
-    round-trips channels-last bf16 through NCHW copies (measured 120 ms of a 140 ms decode of 64 images)."""
-    if x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) \
-            and x.shape[1] % 32 == 0 and norm.num_groups == 32:
+def _fast(x: torch.Tensor) -> bool:
+    """bf16 channels-last CUDA activations: the layout the libsdvar decoder kernels take."""
+    return x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) \
+        and x.shape[1] % 8 == 0
+
+
+def _bias32(conv: nn.Conv2d) -> torch.Tensor:
+    if getattr(conv, "_b32", None) is None or conv._b32.device != conv.bias.device:
+        conv._b32 = conv.bias.detach().float().contiguous()
+    return conv._b32
+
+
+def _conv_nobias(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    return F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
+
+
+def _conv_bias_res(conv: nn.Conv2d, x: torch.Tensor, res=None) -> torch.Tensor:
+    """conv(x) + bias (+ res).  Device path: bias-free cuDNN convolution, then ONE libsdvar pass adds bias and skip connection in
+    place (cuDNN's own bias is a separate un-vectorised broadcast kernel, and the skip add a third pass)."""
+    if _fast(x) and conv.out_channels % 8 == 0:
+        h = _conv_nobias(conv, x)
+        if _fast(h) and (res is None or (_fast(res) and res.shape == h.shape)):
+            from .. import _cabi
+            N, C, H, W = h.shape
+            _cabi.bias_residual_nhwc(h, _bias32(conv), res, N * H * W, C, h)
+            return h
+        h = h + conv.bias.view(1, -1, 1, 1)
+        return h if res is None else res + h
+    h = conv(x)
+    return h if res is None else res + h
+
+
+def _gn_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool, pre_bias=None) -> torch.Tensor:
+    """GroupNorm (+SiLU) of x (+ pre_bias per channel).  On the device path (bf16, channels-last) this is the fused libsdvar kernel:
+    PyTorch's GroupNorm round-trips channels-last bf16 through NCHW copies (measured 120 ms of a 140 ms decode of 64 images)."""
+    if _fast(x) and x.shape[1] % 32 == 0 and norm.num_groups == 32:
         from .. import _cabi
         N, C, H, W = x.shape
         if getattr(norm, "_w32", None) is None or norm._w32.device != x.device:
@@ -37,8 +69,10 @@ def _gn_act(norm: nn.GroupNorm, x: torch.Tensor, silu: bool) -> torch.Tensor:
         if key not in _GN_SCRATCH:
             _GN_SCRATCH[key] = torch.empty(N * 128 * 64, device=x.device, dtype=torch.float32)
         y = torch.empty_like(x)
-        _cabi.groupnorm_silu_nhwc(x, N, H * W, C, norm._w32, norm._b32, norm.eps, silu, y, _GN_SCRATCH[key])
+        _cabi.groupnorm_silu_nhwc(x, N, H * W, C, norm._w32, norm._b32, norm.eps, silu, y, _GN_SCRATCH[key], pre_bias=pre_bias)
         return y
+    if pre_bias is not None:
+        x = x + pre_bias.to(x.dtype).view(1, -1, 1, 1)
     y = norm(x)
     return F.silu(y) if silu else y
 
@@ -52,8 +86,13 @@ class _Res(nn.Module):
             self.nin_shortcut = nn.Conv2d(cin, cout, 1)
 
     def forward(self, x):
-        h = self.conv2(_gn_act(self.norm2, self.conv1(_gn_act(self.norm1, x, True)), True))
-        return (self.nin_shortcut(x) if hasattr(self, "nin_shortcut") else x) + h
+        a = _gn_act(self.norm1, x, True)
+        if _fast(a) and self.conv1.out_channels % 32 == 0:
+            # conv1 runs bias-free; its bias is folded into norm2's statistics and affine
+            b = _gn_act(self.norm2, _conv_nobias(self.conv1, a), True, pre_bias=_bias32(self.conv1))
+        else:
+            b = _gn_act(self.norm2, self.conv1(a), True)
+        return _conv_bias_res(self.conv2, b, self.nin_shortcut(x) if hasattr(self, "nin_shortcut") else x)
 
 
 class _SpatialAttn(nn.Module):
@@ -75,7 +114,14 @@ class _Up(nn.Module):
         self.conv = nn.Conv2d(c, c, 3, padding=1)
 
     def forward(self, x):
-        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        if _fast(x):
+            from .. import _cabi
+            N, C, H, W = x.shape
+            y = torch.empty((N, C, 2 * H, 2 * W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+            _cabi.upsample2x_nhwc(x, N, H, W, C, y)
+        else:
+            y = F.interpolate(x, scale_factor=2.0, mode="nearest")
+        return _conv_bias_res(self.conv, y)
 
 
 class _Level(nn.Module):
@@ -119,7 +165,7 @@ class Decoder(nn.Module):
         self.norm_out, self.conv_out = _gn(c), nn.Conv2d(c, in_channels, 3, padding=1)
 
     def forward(self, z):
-        h = self.mid(self.conv_in(z))
+        h = self.mid(_conv_bias_res(self.conv_in, z))
         for lv in reversed(range(len(self.up))):
             h = self.up[lv](h)
         return self.conv_out(_gn_act(self.norm_out, h, True))

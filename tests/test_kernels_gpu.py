@@ -252,6 +252,26 @@ def test_gemm_bf16_gelu_and_residual(cuda_lib):
     assert torch.allclose(x.cpu(), ref, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("M,N,K,tpi", [(4700, 1920, 1920, 47), (9 * 1024, 1920, 7680, 1024)])
+def test_gemm_residual_pair_kernel(cuda_lib, M, N, K, tpi):
+    """CTA-pair kernel, TMA-staged in-place residual epilogue: ragged last row tile (4700 = 18*256 + 92) and a half-empty last
+    column tile (1920 = 7.5 * 256); x += gate[img] * (A W^T + bias)  (models/basic_var.py:168-169)."""
+    imgs = M // tpi
+    A = hashed("g3.A", 0, (M, K), 1.0, dtype=torch.bfloat16)
+    W = hashed("g3.W", 1, (N, K), 1.0 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = hashed("g3.b", 2, (N,), 0.5)
+    gate = hashed("g3.g", 3, (imgs, 6 * N), 1.0)
+    x0 = hashed("g3.x", 4, (M + 1, N), 1.0)          # one guard row after the matrix: must stay untouched
+    Ad, Wd, bd, gd, x = A.to(DEV), W.to(DEV), bias.to(DEV), gate.to(DEV), x0.to(DEV)
+    cuda_lib.gemm_bf16(Ad, K, Wd, K, M, N, K, cuda_lib.GemmEpilogue(epilogue=cuda_lib.EPI_RESID_F32, bias=bd.data_ptr(), out_f32=x.data_ptr(), ldo=N,
+                                                                 gate=gd.data_ptr() + 2 * N * 4, ld_gate=6 * N, tokens_per_img=tpi))
+    torch.cuda.synchronize()
+    acc = (Ad.float() @ Wd.float().t()).cpu() + bias
+    ref = x0[:M] + acc * gate[:, 2 * N:3 * N].repeat_interleave(tpi, 0)
+    assert torch.allclose(x[:M].cpu(), ref, rtol=2e-4, atol=2e-4)
+    assert torch.equal(x[M].cpu(), x0[M])
+
+
 def _attn_case(cuda_lib, imgs, H, ls_window, kv_off, l2norm, seed, clamp_head=False):
     """QKV epilogue + attention against a plain fp32 torch restatement of basic_var.py:93-117."""
     C = H * 64
@@ -333,3 +353,32 @@ def test_groupnorm_silu_nhwc_vs_torch(cuda_lib, N, C, H, silu):
     cuda_lib.groupnorm_silu_nhwc(x, N, H * H, C, g, b, 1e-6, silu, y, scratch)
     assert y.is_contiguous(memory_format=torch.channels_last)
     assert torch.allclose(y.float(), ref, rtol=2 ** -7, atol=1e-2), float((y.float() - ref).abs().max())
+
+
+@pytest.mark.parametrize("N,C,H", [(2, 160, 32), (1, 320, 16)])
+def test_groupnorm_pre_bias(cuda_lib, N, C, H):
+    """conv bias folded into GroupNorm: GN(x + b) with x the bias-free conv output"""
+    x = (hashed("gnb.x", 0, (N, C, H, H), 1.5) + 0.4).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    g = (1.0 + hashed("gnb.g", 1, (C,), 0.2)).to(DEV)
+    b = hashed("gnb.b", 2, (C,), 0.2).to(DEV)
+    pb = hashed("gnb.pb", 3, (C,), 0.7).to(DEV)
+    ref = torch.nn.functional.silu(torch.nn.functional.group_norm(x.float() + pb.view(1, -1, 1, 1), 32, g, b, eps=1e-6))
+    y = torch.empty_like(x)
+    scratch = torch.empty(N * 128 * 64, device=DEV)
+    cuda_lib.groupnorm_silu_nhwc(x, N, H * H, C, g, b, 1e-6, True, y, scratch, pre_bias=pb)
+    assert torch.allclose(y.float(), ref, rtol=2 ** -7, atol=1e-2), float((y.float() - ref).abs().max())
+
+
+@pytest.mark.parametrize("N,C,H,W,with_res", [(2, 160, 8, 12, True), (3, 640, 4, 4, False), (1, 8, 5, 3, True)])
+def test_bias_residual_and_upsample_nhwc(cuda_lib, N, C, H, W, with_res):
+    """decoder glue: out = h + bias (+ res) with one rounding, and nearest 2x upsampling (bit-exact copy)"""
+    h = hashed("br.h", 0, (N, C, H, W), 1.0).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    r = hashed("br.r", 1, (N, C, H, W), 1.0).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    b = hashed("br.b", 2, (C,), 0.5).to(DEV)
+    ref = h.float() + b.view(1, -1, 1, 1) + (r.float() if with_res else 0.0)
+    out = torch.empty_like(h)
+    cuda_lib.bias_residual_nhwc(h, b, r if with_res else None, N * H * W, C, out)
+    assert torch.equal(out, ref.bfloat16())
+    y = torch.empty((N, C, 2 * H, 2 * W), device=DEV, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    cuda_lib.upsample2x_nhwc(h, N, H, W, C, y)
+    assert torch.equal(y, torch.nn.functional.interpolate(h, scale_factor=2.0, mode="nearest"))
