@@ -51,6 +51,11 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// hot spin (single-lane MMA issuers: reacts within a few tens of cycles, where try_wait may park the thread)
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_test(bar, parity)) {}
+}
+
 // ---- TMA ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -105,6 +110,17 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand read from tensor memory (lane = row, two 16-bit elements per 32-bit column)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -124,6 +140,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 
+// registers -> TMEM: thread i of the warp writes lane (base+i), register j -> column j (16 consecutive columns)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp layouts) ------------------------------------
 // K-major operand tile in shared memory written by TMA with SWIZZLE_128B: rows of 128 bytes (64 bf16),
 // 8-row groups 1024 bytes apart.  start address /16, LBO = 1 (ignored for swizzled K-major), SBO = 1024/16,
@@ -136,6 +163,13 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+// same tile, start address advanced by `bytes` (a multiple of 16 that stays inside the 14-bit field): one 32-bit add instead
+// of rebuilding the descriptor for every K step
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t d, uint32_t bytes) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"((uint32_t)d + (bytes >> 4)), "r"((uint32_t)(d >> 32)));
+  return r;
 }
 // instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, dense, no negate
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
