@@ -269,8 +269,16 @@ def main():
                 kern[fam] = {"bound": "hbm", "achieved": (work + extra) / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms": ms, "launches": n}
         g = kern.get("gemm")
         if g:
-            out["roofline"] = {"bound": "tensor", "kernel": "sdvar::gemm::gemm_kernel<EPI> (tcgen05, all epilogues)", "achieved": g["achieved"],
-                               "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": g["achieved"] / pk["tf_sustained"], "traffic": None,
+            # DRAM bytes per launch of the GEMM family from the committed ncu launch list of this same default workload
+            # (profiles/traffic_r01.json <- profiles/launches_r01.md); null for any other workload
+            traffic = None
+            tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01.json")
+            default_workload = (args.batch, args.depth_draft, args.depth_target, args.gamma, args.px, args.top_k) == (64, 16, 30, 2, 256, 900)
+            if default_workload and os.path.exists(tpath):
+                traffic = json.load(open(tpath))["families"]["gemm"]["dram_bytes_per_launch"]
+            out["roofline"] = {"bound": "tensor", "kernel": "sdvar::gemm2::gemm2_kernel<EPI> / gemm::gemm_kernel<EPI> (tcgen05, all epilogues)", "achieved": g["achieved"],
+                               "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": g["achieved"] / pk["tf_sustained"], "traffic": traffic,
+                               "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the family's launches)",
                                "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
                                "share_of_step_ms": g["ms"], "launches": g["launches"]}
         for k, v in kern.items():
