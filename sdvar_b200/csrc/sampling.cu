@@ -21,7 +21,10 @@ constexpr int kWarps = kThreads / 32;
 __device__ __forceinline__ float spec_expf(float x) {
   const float xc = fmaxf(x, -104.0f);
   const float t = __fmul_rn(xc, 1.44269504088896340736f);
-  const float n = rintf(t);
+  // rintf(t) and (int)n without the quarter-rate FRND / F2I conversions: t is in [-151, 0], so t + 1.5*2^23 lands in the binade
+  // with ulp 1 and the addition itself rounds to nearest-even; the integer is the mantissa difference
+  const float tm = __fadd_rn(t, 12582912.0f);
+  const float n = __fsub_rn(tm, 12582912.0f);
   float r = __fmaf_rn(n, -0.693145751953125f, xc);
   r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
   float p = 1.0f / 5040.0f;
@@ -32,9 +35,60 @@ __device__ __forceinline__ float spec_expf(float x) {
   p = __fmaf_rn(p, r, 0.5f);
   p = __fmaf_rn(p, r, 1.0f);
   p = __fmaf_rn(p, r, 1.0f);
-  const int ni = (int)n;   // in [-151, 0]
-  const float v = __fmul_rn(__fmul_rn(p, u2f((uint32_t)(ni + 100 + 127) << 23)), u2f((uint32_t)(-100 + 127) << 23));
-  return (x < -104.0f) ? 0.0f : v;
+  const int ni = __float_as_int(tm) - 0x4B400000;   // in [-151, 0]
+  // no select for x < -104: the clamped value scales to p * 2^-150 < 2^-150 * 1 = half of the smallest subnormal and the second
+  // (once-rounded) multiplication returns exactly 0, which is what the spec returns below -104
+  return __fmul_rn(__fmul_rn(p, u2f((uint32_t)(ni + 100 + 127) << 23)), u2f((uint32_t)(-100 + 127) << 23));
+}
+
+// ---- two exponentials at once on the packed fp32x2 pipe (FFMA2 / FADD2 / FMUL2: one issue slot for two IEEE-RN operations, so
+// the results are bit-identical to two spec_expf calls while the instruction count per exponential halves).
+struct f32x2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 splat2(float c) { return pk2(c, c); }
+// (exp(x0), exp(x1)), both x <= 0 (or -inf); every lane operation is the one spec_expf performs, in the same order
+__device__ __forceinline__ f32x2 spec_expf2(float x0, float x1) {
+  const f32x2 xc = pk2(fmaxf(x0, -104.0f), fmaxf(x1, -104.0f));
+  const f32x2 t = mul2(xc, splat2(1.44269504088896340736f));
+  const f32x2 tm = add2(t, splat2(12582912.0f));
+  const f32x2 n = add2(tm, splat2(-12582912.0f));
+  f32x2 r = fma2(n, splat2(-0.693145751953125f), xc);
+  r = fma2(n, splat2(-1.42860682030941723212e-6f), r);
+  f32x2 p = splat2(1.0f / 5040.0f);
+  p = fma2(p, r, splat2(1.0f / 720.0f));
+  p = fma2(p, r, splat2(1.0f / 120.0f));
+  p = fma2(p, r, splat2(1.0f / 24.0f));
+  p = fma2(p, r, splat2(1.0f / 6.0f));
+  p = fma2(p, r, splat2(0.5f));
+  p = fma2(p, r, splat2(1.0f));
+  p = fma2(p, r, splat2(1.0f));
+  float tm0, tm1;
+  unpk2(tm, tm0, tm1);
+  const uint32_t s0 = (uint32_t)(__float_as_int(tm0) - 0x4B400000 + 100 + 127) << 23;
+  const uint32_t s1 = (uint32_t)(__float_as_int(tm1) - 0x4B400000 + 100 + 127) << 23;
+  return mul2(mul2(p, pk2(u2f(s0), u2f(s1))), splat2(u2f((uint32_t)(-100 + 127) << 23)));
 }
 
 // ---- block reductions.  `slot` alternates between two smem buffers so one barrier per reduction suffices.
@@ -208,7 +262,10 @@ k3_sample_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int 
       float p[E];
       float z = 0.0f;
 #pragma unroll
-      for (int e = 0; e < E; ++e) { p[e] = spec_expf(__fsub_rn(fkey_inv(key[e]), m)); z = __fadd_rn(z, p[e]); }
+      for (int e = 0; e < E; e += 2) {
+        unpk2(spec_expf2(__fsub_rn(fkey_inv(key[e]), m), __fsub_rn(fkey_inv(key[e + 1]), m)), p[e], p[e + 1]);
+        z = __fadd_rn(__fadd_rn(z, p[e]), p[e + 1]);
+      }
       const float Z = block_sum(z, sm, slot);
       float tot = 0.0f;
 #pragma unroll
@@ -254,7 +311,10 @@ k3_sample_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int 
       float ex[E];
       float z = 0.0f;
 #pragma unroll
-      for (int e = 0; e < E; ++e) { ex[e] = spec_expf(__fsub_rn(fkey_inv(key[e]), m)); z = __fadd_rn(z, ex[e]); }
+      for (int e = 0; e < E; e += 2) {
+        unpk2(spec_expf2(__fsub_rn(fkey_inv(key[e]), m), __fsub_rn(fkey_inv(key[e + 1]), m)), ex[e], ex[e + 1]);
+        z = __fadd_rn(__fadd_rn(z, ex[e]), ex[e + 1]);
+      }
       const float Z2 = block_sum(z, sm, slot);
       float best = -1.0f, bestp = 0.0f;
       int bi = 0x7FFFFFFF;
@@ -379,23 +439,27 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
     mt = fkey_inv(kt);
     md = fkey_inv(kd);
     // pass 2: canonical exp sums; the owner of element d keeps its two exponentials
-    float zt = 0.0f, zd = 0.0f;
+    f32x2 z2 = pk2(0.0f, 0.0f);                    // (zt, zd): two independent in-order chains
+    const f32x2 negm = pk2(-mt, -md);              // a - m == a + (-m) exactly
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float4 a = st4[i * kThreads + tid], c = sd4[i * kThreads + tid];
       float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        av[q] = spec_expf(__fsub_rn(av[q], mt));
-        cv[q] = spec_expf(__fsub_rn(cv[q], md));
-        zt = __fadd_rn(zt, av[q]);
-        zd = __fadd_rn(zd, cv[q]);
+        float x0, x1;
+        unpk2(add2(pk2(av[q], cv[q]), negm), x0, x1);
+        const f32x2 e2 = spec_expf2(x0, x1);
+        z2 = add2(z2, e2);
+        unpk2(e2, av[q], cv[q]);
       }
       // the exponentials replace the staged logits (each thread rewrites only the chunks it owns), so neither the accept
       // test nor a residual resample has to exponentiate again
       st4[i * kThreads + tid] = make_float4(av[0], av[1], av[2], av[3]);
       sd4[i * kThreads + tid] = make_float4(cv[0], cv[1], cv[2], cv[3]);
     }
+    float zt, zd;
+    unpk2(z2, zt, zd);
     block_sum2(zt, zd, sm, slot);  // zt, zd now hold Zt, Zd
     const float izt = __fdiv_rn(1.0f, zt), izd = __fdiv_rn(1.0f, zd);
     // the owner of element d evaluates the accept test and publishes the per-token outputs itself
