@@ -55,7 +55,7 @@ ln_modulate_kernel(const float* __restrict__ x, int M, int C, int tokens_per_img
 // Register-resident variant for the model widths in use (C = 128*NITER): all NITER 16-byte loads of a lane are issued
 // back to back (7.7 KB in flight per warp at C=1920), no shared-memory staging, 8 rows per CTA.
 template <int NITER>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NITER > 15 ? 2 : NITER > 12 ? 3 : 4)   // cap registers: ptxas otherwise hoists all scale/shift loads (127 regs, 2 CTAs/SM)
 ln_modulate_reg_kernel(const float* __restrict__ x, int M, int tokens_per_img, const float* __restrict__ scale,
                        const float* __restrict__ shift, int ld_mod, float eps, __nv_bfloat16* __restrict__ out) {
   constexpr int C = NITER * 128;
