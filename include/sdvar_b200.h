@@ -98,6 +98,12 @@ int sdvar_vq_next_input(const long long* idx_Bl, int B, int pn, int HW, int pn_n
                         const float* phi_w, const float* phi_b, float* f_hat, float* next_map, float* scratch,
                         void* stream);
 
+/* encode side: nearest codebook entry per row, reference models/quant.py:155-157
+ * (`d = |z|^2 + |e|^2 - 2 z e^T; argmin`).  z_NC (N,Cvae) fp32, codebook (V,Cvae) fp32, idx_out (N) int64.
+ * d = fma(-2, <z,e>, |z|^2 + |e|^2), dot products as sequential fma chains over c (oracle/spec_c: sdvar_spec_nearest_code),
+ * lowest index on ties.  Cvae must be 32. */
+int sdvar_vq_nearest_code(const float* z_NC, const float* codebook, long long N, int Cvae, int V, long long* idx_out, void* stream);
+
 /* stage input map (models/var.py:185-188):  x[r, t, :] = W_we @ next_map[b, :, t] + b_we + lvl_pos[t, :]
  * for r in {b, B+b} (the CFG repeat), next_map (B,Cvae,l) fp32, W_we (C,Cvae), lvl_pos (l,C) slice for the
  * stage, x (2B, ldx_tokens, C) fp32 written at token offset tok_off with ldx_tokens tokens per image. */

@@ -11,6 +11,9 @@ load_state_dict, so the fixtures hold only small inputs/outputs:
   tiny_var.npz   reference VAR.autoregressive_infer_cfg / VAR.forward / SDVAR.sd_test3 on a depth-2/3 model, 4-stage pyramid
   blocks.npz     reference AdaLNSelfAttn stack (models/basic_var.py:152-159) input/output on the tiny model
   d16.npz        reference VAR-d16 autoregressive_infer_cfg, B=1, 256 px pyramid (BASELINE.json configs[0] size): tokens, f_hat
+  encode.npz     reference encode side (`python oracle/make_golden.py encode` writes only this one): VectorQuantizer2.
+                 f_to_idxBl_or_fhat (models/quant.py:135-166) on a hashed 16x16 feature map (tokens of all 10 scales, final
+                 f_hat) and quant_conv(Encoder(img)) (models/vqvae.py:66, models/basic_vae.py:144-160) on a hashed image
 """
 import contextlib
 import io
@@ -47,7 +50,38 @@ def load_vae(vae, vsd):
     assert all(k.startswith(("encoder.", "quant_conv.")) for k in r.missing_keys) and not r.unexpected_keys
 
 
+def encode_golden():
+    """encode side (SURVEY.md 8f #3)"""
+    os.makedirs(OUT, exist_ok=True)
+    with quiet():
+        import models as R
+    o = {}
+    # multi-scale residual quantisation of a feature map, 256 px pyramid, codebook / Phi from the hashed VQVAE recipe
+    vsd = vqvae_state_dict(ch=32, patch_nums=P256, with_encoder=True)
+    with quiet():
+        vae = R.VQVAE(vocab_size=4096, z_channels=32, ch=32, test_mode=True, share_quant_resi=4, v_patch_nums=P256)
+    vae.load_state_dict(vsd, strict=True)
+    f = hashed("golden.encode.f", 0, (2, 32, 16, 16), 1.5)
+    with torch.no_grad():
+        idx = vae.quantize.f_to_idxBl_or_fhat(f, to_fhat=False)
+        fh = vae.quantize.f_to_idxBl_or_fhat(f, to_fhat=True)
+    o["f"] = f.numpy()
+    for si, t in enumerate(idx):
+        o[f"idx_{si}"] = t.numpy().astype(np.int16)
+    o["f_hat_last"] = fh[-1].numpy()
+    o["f_hat_3"] = fh[3].numpy()
+    # encoder + quant_conv on a 64x64 image (latent 4x4)
+    img = hashed("golden.encode.img", 0, (2, 3, 64, 64), 1.0)
+    with torch.no_grad():
+        o["img"] = img.numpy()
+        o["feat"] = vae.quant_conv(vae.encoder(img)).numpy()
+    np.savez_compressed(os.path.join(OUT, "encode.npz"), **o)
+    print("wrote encode.npz", {k: v.shape for k, v in o.items()})
+
+
 def main():
+    if sys.argv[1:] == ["encode"]:
+        return encode_golden()
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     with quiet():
@@ -173,6 +207,7 @@ def main():
         f, _ = orig(si, 10, f, h)
     o["f_hat"] = f.numpy()
     np.savez_compressed(os.path.join(OUT, "d16.npz"), **o)
+    encode_golden()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
 

@@ -164,6 +164,31 @@ class RefVQ:
         f_hat.add_(self.phi(si, h))
         return f_hat, f_hat
 
+    def f_to_idxBl_or_fhat(self, f_BChw: torch.Tensor, to_fhat: bool, nearest=None):
+        """Multi-scale residual quantisation, reference models/quant.py:135-166 (using_znorm=False).  `nearest(z_NC) -> idx_N`
+        overrides the reference's addmm/argmin (default) -- tests pass the C spec's fixed-order search."""
+        B, C, H, W = f_BChw.shape
+        SN = len(self.patch_nums)
+        f_rest = f_BChw.detach().float().clone()
+        f_hat = torch.zeros_like(f_rest)
+        out = []
+        for si, pn in enumerate(self.patch_nums):
+            z = F.interpolate(f_rest, size=(pn, pn), mode="area") if si != SN - 1 else f_rest
+            z_NC = z.permute(0, 2, 3, 1).reshape(-1, C)
+            if nearest is None:
+                d = torch.sum(z_NC.square(), dim=1, keepdim=True) + torch.sum(self.codebook.square(), dim=1, keepdim=False)
+                d.addmm_(z_NC, self.codebook.T, alpha=-2, beta=1)
+                idx_N = torch.argmin(d, dim=1)
+            else:
+                idx_N = nearest(z_NC.contiguous())
+            h = self.embedding(idx_N.view(B, pn, pn)).permute(0, 3, 1, 2)
+            h = F.interpolate(h, size=(H, W), mode="bicubic").contiguous() if si != SN - 1 else h.contiguous()
+            h = self.phi(si, h)
+            f_hat.add_(h)
+            f_rest.sub_(h)
+            out.append(f_hat.clone() if to_fhat else idx_N.reshape(B, pn * pn))
+        return out
+
     # -- closed forms the CUDA kernel implements (SURVEY.md A6, pin P5) --
     @staticmethod
     def bicubic_matrix(pn: int, HW: int) -> torch.Tensor:
@@ -254,6 +279,29 @@ class RefDecoder:
                 h = self._conv(f"decoder.up.{i_level}.upsample.conv", F.interpolate(h, scale_factor=2, mode="nearest"), 1)
         h = self._conv("decoder.conv_out", F.silu(self._gn("decoder.norm_out", h)), 1)
         return h.clamp_(-1, 1)
+
+
+class RefEncoder(RefDecoder):
+    """quant_conv(Encoder(img)), reference models/vqvae.py:66 + models/basic_vae.py:99-160 (encode side, SURVEY.md 8f #3)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2):
+        self.sd = {k: v.float() for k, v in sd.items() if k.startswith(("encoder.", "quant_conv."))}
+        self.ch_mult, self.nrb = ch_mult, num_res_blocks
+
+    def encode_features(self, img: torch.Tensor) -> torch.Tensor:
+        h = self._conv("encoder.conv_in", img.float(), 1)
+        nres = len(self.ch_mult)
+        for i_level in range(nres):
+            for i_block in range(self.nrb):
+                h = self._res(f"encoder.down.{i_level}.block.{i_block}", h)
+                if i_level == nres - 1:
+                    h = self._attn(f"encoder.down.{i_level}.attn.{i_block}", h)
+            if i_level != nres - 1:   # Downsample2x, basic_vae.py:36-37
+                n = f"encoder.down.{i_level}.downsample.conv"
+                h = F.conv2d(F.pad(h, pad=(0, 1, 0, 1), mode="constant", value=0), self.sd[n + ".weight"], self.sd[n + ".bias"], stride=2)
+        h = self._res("encoder.mid.block_2", self._attn("encoder.mid.attn_1", self._res("encoder.mid.block_1", h)))
+        h = self._conv("encoder.conv_out", F.silu(self._gn("encoder.norm_out", h)), 1)
+        return self._conv("quant_conv", h, 1)
 
 
 # --------------------------------------------------------------------------------------

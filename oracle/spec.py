@@ -56,6 +56,16 @@ def expf(x: torch.Tensor) -> torch.Tensor:
     return torch.tensor([l.sdvar_spec_expf(float(v)) for v in x.flatten().tolist()], dtype=torch.float32).view(x.shape)
 
 
+def nearest_code(z_NC: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
+    """Fixed-order nearest codebook entry (the arithmetic of sdvar_vq_nearest_code); z (N,C), codebook (V,C) fp32 CPU."""
+    z = z_NC.detach().float().contiguous().cpu()
+    e = codebook.detach().float().contiguous().cpu()
+    out = torch.empty(z.shape[0], dtype=torch.int64)
+    rc = lib().sdvar_spec_nearest_code(_p(z), _p(e), C.c_longlong(z.shape[0]), C.c_int(z.shape[1]), C.c_int(e.shape[0]), _p(out))
+    assert rc == 0
+    return out
+
+
 def sample(logits_2BLV: torch.Tensor, seg_begin: Sequence[int], t1, t2, top_k: int, top_p: float,
            noise: Optional[torch.Tensor], want_mixed=True):
     """returns (idx (B,L) int64 or None, mixed (B,L,V) or None, prob (B,L) or None)"""

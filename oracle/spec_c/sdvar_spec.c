@@ -223,3 +223,25 @@ int sdvar_spec_verify(const float* xt, const float* xd, const long long* draft_i
   summary[0] = min_stages; summary[1] = tot_acc; summary[2] = tot_rej; summary[3] = 0;
   return 0;
 }
+
+/* nearest codebook entry (reference models/quant.py:155-157), the arithmetic of sdvar_vq_nearest_code:
+ * d = fma(-2, <z,e>, |z|^2 + |e|^2), every dot product a sequential fma chain over c, argmin with the lowest index on ties. */
+int sdvar_spec_nearest_code(const float* z, const float* E, long long N, int C, int V, long long* idx_out) {
+  for (long long r = 0; r < N; ++r) {
+    const float* zr = z + r * C;
+    float zsq = 0.0f;
+    for (int c = 0; c < C; ++c) zsq = fmaf(zr[c], zr[c], zsq);
+    float best = INFINITY;
+    long long bi = 0;
+    for (int v = 0; v < V; ++v) {
+      const float* e = E + (long long)v * C;
+      float esq = 0.0f, dot = 0.0f;
+      for (int c = 0; c < C; ++c) esq = fmaf(e[c], e[c], esq);
+      for (int c = 0; c < C; ++c) dot = fmaf(zr[c], e[c], dot);
+      const float d = fmaf(-2.0f, dot, zsq + esq);
+      if (d < best) { best = d; bi = v; }
+    }
+    idx_out[r] = bi;
+  }
+  return 0;
+}

@@ -24,7 +24,7 @@ EXPORTS = [
     "sdvar_sample_cfg_topk_topp", "sdvar_verify_accept_resample", "sdvar_verify_top1", "sdvar_vq_next_input",
     "sdvar_embed_next_map", "sdvar_first_map", "sdvar_ln_modulate", "sdvar_silu_bf16", "sdvar_f32_to_bf16",
     "sdvar_gemm_bf16", "sdvar_attention", "sdvar_var_forward", "sdvar_profile_begin", "sdvar_profile_end",
-    "sdvar_groupnorm_silu_nhwc", "sdvar_bias_residual_nhwc", "sdvar_upsample2x_nhwc",
+    "sdvar_groupnorm_silu_nhwc", "sdvar_bias_residual_nhwc", "sdvar_upsample2x_nhwc", "sdvar_vq_nearest_code",
 ]
 PROFILE_FAMILIES = ("gemm", "attention", "ln_modulate", "sample", "verify", "vq", "embed", "misc")
 
@@ -84,7 +84,9 @@ def _check(rc: int, what: str):
 def ptr(t: Optional[torch.Tensor]):
     if t is None:
         return C.c_void_p(0)
-    assert t.is_cuda and t.is_contiguous(), "C-ABI arguments must be contiguous CUDA tensors"
+    if not t.is_cuda:
+        raise SdvarError("C-ABI arguments must be CUDA tensors: libsdvar_b200 has no CPU path")
+    assert t.is_contiguous(), "C-ABI arguments must be contiguous"
     return C.c_void_p(t.data_ptr())
 
 
@@ -128,6 +130,11 @@ def verify_top1(xt, draft_idx, B, L, V, seg_begin, match, n_match):
 def vq_next_input(idx_Bl, B, pn, HW, pn_next, Cvae, codebook, phi_w, phi_b, f_hat, next_map):
     _check(lib().sdvar_vq_next_input(ptr(idx_Bl), B, pn, HW, pn_next, Cvae, ptr(codebook), ptr(phi_w), ptr(phi_b),
                                      ptr(f_hat), ptr(next_map), C.c_void_p(0), stream_ptr()), "sdvar_vq_next_input")
+
+
+def vq_nearest_code(z_NC, codebook, N, Cvae, V, idx_out):
+    _check(lib().sdvar_vq_nearest_code(ptr(z_NC), ptr(codebook), C.c_longlong(N), Cvae, V, ptr(idx_out), stream_ptr()),
+           "sdvar_vq_nearest_code")
 
 
 def embed_next_map(next_map, B, l, Cvae, Cm, W, b, lvl_pos, x, ldx_tokens, tok_off):

@@ -197,9 +197,93 @@ __global__ void first_map_kernel(const float* __restrict__ cond, int first_l, in
     x[((long long)r * ldx_tokens + tok_off + t) * C + c] = cond[(long long)r * C + c] + pos_start[(long long)t * C + c] + lvl_pos[(long long)t * C + c];
 }
 
+// ---- encode side: nearest codebook entry, reference models/quant.py:155-157 -------------------------------
+// d(r, v) = fma(-2, <z_r, e_v>, |z_r|^2 + |e_v|^2) with every dot product a sequential fma chain over c = 0..31 (the fixed order
+// of oracle/spec_c:sdvar_spec_nearest_code), argmin with the lowest index on ties.  32 rows of z per CTA live in shared memory;
+// a thread owns codes tid, tid+256, ... (one code = 32 registers) and keeps the running best of all 32 rows in registers.
+constexpr int kNcRows = 32;
+__global__ void __launch_bounds__(256)
+vq_nearest_code_kernel(const float* __restrict__ z, const float* __restrict__ codebook, long long N, int V,
+                       long long* __restrict__ idx_out) {
+  __shared__ __align__(16) float sz[kNcRows][kC];
+  __shared__ float szsq[kNcRows];
+  __shared__ unsigned long long sbest[8][kNcRows];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long row0 = (long long)blockIdx.x * kNcRows;
+  for (int i = tid; i < kNcRows * kC; i += 256) {
+    const long long r = row0 + i / kC;
+    sz[i / kC][i % kC] = r < N ? z[r * kC + i % kC] : 0.0f;
+  }
+  __syncthreads();
+  if (tid < kNcRows) {
+    float a = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) a = __fmaf_rn(sz[tid][c], sz[tid][c], a);
+    szsq[tid] = a;
+  }
+  __syncthreads();
+  float bd[kNcRows];
+  int bi[kNcRows];
+#pragma unroll
+  for (int r = 0; r < kNcRows; ++r) { bd[r] = INFINITY; bi[r] = 0x7FFFFFFF; }
+  for (int v = tid; v < V; v += 256) {
+    float e[kC];
+    const float4* e4 = reinterpret_cast<const float4*>(codebook + (long long)v * kC);
+#pragma unroll
+    for (int q = 0; q < kC / 4; ++q) {
+      const float4 t = __ldg(e4 + q);
+      e[4 * q] = t.x; e[4 * q + 1] = t.y; e[4 * q + 2] = t.z; e[4 * q + 3] = t.w;
+    }
+    float esq = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) esq = __fmaf_rn(e[c], e[c], esq);
+#pragma unroll
+    for (int r = 0; r < kNcRows; ++r) {
+      float dot = 0.0f;
+#pragma unroll
+      for (int c = 0; c < kC; ++c) dot = __fmaf_rn(sz[r][c], e[c], dot);
+      const float d = __fmaf_rn(-2.0f, dot, __fadd_rn(szsq[r], esq));
+      if (d < bd[r]) { bd[r] = d; bi[r] = v; }     // codes are visited in increasing order: strict < keeps the lowest index
+    }
+  }
+  // (distance key, index) packed so that the u64 minimum is "smallest distance, then lowest index"
+#pragma unroll
+  for (int r = 0; r < kNcRows; ++r) {
+    unsigned long long w = ((unsigned long long)fkey(bd[r]) << 32) | (unsigned long long)(uint32_t)bi[r];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, w, off);
+      w = o < w ? o : w;
+    }
+    if (lane == 0) sbest[warp][r] = w;
+  }
+  __syncthreads();
+  if (tid < kNcRows && row0 + tid < N) {
+    unsigned long long w = sbest[0][tid];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) w = sbest[k][tid] < w ? sbest[k][tid] : w;
+    idx_out[row0 + tid] = (long long)(uint32_t)(w & 0xFFFFFFFFull);
+  }
+}
+
 }  // namespace sdvar
 
 using namespace sdvar;
+
+extern "C" int sdvar_vq_nearest_code(const float* z_NC, const float* codebook, long long N, int Cvae, int V, long long* idx_out,
+                                     void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(z_NC && codebook && idx_out, "NULL argument");
+  SDVAR_REQUIRE(Cvae == kC, "Cvae=%d unsupported (32)", Cvae);
+  SDVAR_REQUIRE(N > 0 && V > 0, "bad geometry N=%lld V=%d", N, V);
+  SDVAR_REQUIRE(((uintptr_t)codebook & 15) == 0, "codebook must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfileScope prof(st, FAM_VQ, (double)N * (Cvae * 4.0 + 8.0) + (double)V * Cvae * 4.0);
+  const long long blocks = (N + kNcRows - 1) / kNcRows;
+  vq_nearest_code_kernel<<<(unsigned)blocks, 256, 0, st>>>(z_NC, codebook, N, V, idx_out);
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
 
 extern "C" int sdvar_vq_next_input(const long long* idx_Bl, int B, int pn, int HW, int pn_next, int Cvae,
                                    const float* codebook, const float* phi_w, const float* phi_b, float* f_hat,

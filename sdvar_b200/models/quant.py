@@ -123,5 +123,32 @@ class VectorQuantizer2(nn.Module):
     def forward(self, *a, **k):
         raise NotImplementedError("VectorQuantizer2.forward is VAE training (SURVEY.md section 2 row 6): out of scope")
 
-    def f_to_idxBl_or_fhat(self, *a, **k):
-        raise NotImplementedError("encode side (nearest-code search) is SURVEY.md 8f #3: not built yet")
+    # ---- encode side ------------------------------------------------------------
+    def f_to_idxBl_or_fhat(self, f_BChw: torch.Tensor, to_fhat: bool, v_patch_nums=None):
+        """Multi-scale residual quantisation of an encoder feature map (models/quant.py:135-166): per scale, area-downsample
+        the residual, take the nearest codebook entry (``sdvar_vq_nearest_code``), add Phi(bicubic_up(embedding)) to f_hat
+        (``sdvar_vq_next_input``) and continue on ``f - f_hat``.  Returns the token lists (B, pn*pn) or the f_hat snapshots.
+        The reference subtracts each scale from a running residual; here the residual is recomputed as ``f - f_hat`` (one
+        rounding instead of a chain), so an index can differ from the reference's only on a near-tie of two code distances."""
+        assert not self.using_znorm, "using_znorm=True (cosine nearest neighbour) is not supported"
+        pns = tuple(v_patch_nums) if v_patch_nums is not None else self.v_patch_nums
+        assert tuple(int(p if isinstance(p, int) else p[0]) for p in pns) == self.v_patch_nums, \
+            "only the model's own patch_nums are supported"
+        B, C, H, W = f_BChw.shape
+        HW, SN = self.v_patch_nums[-1], len(self.v_patch_nums)
+        assert C == self.Cvae and H == HW and W == HW, f"feature map {tuple(f_BChw.shape)} does not match the {HW}x{HW} latent grid"
+        f = f_BChw.detach().float().contiguous()
+        f_rest = f.clone()
+        f_hat = torch.zeros_like(f)
+        cb = self.embedding.weight.detach().float().contiguous()
+        out = []
+        for si, pn in enumerate(self.v_patch_nums):
+            z = torch.nn.functional.interpolate(f_rest, size=(pn, pn), mode="area") if si != SN - 1 else f_rest
+            z_NC = z.permute(0, 2, 3, 1).reshape(-1, C).contiguous()
+            idx_N = torch.empty(z_NC.shape[0], dtype=torch.int64, device=f.device)
+            _cabi.vq_nearest_code(z_NC, cb, z_NC.shape[0], C, self.vocab_size, idx_N)
+            idx_Bl = idx_N.view(B, pn * pn)
+            self.next_input_from_idx(si, f_hat, idx_Bl, codebook=cb)
+            torch.sub(f, f_hat, out=f_rest)
+            out.append(f_hat.clone() if to_fhat else idx_Bl)
+        return out

@@ -4,8 +4,8 @@ The decoder (``fhat_to_img``, reference models/vqvae.py:62-63 + models/basic_vae
 four north-star kernel families; it is the boundary right after the path and runs here through
 cuDNN convolutions (library code, bias-free) in bf16 channels-last; GroupNorm+SiLU, bias+skip adds and the 2x upsampling are
 libsdvar kernels.  Parameter names follow the reference checkpoint
-(``decoder.*``, ``post_quant_conv.*``, ``quantize.*``); encode-side tensors (``encoder.*``, ``quant_conv.*``) of a
-real ``vae_ch160v4096z32.pth`` are accepted and ignored by ``load_state_dict``.
+(``decoder.*``, ``post_quant_conv.*``, ``quantize.*``); the encode side (``encoder.*``, ``quant_conv.*``) is
+created when asked for or when a state dict that carries it (a real ``vae_ch160v4096z32.pth``) is loaded.
 """
 from __future__ import annotations
 
@@ -171,13 +171,65 @@ class Decoder(nn.Module):
         return self.conv_out(_gn_act(self.norm_out, h, True))
 
 
+class _Down(nn.Module):
+    """Downsample2x (reference models/basic_vae.py:31-37): zero-pad right/bottom by one, 3x3 conv with stride 2."""
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, pad=(0, 1, 0, 1), mode="constant", value=0))
+
+
+class _EncLevel(nn.Module):
+    def __init__(self, cin, cout, n, with_attn, with_down):
+        super().__init__()
+        self.block = nn.ModuleList([_Res(cin if i == 0 else cout, cout) for i in range(n)])
+        self.attn = nn.ModuleList([_SpatialAttn(cout) for _ in range(n)] if with_attn else [])
+        if with_down:
+            self.downsample = _Down(cout)
+
+    def forward(self, h):
+        for i, b in enumerate(self.block):
+            h = b(h)
+            if len(self.attn):
+                h = self.attn[i](h)
+        return self.downsample(h) if hasattr(self, "downsample") else h
+
+
+class Encoder(nn.Module):
+    """Encode side, reference models/basic_vae.py:99-160; same parameter names (``encoder.*``).  Runs in
+    fp32 through PyTorch/cuDNN (library code, off the hot path): the nearest-code decision downstream is precision sensitive."""
+
+    def __init__(self, ch=160, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, in_channels=3, z_channels=32):
+        super().__init__()
+        n = len(ch_mult)
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, padding=1)
+        in_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList([_EncLevel(ch * in_mult[lv], ch * ch_mult[lv], num_res_blocks, with_attn=(lv == n - 1),
+                                             with_down=(lv != n - 1)) for lv in range(n)])
+        c = ch * ch_mult[-1]
+        self.mid = _Mid(c)
+        self.norm_out, self.conv_out = _gn(c), nn.Conv2d(c, z_channels, 3, padding=1)
+
+    def forward(self, x):
+        h = self.conv_in(x)
+        for lv in self.down:
+            h = lv(h)
+        return self.conv_out(_gn_act(self.norm_out, self.mid(h), True))
+
+
 class VQVAE(nn.Module):
     def __init__(self, vocab_size=4096, z_channels=32, ch=128, dropout=0.0, beta=0.25, using_znorm=False, quant_conv_ks=3,
                  quant_resi=0.5, share_quant_resi=4, default_qresi_counts=0, v_patch_nums=(1, 2, 3, 4, 5, 6, 8, 10, 13, 16),
-                 test_mode=True, decoder_dtype=torch.bfloat16):
+                 test_mode=True, decoder_dtype=torch.bfloat16, with_encoder=False):
         super().__init__()
         self.test_mode, self.V, self.Cvae, self.vocab_size = test_mode, vocab_size, z_channels, vocab_size
+        self._ch, self._qks = ch, quant_conv_ks
         self.decoder = Decoder(ch=ch, z_channels=z_channels)
+        if with_encoder:
+            self._build_encoder()
         self.downsample = 16
         self.quantize = VectorQuantizer2(vocab_size=vocab_size, Cvae=z_channels, using_znorm=using_znorm, beta=beta,
                                          default_qresi_counts=default_qresi_counts, v_patch_nums=v_patch_nums,
@@ -189,6 +241,17 @@ class VQVAE(nn.Module):
             self.eval()
             for p in self.parameters():
                 p.requires_grad_(False)
+
+    def _build_encoder(self):
+        """The encode side is optional: it is created on request or when a state dict carrying ``encoder.*`` is loaded."""
+        if not hasattr(self, "encoder"):
+            dev = self.post_quant_conv.weight.device if hasattr(self, "post_quant_conv") else None
+            self.encoder = Encoder(ch=self._ch, z_channels=self.Cvae).to(dev)
+            self.quant_conv = nn.Conv2d(self.Cvae, self.Cvae, self._qks, padding=self._qks // 2).to(dev)
+            if self.test_mode:
+                self.encoder.eval(); self.quant_conv.eval()
+                for p in list(self.encoder.parameters()) + list(self.quant_conv.parameters()):
+                    p.requires_grad_(False)
 
     def _decoder_exec(self):
         """bf16 channels-last copy of (post_quant_conv, decoder), refreshed when the fp32 master weights change."""
@@ -222,14 +285,38 @@ class VQVAE(nn.Module):
                 outs.append(self.fhat_to_img(f_hat))
         return self.fhat_to_img(f_hat) if last_one else outs
 
-    def img_to_idxBl(self, *a, **k):
-        raise NotImplementedError("encode side (Encoder + nearest-code search) is SURVEY.md 8f #3: not built yet")
+    def embed_to_img(self, ms_h_BChw: List[torch.Tensor], all_to_max_scale: bool = True, last_one: bool = False):
+        """models/vqvae.py:78-82"""
+        fh = self.quantize.embed_to_fhat(ms_h_BChw, all_to_max_scale=all_to_max_scale, last_one=last_one)
+        return self.fhat_to_img(fh) if last_one else [self.fhat_to_img(f) for f in fh]
+
+    @torch.no_grad()
+    def encode_features(self, inp_img_no_grad: torch.Tensor) -> torch.Tensor:
+        """quant_conv(encoder(img)) (models/vqvae.py:66), fp32 without TF32 convolutions."""
+        if not hasattr(self, "encoder"):
+            raise RuntimeError("this VQVAE was built without its encode side: construct it with with_encoder=True or load a "
+                               "state dict that carries encoder.* / quant_conv.*")
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return self.quant_conv(self.encoder(inp_img_no_grad.float()))
+
+    @torch.no_grad()
+    def img_to_idxBl(self, inp_img_no_grad: torch.Tensor, v_patch_nums=None) -> List[torch.Tensor]:
+        """models/vqvae.py:65-67: image (B,3,H,W) in [-1,1] -> token lists [(B, pn*pn) int64]."""
+        return self.quantize.f_to_idxBl_or_fhat(self.encode_features(inp_img_no_grad), to_fhat=False, v_patch_nums=v_patch_nums)
+
+    @torch.no_grad()
+    def img_to_reconstructed_img(self, x: torch.Tensor, v_patch_nums=None, last_one: bool = False):
+        """models/vqvae.py:84-90"""
+        ls = self.quantize.f_to_idxBl_or_fhat(self.encode_features(x), to_fhat=True, v_patch_nums=v_patch_nums)
+        return self.fhat_to_img(ls[-1]) if last_one else [self.fhat_to_img(f) for f in ls]
 
     def forward(self, *a, **k):
         raise NotImplementedError("VQVAE.forward is VAE training: out of scope")
 
     def load_state_dict(self, state_dict: Dict[str, Any], strict=True, assign=False):
-        sd = {k: v for k, v in state_dict.items() if not k.startswith(("encoder.", "quant_conv."))}
+        if any(k.startswith("encoder.") for k in state_dict):
+            self._build_encoder()
+        sd = dict(state_dict)
         if "quantize.ema_vocab_hit_SV" in sd and sd["quantize.ema_vocab_hit_SV"].shape != self.quantize.ema_vocab_hit_SV.shape:
             sd["quantize.ema_vocab_hit_SV"] = self.quantize.ema_vocab_hit_SV
         self._dec_cache = None

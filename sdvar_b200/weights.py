@@ -178,13 +178,54 @@ def _decoder_shapes(ch: int, z: int, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, 
     return out
 
 
+def _encoder_shapes(ch: int, z: int, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, in_channels=3, prefix="encoder."):
+    """(name, shape) list mirroring reference models/basic_vae.py:99-142 (Encoder.__init__)."""
+    out = []
+
+    def conv(name, cin, cout, k):
+        out.append((name + ".weight", (cout, cin, k, k)))
+        out.append((name + ".bias", (cout,)))
+
+    def norm(name, c):
+        out.append((name + ".weight", (c,)))
+        out.append((name + ".bias", (c,)))
+
+    def res(name, cin, cout):
+        norm(name + ".norm1", cin); conv(name + ".conv1", cin, cout, 3)
+        norm(name + ".norm2", cout); conv(name + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(name + ".nin_shortcut", cin, cout, 1)
+
+    def attn(name, c):
+        norm(name + ".norm", c); conv(name + ".qkv", c, 3 * c, 1); conv(name + ".proj_out", c, c, 1)
+
+    nres = len(ch_mult)
+    in_mult = (1,) + tuple(ch_mult)
+    conv(prefix + "conv_in", in_channels, ch, 3)
+    block_in = ch
+    for i_level in range(nres):
+        block_in, block_out = ch * in_mult[i_level], ch * ch_mult[i_level]
+        for i_block in range(num_res_blocks):
+            res(f"{prefix}down.{i_level}.block.{i_block}", block_in, block_out)
+            block_in = block_out
+            if i_level == nres - 1:
+                attn(f"{prefix}down.{i_level}.attn.{i_block}", block_in)
+        if i_level != nres - 1:
+            conv(f"{prefix}down.{i_level}.downsample.conv", block_in, block_in, 3)
+    res(prefix + "mid.block_1", block_in, block_in)
+    attn(prefix + "mid.attn_1", block_in)
+    res(prefix + "mid.block_2", block_in, block_in)
+    norm(prefix + "norm_out", block_in)
+    conv(prefix + "conv_out", block_in, z, 3)
+    return out
+
+
 def vqvae_state_dict(V: int = 4096, Cvae: int = 32, ch: int = 160, patch_nums: Sequence[int] = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16),
                      share_quant_resi: int = 4, seed: int = 0, device="cpu", with_encoder: bool = False,
                      tag: str = "vae") -> Dict[str, torch.Tensor]:
-    """Inference-side VQVAE state dict (quantizer + post_quant_conv + decoder).
+    """VQVAE state dict: quantizer + post_quant_conv + decoder, plus encoder + quant_conv with ``with_encoder``.
 
-    Keys follow reference models/vqvae.py:36-50 and models/quant.py:27-39.  The encoder and
-    ``quant_conv`` are encode-side only and omitted unless asked for.
+    Keys follow reference models/vqvae.py:36-50, models/basic_vae.py:99-208 and models/quant.py:27-39.
     """
     sd: Dict[str, torch.Tensor] = {}
     sd["quantize.embedding.weight"] = hashed(f"{tag}.codebook", seed, (V, Cvae), 1.0, device)
@@ -194,7 +235,10 @@ def vqvae_state_dict(V: int = 4096, Cvae: int = 32, ch: int = 160, patch_nums: S
         sd[f"quantize.quant_resi.qresi_ls.{i}.bias"] = hashed(f"{tag}.phi{i}.b", seed, (Cvae,), 0.02, device)
     sd["post_quant_conv.weight"] = hashed(f"{tag}.pqc.w", seed, (Cvae, Cvae, 3, 3), 0.06, device)
     sd["post_quant_conv.bias"] = hashed(f"{tag}.pqc.b", seed, (Cvae,), 0.02, device)
-    for name, shape in _decoder_shapes(ch, Cvae):
+    shapes = _decoder_shapes(ch, Cvae)
+    if with_encoder:
+        shapes = shapes + _encoder_shapes(ch, Cvae) + [("quant_conv.weight", (Cvae, Cvae, 3, 3)), ("quant_conv.bias", (Cvae,))]
+    for name, shape in shapes:
         if ".norm" in name and name.endswith(".weight"):
             sd[name] = 1.0 + hashed(f"{tag}.{name}", seed, shape, 0.05, device)
         elif name.endswith(".bias"):
@@ -202,6 +246,4 @@ def vqvae_state_dict(V: int = 4096, Cvae: int = 32, ch: int = 160, patch_nums: S
         else:
             fan_in = shape[1] * shape[2] * shape[3]
             sd[name] = hashed(f"{tag}.{name}", seed, shape, 1.0 / math.sqrt(fan_in), device)
-    if with_encoder:
-        raise NotImplementedError("encode side is out of scope (SURVEY.md 8f #3)")
     return sd

@@ -36,8 +36,10 @@ def test_no_cpu_fallback():
     vae, var = build_vae_var("cpu", patch_nums=(1, 2, 3, 4), ch=32, depth=2)
     with pytest.raises(cabi.SdvarError):
         var.autoregressive_infer_cfg(1, 3)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):            # built without its encode side
         vae.img_to_idxBl(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(cabi.SdvarError):          # the nearest-code search has no CPU path either
+        vae.quantize.f_to_idxBl_or_fhat(torch.zeros(1, 32, 4, 4), to_fhat=False)
 
 
 def test_product_never_imports_oracle():
@@ -75,11 +77,10 @@ def test_state_dict_surface_matches_reference_checkpoint_keys():
               "blocks.0.attn.proj.bias", "blocks.1.ffn.fc2.weight", "blocks.0.ada_gss", "shared_ada_lin.1.weight",
               "head_nm.ada_lin.1.bias", "head.weight"):
         assert k in keys, k
-    # a real VQVAE checkpoint also carries encode-side tensors; they are accepted and ignored
-    sd = vqvae_state_dict(ch=32, patch_nums=(1, 2, 3, 4))
-    sd["encoder.conv_in.weight"] = torch.zeros(1)
-    sd["quant_conv.bias"] = torch.zeros(1)
-    vae.load_state_dict(sd, strict=True)
+    # a real VQVAE checkpoint also carries the encode side; loading it creates encoder / quant_conv
+    assert not hasattr(vae, "encoder")
+    vae.load_state_dict(vqvae_state_dict(ch=32, patch_nums=(1, 2, 3, 4), with_encoder=True), strict=True)
+    assert "encoder.down.4.attn.1.proj_out.weight" in vae.state_dict() and "quant_conv.weight" in vae.state_dict()
 
 
 def test_stage_tables_and_phi_index():

@@ -136,3 +136,46 @@ def test_param_counts_match_readme():
         n = (C * 32 + C) + 1001 * C + C + 680 * C + 10 * C + depth * (3 * C * C + 2 * C + depth + C * C + C + 8 * C * C + 5 * C + 6 * C * C + 6 * C) \
             + (2 * C * C + 2 * C) + (4096 * C + 4096)
         assert abs(n / 1e6 - want) < 0.6, (depth, n / 1e6)
+
+
+# ---- encode side ------------------------------------------------------------------------------------
+def _encode_golden():
+    return np.load(os.path.join(G, "encode.npz"))
+
+
+def test_encode_oracle_matches_reference_golden():
+    """oracle restatement of VectorQuantizer2.f_to_idxBl_or_fhat (models/quant.py:135-166) and of quant_conv(Encoder(img))
+    vs fixtures generated by the real reference: tokens of all 10 scales identical, f_hat / features to fp32 round-off."""
+    from oracle.ref_model import RefEncoder, RefVQ
+    from sdvar_b200.weights import vqvae_state_dict
+    g = _encode_golden()
+    sd = vqvae_state_dict(ch=32, patch_nums=P256, with_encoder=True)
+    vq = RefVQ(sd, P256)
+    f = torch.from_numpy(g["f"])
+    idx = vq.f_to_idxBl_or_fhat(f, to_fhat=False)
+    for si, t in enumerate(idx):
+        assert torch.equal(t, torch.from_numpy(g[f"idx_{si}"].astype(np.int64))), si
+    fh = vq.f_to_idxBl_or_fhat(f, to_fhat=True)
+    assert torch.allclose(fh[-1], torch.from_numpy(g["f_hat_last"]), atol=1e-6)
+    assert torch.allclose(fh[3], torch.from_numpy(g["f_hat_3"]), atol=1e-6)
+    feat = RefEncoder(sd).encode_features(torch.from_numpy(g["img"]))
+    assert torch.allclose(feat, torch.from_numpy(g["feat"]), atol=2e-6), float((feat - torch.from_numpy(g["feat"])).abs().max())
+
+
+def test_nearest_code_spec_matches_reference_argmin():
+    """C spec of the nearest-code search (fixed fma order) vs the reference's addmm/argmin on the golden feature map: the same
+    tokens at every scale (no near-ties in the fixture), plus the tie rule (duplicate code rows -> lowest index)."""
+    from oracle import spec
+    from oracle.ref_model import RefVQ
+    from sdvar_b200.weights import vqvae_state_dict
+    g = _encode_golden()
+    sd = vqvae_state_dict(ch=32, patch_nums=P256)
+    vq = RefVQ(sd, P256)
+    idx = vq.f_to_idxBl_or_fhat(torch.from_numpy(g["f"]), to_fhat=False, nearest=lambda z: spec.nearest_code(z, vq.codebook))
+    for si, t in enumerate(idx):
+        assert torch.equal(t, torch.from_numpy(g[f"idx_{si}"].astype(np.int64))), si
+    cb = vq.codebook.clone()
+    cb[7] = cb[3000]
+    cb[9] = cb[3000]
+    z = cb[[3000, 5, 9]].clone()
+    assert spec.nearest_code(z, cb).tolist() == [7, 5, 7]
