@@ -146,8 +146,31 @@ def cpu_reference_run(args, n_images: int, steps: int, warmup: int, device_for_i
                        f"oracle/ref_model.py:sd_generate + decoder, {warmup} warm-up"), dt, stats
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner on the first collective) must not share stdout with the ONE JSON line:
+    fd 1 points at stderr while the benchmark runs and is restored by _emit."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)
+
+
 def main():
     args = parse()
+    _quiet_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -163,16 +186,16 @@ def main():
             return 0
         dev = f"cuda:{local}" if has_cuda else "cpu"
         cb, dt, stats = cpu_reference_run(args, args.cpu_sample_images, args.steps, args.warmup, dev)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
+        _emit({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                           "config": {"workload": workload, "note": "CPU reference arm: bounded sample of the same workload"},
                           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0, "accept_stats": {k: stats[k] for k in ("rounds", "target_passes", "accepted_tokens", "rejected_tokens")}}))
+                          "gpu_launches": 0, "accept_stats": {k: stats[k] for k in ("rounds", "target_passes", "accepted_tokens", "rejected_tokens")}})
         return 0
 
     if not has_cuda:
-        print(json.dumps({"error": "no CUDA device: sdvar_b200 has no CPU fallback"}))
+        _emit({"error": "no CUDA device: sdvar_b200 has no CPU fallback"})
         return 2
     import torch.distributed as dist
     torch.cuda.set_device(local)
@@ -289,7 +312,7 @@ def main():
         cb, _, _ = cpu_reference_run(args, args.cpu_sample_images, 1, 0, dev)
         out["cpu_baseline"] = cb
     if rank == 0:
-        print(json.dumps(out))
+        _emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
