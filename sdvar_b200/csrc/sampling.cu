@@ -91,6 +91,16 @@ __device__ __forceinline__ f32x2 spec_expf2(float x0, float x1) {
   return mul2(mul2(p, pk2(u2f(s0), u2f(s1))), splat2(u2f((uint32_t)(-100 + 127) << 23)));
 }
 
+// IEEE a / b for a >= 0 and b > 0.  ptxas' inline division has a fast path for operands with ordinary exponents and CALLs a
+// ~60-instruction subroutine otherwise -- and a ZERO numerator counts as "otherwise".  Most numerators here are exact zeros
+// (masked-out vocabulary entries), which sent every warp through the subroutine on every division (40 % of K3's
+// instructions).  Dividing 1 instead and selecting 0 afterwards gives the same bits (0 / b == +0).
+__device__ __forceinline__ float fdiv_nz(float a, float b) {
+  const bool z = a == 0.0f;
+  const float q = __fdiv_rn(z ? 1.0f : a, b);
+  return z ? 0.0f : q;
+}
+
 // ---- block reductions.  `slot` alternates between two smem buffers so one barrier per reduction suffices.
 struct RedSmem {
   float f[2][2][kWarps];
@@ -269,7 +279,7 @@ k3_sample_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int 
       const float Z = block_sum(z, sm, slot);
       float tot = 0.0f;
 #pragma unroll
-      for (int e = 0; e < E; ++e) { p[e] = __fdiv_rn(p[e], Z); tot = __fadd_rn(tot, p[e]); }
+      for (int e = 0; e < E; ++e) { p[e] = fdiv_nz(p[e], Z); tot = __fadd_rn(tot, p[e]); }
       tot = block_sum(tot, sm, slot);      // canonical mass of the whole row = mass{key <= kmax}
       // Midpoint bisection on the canonical masked mass with early exit: lo is good (mass{key<=lo} <= thr, nL = #{key<=lo}),
       // hi is bad.  The mass only changes at key values, so once at most one key separates lo from hi no threshold in
@@ -318,14 +328,28 @@ k3_sample_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int 
       const float Z2 = block_sum(z, sm, slot);
       float best = -1.0f, bestp = 0.0f;
       int bi = 0x7FFFFFFF;
+      const bool filtered = (top_k > 0 && top_k < V) || thr >= 0.0f;   // block-uniform: masked entries (exact zeros) exist
+      if (filtered) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
+        for (int i = 0; i < NV; ++i) {
+          const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float pv = __fdiv_rn(ex[4 * i + c], Z2);
-          const float r = __fdiv_rn(pv, nn[c]);
-          if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; bestp = pv; }
+          for (int c = 0; c < 4; ++c) {
+            const float pv = fdiv_nz(ex[4 * i + c], Z2);
+            const float r = fdiv_nz(pv, nn[c]);
+            if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; bestp = pv; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float pv = __fdiv_rn(ex[4 * i + c], Z2);
+            const float r = __fdiv_rn(pv, nn[c]);
+            if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; bestp = pv; }
+          }
         }
       }
       const unsigned long long w = block_max_u64(pack_best(best, bi), sm, slot);
@@ -510,7 +534,7 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
         const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float r = __fdiv_rn(anyp ? rv[4 * i + q] : pv[4 * i + q], nn[q]);
+          const float r = fdiv_nz(anyp ? rv[4 * i + q] : pv[4 * i + q], nn[q]);
           if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + q; }
         }
       }
