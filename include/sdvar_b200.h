@@ -98,6 +98,10 @@ int sdvar_vq_next_input(const long long* idx_Bl, int B, int pn, int HW, int pn_n
                         const float* phi_w, const float* phi_b, float* f_hat, float* next_map, float* scratch,
                         void* stream);
 
+/* test hook: the kernels' exponential (oracle/spec_c: sdvar_spec_expf) applied element-wise through the packed fp32x2 and the
+ * scalar code path, so the arithmetic spec can be pinned bit for bit on adversarial inputs.  x[n] <= 0 (or -inf). */
+int sdvar_debug_spec_expf(const float* x, long long n, float* y_packed, float* y_scalar, void* stream);
+
 /* encode side: nearest codebook entry per row, reference models/quant.py:155-157
  * (`d = |z|^2 + |e|^2 - 2 z e^T; argmin`).  z_NC (N,Cvae) fp32, codebook (V,Cvae) fp32, idx_out (N) int64.
  * d = fma(-2, <z,e>, |z|^2 + |e|^2), dot products as sequential fma chains over c (oracle/spec_c: sdvar_spec_nearest_code),

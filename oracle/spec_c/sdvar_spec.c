@@ -41,8 +41,11 @@ static inline uint32_t fkey(float f) {
 /* exp(x) for x <= ~88: Cody-Waite reduction, degree-7 Taylor/Horner in fmaf, exact 2^n scaling */
 float sdvar_spec_expf(float x) {
   if (x < -104.0f) return 0.0f; /* also -inf */
-  const float t = x * 1.44269504088896340736f;
-  const float n = rintf(t);
+  /* n = rint(x * log2 e) with ONE rounding: the product enters the 1.5 * 2^23 addition unrounded (a fused multiply-add), whose
+   * result has ulp 1, so the addition itself rounds to the nearest integer (ties to even).  Stated as an fma on purpose: ptxas
+   * contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, so a two-rounding definition could not be kept on the GPU. */
+  const float tm = fmaf(x, 1.44269504088896340736f, 12582912.0f);
+  const float n = tm - 12582912.0f;
   float r = fmaf(n, -0.693145751953125f, x);
   r = fmaf(n, -1.42860682030941723212e-6f, r);
   float p = 1.0f / 5040.0f;

@@ -25,6 +25,7 @@ EXPORTS = [
     "sdvar_embed_next_map", "sdvar_first_map", "sdvar_ln_modulate", "sdvar_silu_bf16", "sdvar_f32_to_bf16",
     "sdvar_gemm_bf16", "sdvar_attention", "sdvar_var_forward", "sdvar_profile_begin", "sdvar_profile_end",
     "sdvar_groupnorm_silu_nhwc", "sdvar_bias_residual_nhwc", "sdvar_upsample2x_nhwc", "sdvar_vq_nearest_code",
+    "sdvar_debug_spec_expf",
 ]
 PROFILE_FAMILIES = ("gemm", "attention", "ln_modulate", "sample", "verify", "vq", "embed", "misc")
 
@@ -135,6 +136,11 @@ def vq_next_input(idx_Bl, B, pn, HW, pn_next, Cvae, codebook, phi_w, phi_b, f_ha
 def vq_nearest_code(z_NC, codebook, N, Cvae, V, idx_out):
     _check(lib().sdvar_vq_nearest_code(ptr(z_NC), ptr(codebook), C.c_longlong(N), Cvae, V, ptr(idx_out), stream_ptr()),
            "sdvar_vq_nearest_code")
+
+
+def debug_spec_expf(x, y_packed, y_scalar):
+    _check(lib().sdvar_debug_spec_expf(ptr(x), C.c_longlong(x.numel()), ptr(y_packed), ptr(y_scalar), stream_ptr()),
+           "sdvar_debug_spec_expf")
 
 
 def embed_next_map(next_map, B, l, Cvae, Cm, W, b, lvl_pos, x, ldx_tokens, tok_off):

@@ -20,10 +20,10 @@ constexpr int kWarps = kThreads / 32;
 // exact-or-once-rounded steps (2^(n+100) then 2^-100), which rounds identically to a single multiplication by 2^n.
 __device__ __forceinline__ float spec_expf(float x) {
   const float xc = fmaxf(x, -104.0f);
-  const float t = __fmul_rn(xc, 1.44269504088896340736f);
-  // rintf(t) and (int)n without the quarter-rate FRND / F2I conversions: t is in [-151, 0], so t + 1.5*2^23 lands in the binade
-  // with ulp 1 and the addition itself rounds to nearest-even; the integer is the mantissa difference
-  const float tm = __fadd_rn(t, 12582912.0f);
+  // n = rint(xc * log2 e) with one rounding and without the quarter-rate FRND / F2I conversions: the exact product is added to
+  // 1.5*2^23 inside one fma (the spec is stated that way), the sum lands in the binade with ulp 1, so the fma itself rounds to
+  // nearest-even; the integer is the mantissa difference
+  const float tm = __fmaf_rn(xc, 1.44269504088896340736f, 12582912.0f);
   const float n = __fsub_rn(tm, 12582912.0f);
   float r = __fmaf_rn(n, -0.693145751953125f, xc);
   r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
@@ -71,8 +71,7 @@ __device__ __forceinline__ f32x2 splat2(float c) { return pk2(c, c); }
 // (exp(x0), exp(x1)), both x <= 0 (or -inf); every lane operation is the one spec_expf performs, in the same order
 __device__ __forceinline__ f32x2 spec_expf2(float x0, float x1) {
   const f32x2 xc = pk2(fmaxf(x0, -104.0f), fmaxf(x1, -104.0f));
-  const f32x2 t = mul2(xc, splat2(1.44269504088896340736f));
-  const f32x2 tm = add2(t, splat2(12582912.0f));
+  const f32x2 tm = fma2(xc, splat2(1.44269504088896340736f), splat2(12582912.0f));
   const f32x2 n = add2(tm, splat2(-12582912.0f));
   f32x2 r = fma2(n, splat2(-0.693145751953125f), xc);
   r = fma2(n, splat2(-1.42860682030941723212e-6f), r);
@@ -191,6 +190,18 @@ __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v
 // (value, index) -> u64 whose max is "largest value, then lowest index"
 __device__ __forceinline__ unsigned long long pack_best(float r, int idx) {
   return ((unsigned long long)fkey(r) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
+}
+
+// test hook: y[i] = (packed, scalar) spec exponentials of x[i], so the exp spec can be pinned element by element
+__global__ void spec_expf_kernel(const float* __restrict__ x, long long n, float* __restrict__ y_packed, float* __restrict__ y_scalar) {
+  for (long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 2LL * gridDim.x * blockDim.x) {
+    const float a = x[i], b = (i + 1 < n) ? x[i + 1] : 0.0f;
+    float e0, e1;
+    unpk2(spec_expf2(a, b), e0, e1);
+    y_packed[i] = e0;
+    y_scalar[i] = spec_expf(a);
+    if (i + 1 < n) { y_packed[i + 1] = e1; y_scalar[i + 1] = spec_expf(b); }
+  }
 }
 
 // ================================================================================================
@@ -729,6 +740,15 @@ extern "C" int sdvar_verify_top1(const float* xt, const long long* draft_idx, in
     case 8: top1_match_kernel<8><<<grid, kThreads, 0, st>>>(xt, draft_idx, B, L, seg, match, n_match); break;
     default: SDVAR_REQUIRE(false, "V=%d unsupported", V);
   }
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
+
+// y_packed / y_scalar [n] = the kernels' exponential (fp32x2 and scalar code paths) of x[n] <= 0: bit-exactness test hook
+extern "C" int sdvar_debug_spec_expf(const float* x, long long n, float* y_packed, float* y_scalar, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(x && y_packed && y_scalar && n > 0, "bad argument");
+  spec_expf_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(x, n, y_packed, y_scalar);
   SDVAR_LAUNCH_CHECK();
   return SDVAR_OK;
 }

@@ -450,3 +450,31 @@ def test_encoder_features_and_img_round_trip():
     bare = VQVAE(vocab_size=4096, z_channels=32, ch=32, v_patch_nums=pns).to(DEV)
     with pytest.raises(RuntimeError):
         bare.img_to_idxBl(img)
+
+
+def test_spec_expf_bit_exact_on_adversarial_inputs(cuda_lib):
+    """The kernels' exponential (packed fp32x2 path and scalar path) vs oracle/spec_c:sdvar_spec_expf, bit for bit, on a dense
+    sweep of [-110, 0], on inputs whose product with log2(e) sits within a few ulp of a half-integer (where a two-rounding and
+    a one-rounding range reduction would pick different n) and on the special values 0, -0, -104, below -104, -inf."""
+    from oracle import spec
+    l2e = np.float64(1.4426950408889634)
+    dense = -np.linspace(0.0, 110.0, 200001, dtype=np.float64)
+    halves = []
+    for k in range(0, 151):
+        x0 = np.float32(-(k + 0.5) / l2e)
+        for d in range(-6, 7):                      # neighbours of the half-integer crossing, in ulps
+            v = x0
+            for _ in range(abs(d)):
+                v = np.nextafter(v, np.float32(-200.0) if d < 0 else np.float32(0.0))
+            halves.append(v)
+    special = np.array([0.0, -0.0, -104.0, -104.00001, -103.99999, -150.0, -1e30, -np.inf], dtype=np.float32)
+    x = np.concatenate([dense.astype(np.float32), np.array(halves, dtype=np.float32), special])
+    xt = torch.from_numpy(x)
+    ref = spec.expf(xt)
+    yp = torch.empty_like(xt, device=DEV)
+    ys = torch.empty_like(xt, device=DEV)
+    cuda_lib.debug_spec_expf(xt.to(DEV), yp, ys)
+    torch.cuda.synchronize()
+    assert torch.equal(yp.cpu().view(torch.int32), ref.view(torch.int32))
+    assert torch.equal(ys.cpu().view(torch.int32), ref.view(torch.int32))
+    assert float(ref[-1]) == 0.0 and float(ref[-4]) == 0.0
