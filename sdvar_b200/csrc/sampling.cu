@@ -474,27 +474,29 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
     mt = fkey_inv(kt);
     md = fkey_inv(kd);
     // pass 2: canonical exp sums; the owner of element d keeps its two exponentials
-    f32x2 z2 = pk2(0.0f, 0.0f);                    // (zt, zd): two independent in-order chains
-    const f32x2 negm = pk2(-mt, -md);              // a - m == a + (-m) exactly
+    // two adjacent elements of the SAME row per packed instruction: the pairs are the register pairs LDS.128 delivers and
+    // STS.128 takes back, so no moves are spent on re-pairing; the row sums stay scalar, in element order (the canonical order)
+    float zt = 0.0f, zd = 0.0f;
+    const f32x2 nmt = pk2(-mt, -mt), nmd = pk2(-md, -md);    // a - m == a + (-m) exactly
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float4 a = st4[i * kThreads + tid], c = sd4[i * kThreads + tid];
-      float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float x0, x1;
-        unpk2(add2(pk2(av[q], cv[q]), negm), x0, x1);
-        const f32x2 e2 = spec_expf2(x0, x1);
-        z2 = add2(z2, e2);
-        unpk2(e2, av[q], cv[q]);
-      }
+      float4 a = st4[i * kThreads + tid], c = sd4[i * kThreads + tid];
+      float x0, x1;
+      unpk2(add2(pk2(a.x, a.y), nmt), x0, x1);
+      unpk2(spec_expf2(x0, x1), a.x, a.y);
+      unpk2(add2(pk2(a.z, a.w), nmt), x0, x1);
+      unpk2(spec_expf2(x0, x1), a.z, a.w);
+      unpk2(add2(pk2(c.x, c.y), nmd), x0, x1);
+      unpk2(spec_expf2(x0, x1), c.x, c.y);
+      unpk2(add2(pk2(c.z, c.w), nmd), x0, x1);
+      unpk2(spec_expf2(x0, x1), c.z, c.w);
+      zt = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(zt, a.x), a.y), a.z), a.w);
+      zd = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(zd, c.x), c.y), c.z), c.w);
       // the exponentials replace the staged logits (each thread rewrites only the chunks it owns), so neither the accept
       // test nor a residual resample has to exponentiate again
-      st4[i * kThreads + tid] = make_float4(av[0], av[1], av[2], av[3]);
-      sd4[i * kThreads + tid] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+      st4[i * kThreads + tid] = a;
+      sd4[i * kThreads + tid] = c;
     }
-    float zt, zd;
-    unpk2(z2, zt, zd);
     block_sum2(zt, zd, sm, slot);  // zt, zd now hold Zt, Zd
     const float izt = __fdiv_rn(1.0f, zt), izd = __fdiv_rn(1.0f, zd);
     // the owner of element d evaluates the accept test and publishes the per-token outputs itself
