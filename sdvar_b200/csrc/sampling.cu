@@ -454,10 +454,7 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
       bulk_g2s(stage_buf + (st ^ 1) * 2 * V, xt + nrow * V, V * 4, &full[st ^ 1]);
       bulk_g2s(stage_buf + (st ^ 1) * 2 * V + V, xd + nrow * V, V * 4, &full[st ^ 1]);
     }
-    const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
-    const int j = seg_of(seg, pos);
     const int d = (int)draft_idx[row];
-    const float uu = u[row];
     mbar_wait_par(&full[st], (k >> 1) & 1);
     float4* st4 = reinterpret_cast<float4*>(stage_buf + st * 2 * V);
     float4* sd4 = st4 + V / 4;
@@ -498,11 +495,15 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
       sd4[i * kThreads + tid] = c;
     }
     block_sum2(zt, zd, sm, slot);  // zt, zd now hold Zt, Zd
-    const float izt = __fdiv_rn(1.0f, zt), izd = __fdiv_rn(1.0f, zd);
-    // the owner of element d evaluates the accept test and publishes the per-token outputs itself
+    // the owner of element d evaluates the accept test and publishes the per-token outputs itself; everything only it needs
+    // (1/Z, image / position / stage of the row, u) is computed there and not by the other 255 threads
     const bool owner = ((d >> 2) & (kThreads - 1)) == tid;
     int rej = 0;
     if (owner) {
+      const float izt = __fdiv_rn(1.0f, zt), izd = __fdiv_rn(1.0f, zd);
+      const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+      const int j = seg_of(seg, pos);
+      const float uu = u[row];
       const float* rt = stage_buf + st * 2 * V;
       const float pdv = __fmul_rn(rt[d], izt), qdv = __fmul_rn(rt[V + d], izd);
       rej = (__fmul_rn(uu, qdv) < pdv) ? 0 : 1;
@@ -519,6 +520,7 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
     const int acc = __syncthreads_or(rej) ? 0 : 1;
     int out = d;
     if (!acc) {  // block-uniform: residual resample from the staged logits
+      const float izt = __fdiv_rn(1.0f, zt), izd = __fdiv_rn(1.0f, zd);
       const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
       float4 nz[NV];
 #pragma unroll
