@@ -244,6 +244,10 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                   l4[(i >> 1) & 3] += e0 + e1;     // row sum in fp32 before rounding (rounding errors of P average out)
                   pk[i >> 1] = pack_bf16x2(e0, e1);
                 }
+              } else if (__all_sync(0xffffffffu, nvalid <= 0)) {
+                // the whole 32-key chunk lies past every row's visible prefix (tail of the last key tile): P = 0, no exponentials
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = 0u;
               } else {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
