@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDVAR_ABI_VERSION 1
+#define SDVAR_ABI_VERSION 2
 #define SDVAR_MAX_SEG 16   /* max stages in one launch (a pyramid has 10) */
 #define SDVAR_MAX_DEPTH 64 /* max transformer blocks per model */
 
@@ -50,15 +50,17 @@ int sdvar_num_sms(int device);
  * replaces models/var.py:199-202 (CFG mix) + models/helpers.py:6-19 (sample_with_top_k_top_p_).
  * rows are (b,pos), b<B, pos<L; cond logits at row b*in_ld+in_off+pos and uncond logits at row
  * (B+b)*in_ld+in_off+pos of logits_2BLV (fp32, V % 1024 == 0, V <= 8192): in_ld/in_off select one stage's slice
- * of a multi-stage verify window (in_ld=L, in_off=0 for a dense (2B,L,V) tensor).  Outputs are dense (B,L,..).  seg_begin_host[S+1] partitions [0,L) into stages;
+ * of a multi-stage verify window (in_ld=L, in_off=0 for a dense (2B,L,V) tensor).  Outputs go to row b*out_ld+out_off+pos
+ * of idx_out / mixed_out / prob_out (out_ld=L, out_off=0: dense (B,L,..)), so the draft's per-stage launches can fill the
+ * window-shaped buffers K4 reads.  seg_begin_host[S+1] partitions [0,L) into stages;
  * stage j uses t1[j]=fl32(1+t_j), t2[j]=fl32(t_j), t_j = cfg*si/(K-1):  x = cond*t1 - uncond*t2.
  * top_k<=0 disables top-k; one_minus_top_p<0 disables top-p (else it is fl32(1-top_p)).
- * noise (B*L,V) is the pre-drawn Exp(1) tensor torch.multinomial would draw; NULL => no sampling
- * (filter only).  Outputs (each may be NULL): idx_out (B,L) int64; mixed_out (B,L,V) the mixed logits
- * with removed entries set to -inf (the reference masks them in place); prob_out (B,L) the sampled
+ * noise (B*L,V) is the pre-drawn Exp(1) tensor torch.multinomial would draw (row b*L+pos); NULL => no sampling
+ * (filter only).  Outputs (each may be NULL): idx_out int64; mixed_out the mixed logits
+ * with removed entries set to -inf (the reference masks them in place); prob_out the sampled
  * token's probability under the filtered distribution.  Arithmetic is bit-exact to
- * oracle/spec_c/sdvar_spec.c:sdvar_spec_sample. */
-int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L, int in_ld, int in_off, int V,
+ * oracle/spec_c/sdvar_spec.c:sdvar_spec_sample.  No workspace. */
+int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L, int in_ld, int in_off, int out_ld, int out_off, int V,
                                const int* seg_begin_host, int S,
                                const float* t1_host, const float* t2_host, int top_k, float one_minus_top_p,
                                const float* noise, long long* idx_out, float* mixed_out, float* prob_out,
@@ -69,13 +71,17 @@ int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L, int in_ld
  * sdvar_verify_top1 below).  Per token row (b,pos): p=softmax(xt), q=softmax(xd) (both the
  * mixed+filtered logits, (B,L,V) fp32), accept iff u*q[d] < p[d]; on reject
  * out = argmax(max(0,p-q)/noise) (argmax(p/noise) if the residual is identically 0), else out=d.
+ * A whole verify window is ONE launch: seg_begin_host[S+1] partitions [0,L) into its stages.
+ * u (B*L) and noise (B*L,V): row b*L+pos when stage_major_aux == 0; when stage_major_aux != 0 they are the per-stage
+ * draws laid end to end, row B*seg_begin[j] + b*l_j + (pos - seg_begin[j]) for pos in stage j.
  * Per (image, stage): first_reject (index within the stage of the first rejected token, l_j if none)
  * and n_accept; per image accepted_stages = #leading stages without a reject;
  * summary[0]=min_b accepted_stages, [1]=#accepted tokens, [2]=#rejected tokens, [3]=0.
- * p_d_out/q_d_out (B,L) may be NULL.  workspace: >= 4 bytes, zero on first use (the kernel leaves it
- * zero).  Bit-exact to oracle/spec_c/sdvar_spec.c:sdvar_spec_verify. */
+ * p_d_out/q_d_out (B,L) may be NULL.  workspace: sdvar_verify_workspace_bytes(B,S) bytes, zero on first use (the kernel
+ * leaves it zero).  Bit-exact to oracle/spec_c/sdvar_spec.c:sdvar_spec_verify. */
+long long sdvar_verify_workspace_bytes(int B, int S);
 int sdvar_verify_accept_resample(const float* xt, const float* xd, const long long* draft_idx, const float* u,
-                                 const float* noise, int B, int L, int V, const int* seg_begin_host, int S,
+                                 const float* noise, int stage_major_aux, int B, int L, int V, const int* seg_begin_host, int S,
                                  long long* out_idx, unsigned char* accept, float* p_d_out, float* q_d_out,
                                  int* first_reject, int* n_accept, int* accepted_stages, int* summary,
                                  int* workspace, void* stream);
@@ -90,13 +96,20 @@ int sdvar_verify_top1(const float* xt, const long long* draft_idx, int B, int L,
  * replaces models/var.py:205-211 + models/quant.py:187-196 (get_next_autoregressive_input),
  * :199-206 (Phi), :218-226 (PhiPartiallyShared index):
  *   h = codebook[idx] (B,l,Cvae) -> (B,Cvae,pn,pn) -> bicubic up to HWxHW (skipped when pn==HW)
- *   f_hat += 0.5*h + 0.5*(conv3x3(h; phi_w, phi_b))            (in place, fp32 (B,Cvae,HW,HW))
+ *   d = (1-r)*h + r*(conv3x3(h; phi_w, phi_b)),  r = resi_ratio = |quant_resi| (0.5 in the released checkpoints)
+ *   f_hat += d                                                  (in place, fp32 (B,Cvae,HW,HW))
+ *   f_rest -= d  when f_rest != NULL                            (encode side: the running residual of models/quant.py:163)
  *   next_map = area-down(f_hat) to pn_next x pn_next            ((B,Cvae,pn_next,pn_next) fp32)
  * pn_next == 0 => last stage, next_map not written.  phi_w (Cvae,Cvae,3,3), phi_b (Cvae) are the
- * Phi module selected by the caller.  Cvae must be 32, HW <= 32.  scratch: B*Cvae*HW*HW floats. */
+ * Phi module selected by the caller.  Cvae must be 32, HW <= 32.  No scratch is needed. */
 int sdvar_vq_next_input(const long long* idx_Bl, int B, int pn, int HW, int pn_next, int Cvae, const float* codebook,
-                        const float* phi_w, const float* phi_b, float* f_hat, float* next_map, float* scratch,
-                        void* stream);
+                        const float* phi_w, const float* phi_b, float resi_ratio, float* f_hat, float* next_map,
+                        float* f_rest, void* stream);
+
+/* the area-down half of the step above on its own (models/quant.py:192, F.interpolate(mode='area')): next_map
+ * (B,Cvae,pn_next,pn_next) = adaptive average of f_hat (B,Cvae,HW,HW) over windows [floor(o*HW/pn), ceil((o+1)*HW/pn)).  Same
+ * kernel, so a stage input rebuilt from a committed f_hat is bit-identical to the one sdvar_vq_next_input returned. */
+int sdvar_vq_area_down(const float* f_hat, int B, int HW, int pn_next, int Cvae, float* next_map, void* stream);
 
 /* test hook: the kernels' exponential (oracle/spec_c: sdvar_spec_expf) applied element-wise through the packed fp32x2 and the
  * scalar code path, so the arithmetic spec can be pinned bit for bit on adversarial inputs.  x[n] <= 0 (or -inf). */
@@ -121,9 +134,13 @@ int sdvar_first_map(const float* cond_2BC, int B2, int first_l, int C, const flo
 /* ---- transformer pieces ----------------------------------------------------------------------
  * LayerNorm (eps, no affine) + adaLN modulate, fp32 in -> bf16 out (models/basic_var.py:157-158,173):
  *   out[r,:] = LN(x[r,:]) * (1 + scale[img(r),:]) + shift[img(r),:],  img(r) = r / tokens_per_img;
- * scale/shift are rows of an fp32 matrix with leading dimension ld_mod (the adaLN output). */
+ * scale/shift are rows of an fp32 matrix with leading dimension ld_mod (the adaLN output).
+ * slot_map (device int32[#images of the pass], or NULL = identity): per-image resources (adaLN rows here, KV-cache slots in
+ * the QKV epilogue and the attention) of pass-image i live at slot slot_map[i].  This is how a SUB-BATCH of images that
+ * share a stage runs as one dense pass while every image keeps its own cache slot (per-image ragged acceptance,
+ * SURVEY.md 8f #2; replaces the batch-global accept_length of models/var.py:1349-1350). */
 int sdvar_ln_modulate(const float* x, int M, int C, int tokens_per_img, const float* scale, const float* shift,
-                      int ld_mod, float eps, sdvar_bf16* out, void* stream);
+                      int ld_mod, const int* slot_map, float eps, sdvar_bf16* out, void* stream);
 
 /* out = silu(x) as bf16 (the SiLU in front of every ada_lin, models/basic_var.py:147,170) */
 int sdvar_silu_bf16(const float* x, long long n, sdvar_bf16* out, void* stream);
@@ -131,7 +148,7 @@ int sdvar_f32_to_bf16(const float* x, long long n, sdvar_bf16* out, void* stream
 
 /* K1: D = epilogue(A[M,K] @ W[N,K]^T), bf16 operands, fp32 accumulation in TMEM (tcgen05.mma),
  * operands staged by TMA.  Replaces F.linear at models/basic_var.py:52,93,119,156 and
- * models/var.py:125.  K % 64 == 0, N % 16 == 0, A/W 16-byte aligned rows. */
+ * models/var.py:125.  K % 64 == 0, N % 32 == 0, A/W 16-byte aligned rows. */
 typedef enum {
   SDVAR_EPI_F32 = 0,        /* out_f32[M,N] = acc + bias                                  (head, ada_lin) */
   SDVAR_EPI_BF16 = 1,       /* out_bf16[M,N] = acc + bias                                                 */
@@ -150,6 +167,7 @@ typedef struct {
   const float* gate;
   int ld_gate;
   int tokens_per_img;
+  const int* slot_map;       /* device int32[#images] or NULL: gate row / KV-cache slot of pass-image i (see sdvar_ln_modulate) */
   /* QKV (models/basic_var.py:93-109): N = 3*H*64; rows r = img*Lq + t.  q -> q_out[img,h,t,:] bf16
    * (normalised, times exp(min(scale_mul[h], ln 100)) when l2norm), k -> k_cache[img,h,kv_off+t,:]
    * (normalised), v -> vT_cache[img,h,:,kv_off+t] (transposed). bias = cat(q_bias,0,v_bias). */
@@ -170,10 +188,12 @@ int sdvar_gemm_bf16(const sdvar_bf16* A, int lda, const sdvar_bf16* W, int ldw, 
  * (models/var.py:108-113; incremental decode is S=1).  softmax scale `scale` (1.0 with l2 norm).
  * logit_bound_log (device, [H], may be NULL): when given, the caller guarantees |q.k| <= exp(min(logit_bound_log[h], ln 100)) <= 40
  * for every head (true for l2-normalised attention, where it is the scale_mul parameter): the kernel then uses that bound
- * as the softmax reference point and runs the one-pass ping-pong variant; NULL selects the general two-pass kernel. */
+ * as the softmax reference point and runs the one-pass ping-pong variant; NULL selects the general two-pass kernel.
+ * slot_map / cache_slots: pass-image i reads the K/V of cache slot slot_map[i] (< cache_slots = image slots the caches hold);
+ * NULL / 0 = identity with cache_slots = imgs. */
 int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, const sdvar_bf16* vT_cache, int imgs, int H,
                     int Lq, int Lmax, int Lmax_pad, int kv_off, const int* seg_begin_host, int S, float scale,
-                    const float* logit_bound_log, sdvar_bf16* out, void* stream);
+                    const float* logit_bound_log, const int* slot_map, int cache_slots, sdvar_bf16* out, void* stream);
 
 /* ---- decoder boundary ------------------------------------------------------------
  * GroupNorm(32 groups, eps, affine) optionally followed by SiLU on channels-last bf16 activations (reference
@@ -216,6 +236,8 @@ typedef struct {
   int kv_off;               /* tokens already in the cache */
   int S;                    /* window stages */
   int seg_begin[SDVAR_MAX_SEG + 1];
+  const int* slot_map;      /* device int32[imgs] or NULL: cache / adaLN slot of pass-image i (sub-batch passes) */
+  int cache_slots;          /* image slots held by k_cache / vT_cache / ada / head_mod (0 = imgs) */
   float* x;                 /* (imgs*Lq, C) fp32 residual stream, in/out */
   const float* ada;         /* adaLN rows [gamma1 gamma2 scale1 scale2 shift1 shift2] (6C fp32) of block i, image r at
                                ada + i*ada_block_stride + r*ada_img_stride (strides in floats) */

@@ -14,6 +14,8 @@ load_state_dict, so the fixtures hold only small inputs/outputs:
   encode.npz     reference encode side (`python oracle/make_golden.py encode` writes only this one): VectorQuantizer2.
                  f_to_idxBl_or_fhat (models/quant.py:135-166) on a hashed 16x16 feature map (tokens of all 10 scales, final
                  f_hat) and quant_conv(Encoder(img)) (models/vqvae.py:66, models/basic_vae.py:144-160) on a hashed image
+  real_width.npz reference VAR.forward teacher-forced logits at the north-star widths (`... widths`): VAR-d16 and a 2-block
+                 model at the d30 width (C=1920, H=30), active gates
 """
 import contextlib
 import io
@@ -79,9 +81,40 @@ def encode_golden():
     print("wrote encode.npz", {k: v.shape for k, v in o.items()})
 
 
+def width_golden():
+    """north-star WIDTHS (`python oracle/make_golden.py widths` writes only this one): teacher-forced logits of the real
+    reference VAR.forward (models/var.py:217-259) for (a) VAR-d16 (C=1024, H=16, 16 blocks) and (b) a 2-block model at the
+    d30 width (C=1920, H=30), 256 px pyramid, B=1, with ACTIVE residual gates (gamma_bias=0.5) and a peaked head
+    (init_head=1.0) so that every block moves the logits.  Stored: the first 96 logit columns of every row, the row argmax
+    and |logit|max."""
+    os.makedirs(OUT, exist_ok=True)
+    kw = dict(gamma_bias=0.5, init_head=1.0)
+    o = {}
+    for name, depth, C, H, seed, lab in (("d16", 16, 1024, 16, 1, 207), ("w30", 2, 1920, 30, 2, 388)):
+        with quiet():
+            import models as R
+            vae = R.VQVAE(vocab_size=4096, z_channels=32, ch=32, test_mode=True, share_quant_resi=4, v_patch_nums=P256)
+            m = R.VAR(vae_local=vae, depth=depth, embed_dim=C, num_heads=H, attn_l2_norm=True, patch_nums=P256,
+                      flash_if_available=False, fused_if_available=False).eval()
+        m.load_state_dict(var_state_dict(depth, patch_nums=P256, seed=seed, tag=name, embed_dim=C, num_heads=H, **kw), strict=True)
+        m.cond_drop_rate = 0.0                      # the reference drops labels even in eval (var.py:226)
+        x_in = hashed(f"golden.width.{name}.x", 0, (1, 679, 32), 1.0)
+        with torch.no_grad():
+            logits = m(torch.tensor([lab]), x_in)
+        o[f"{name}_logits_slice"] = logits[:, :, :96].numpy()
+        o[f"{name}_argmax"] = logits.argmax(-1).numpy().astype(np.int16)
+        o[f"{name}_absmax"] = np.float32(logits.abs().max())
+        o[f"{name}_label"] = np.int64(lab)
+        print(name, "absmax", float(logits.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "real_width.npz"), **o)
+    print("wrote real_width.npz", os.path.getsize(os.path.join(OUT, "real_width.npz")) // 1024, "KiB")
+
+
 def main():
     if sys.argv[1:] == ["encode"]:
         return encode_golden()
+    if sys.argv[1:] == ["widths"]:
+        return width_golden()
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     with quiet():
@@ -208,6 +241,7 @@ def main():
     o["f_hat"] = f.numpy()
     np.savez_compressed(os.path.join(OUT, "d16.npz"), **o)
     encode_golden()
+    width_golden()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
 

@@ -25,6 +25,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define LANES 256
@@ -95,13 +96,32 @@ static int find_seg(const int* seg_begin, int S, int pos) {
 }
 
 /* ---- K3 ------------------------------------------------------------------------------- */
+/* Two arithmetic regimes, chosen by the (launch-uniform) filter setting:
+ *   no filter  : softmax sum in the canonical 256-lane float order over the whole row (canon_sum);
+ *   top-k/top-p: every sum is an INTEGER sum of fixed-point terms, hence independent of the summation order -- the kernel
+ *                may compact the survivors of the top-k cut and histogram them in any order and still agree bit for bit:
+ *                  E_v    = (uint64) rint(e_v * 2^40)             e_v = sdvar_spec_expf(x_v - max) in [0,1]
+ *                  Z      = (float)(sum_v E_v) * 2^-40            (u64 -> f32 round-to-nearest, exact scaling)
+ *                  mass_v = (uint32) rint((e_v / Z) * 2^30)       top-p mass of v, exact integer cumulation
+ *                  removed by top-p  <=>  sum{mass_w : w alive, x_w <= x_v} <= floor(thr * 2^30)  and x_v is not the row maximum
+ *                (the reference accumulates float probabilities in ascending order, helpers.py:12-16; tie groups are kept whole).
+ * Ordering is by VALUE: -0 and +0 are the same logit (keys are taken of x + 0). */
+#define FIX_E 1099511627776.0f /* 2^40 */
+#define FIX_M 1073741824.0f    /* 2^30 */
+
+static int cmp_u32(const void* a, const void* b) {
+  const uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
 /* one row; x is scratch of V floats that receives the mixed+masked logits */
 static long long sample_row(const float* xc, const float* xu, float t1, float t2, int V, int top_k, float thr,
                             const float* noise, float* x, float* e, uint32_t* keys, float* prob_out) {
   for (int v = 0; v < V; ++v) x[v] = xc[v] * t1 - xu[v] * t2; /* two roundings of the products, then the difference */
-  for (int v = 0; v < V; ++v) keys[v] = fkey(x[v]);
+  for (int v = 0; v < V; ++v) keys[v] = fkey(x[v] + 0.0f);
+  const int filtered = (top_k > 0 && top_k < V) || thr >= 0.0f;
   if (top_k > 0 && top_k < V) {
-    /* K = key of the k-th largest = largest K with #{key >= K} >= k */
+    /* K = key of the k-th largest = largest K with #{key >= K} >= k (ties with the k-th value survive) */
     uint32_t K = 0;
     for (int bit = 31; bit >= 0; --bit) {
       const uint32_t tr = K | (1u << bit);
@@ -116,25 +136,52 @@ static long long sample_row(const float* xc, const float* xu, float t1, float t2
   uint32_t kmax = 0;
   for (int v = 0; v < V; ++v) { if (x[v] > m) m = x[v]; if (keys[v] > kmax) kmax = keys[v]; }
   for (int v = 0; v < V; ++v) e[v] = sdvar_spec_expf(x[v] - m);
+  if (!filtered) {
+    if (noise == NULL) return -1;
+    const float Z2 = canon_sum(e, V, NULL, 0);
+    float best = -1.0f, bp = 0.0f;
+    long long bi = 0;
+    for (int v = 0; v < V; ++v) {
+      const float p = e[v] / Z2;
+      const float r = p / noise[v];
+      if (r > best) { best = r; bi = v; bp = p; }
+    }
+    if (prob_out) *prob_out = bp;
+    return bi;
+  }
+  uint64_t Zi = 0;
+  for (int v = 0; v < V; ++v) Zi += (uint64_t)llrintf(e[v] * FIX_E);
   if (thr >= 0.0f) {
-    const float Z = canon_sum(e, V, NULL, 0);
-    /* p_v = e_v / Z, mass(K) = canon_sum(p_v [key_v <= K]); K* = largest K with mass(K) <= thr */
-    static __thread float p[65536];
-    for (int v = 0; v < V; ++v) p[v] = e[v] / Z;
-    uint32_t K = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t tr = K | (1u << bit);
-      if (canon_sum(p, V, keys, tr) <= thr) K = tr;
+    const float Z = (float)Zi * (1.0f / FIX_E);
+    const uint32_t thr_i = (uint32_t)(thr * FIX_M); /* floor */
+    static __thread uint32_t mass[65536], srt[65536];
+    int n = 0;
+    for (int v = 0; v < V; ++v) {
+      mass[v] = (e[v] > 0.0f) ? (uint32_t)llrintf((e[v] / Z) * FIX_M) : 0u;
+      if (x[v] > -INFINITY) srt[n++] = keys[v];
+    }
+    qsort(srt, (size_t)n, sizeof(uint32_t), cmp_u32);
+    /* T = largest alive key with mass{key <= T} <= thr_i (0 = nothing removable) */
+    uint32_t T = 0;
+    for (int i = 0; i < n; ++i) {
+      if (i + 1 < n && srt[i + 1] == srt[i]) continue; /* evaluate a tie group at its last member */
+      uint64_t acc = 0;
+      for (int v = 0; v < V; ++v)
+        if (x[v] > -INFINITY && keys[v] <= srt[i]) acc += mass[v];
+      if (acc <= thr_i) T = srt[i]; else break;
     }
     for (int v = 0; v < V; ++v)
-      if (keys[v] <= K && keys[v] != kmax) { x[v] = -INFINITY; e[v] = 0.0f; }
+      if (x[v] > -INFINITY && keys[v] <= T && keys[v] != kmax) { x[v] = -INFINITY; e[v] = 0.0f; }
   }
   if (noise == NULL) return -1;
-  const float Z2 = canon_sum(e, V, NULL, 0);
+  uint64_t Z2i = 0;
+  for (int v = 0; v < V; ++v) Z2i += (uint64_t)llrintf(e[v] * FIX_E);
+  const float Z2 = (float)Z2i * (1.0f / FIX_E);
   float best = -1.0f;
   long long bi = 0;
   float bp = 0.0f;
   for (int v = 0; v < V; ++v) {
+    if (e[v] == 0.0f) continue; /* masked or underflowed: cannot win the race (0 / noise = 0 > -1 only when nothing else is alive) */
     const float p = e[v] / Z2;
     const float r = p / noise[v];
     if (r > best) { best = r; bi = v; bp = p; }

@@ -21,7 +21,7 @@ EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_QKV = range(5)
 
 EXPORTS = [
     "sdvar_abi_version", "sdvar_last_error", "sdvar_arch_check", "sdvar_num_sms", "sdvar_launch_count",
-    "sdvar_sample_cfg_topk_topp", "sdvar_verify_accept_resample", "sdvar_verify_top1", "sdvar_vq_next_input",
+    "sdvar_sample_cfg_topk_topp", "sdvar_verify_accept_resample", "sdvar_verify_workspace_bytes", "sdvar_verify_top1", "sdvar_vq_next_input", "sdvar_vq_area_down",
     "sdvar_embed_next_map", "sdvar_first_map", "sdvar_ln_modulate", "sdvar_silu_bf16", "sdvar_f32_to_bf16",
     "sdvar_gemm_bf16", "sdvar_attention", "sdvar_var_forward", "sdvar_profile_begin", "sdvar_profile_end",
     "sdvar_groupnorm_silu_nhwc", "sdvar_bias_residual_nhwc", "sdvar_upsample2x_nhwc", "sdvar_vq_nearest_code",
@@ -36,7 +36,7 @@ class SdvarError(RuntimeError):
 
 class GemmEpilogue(C.Structure):
     _fields_ = [("epilogue", C.c_int), ("bias", C.c_void_p), ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p),
-                ("ldo", C.c_int), ("gate", C.c_void_p), ("ld_gate", C.c_int), ("tokens_per_img", C.c_int),
+                ("ldo", C.c_int), ("gate", C.c_void_p), ("ld_gate", C.c_int), ("tokens_per_img", C.c_int), ("slot_map", C.c_void_p),
                 ("q_out", C.c_void_p), ("k_cache", C.c_void_p), ("vT_cache", C.c_void_p), ("scale_mul", C.c_void_p),
                 ("H", C.c_int), ("Lq", C.c_int), ("Lmax", C.c_int), ("Lmax_pad", C.c_int), ("kv_off", C.c_int),
                 ("l2norm", C.c_int)]
@@ -54,7 +54,7 @@ class VarWeights(C.Structure):
 
 class Pass(C.Structure):
     _fields_ = [("imgs", C.c_int), ("Lq", C.c_int), ("Lmax", C.c_int), ("Lmax_pad", C.c_int), ("kv_off", C.c_int),
-                ("S", C.c_int), ("seg_begin", C.c_int * (MAX_SEG + 1)),
+                ("S", C.c_int), ("seg_begin", C.c_int * (MAX_SEG + 1)), ("slot_map", C.c_void_p), ("cache_slots", C.c_int),
                 ("x", C.c_void_p), ("ada", C.c_void_p), ("ada_block_stride", C.c_longlong), ("ada_img_stride", C.c_longlong),
                 ("head_mod", C.c_void_p),
                 ("k_cache", C.c_void_p * MAX_DEPTH), ("vT_cache", C.c_void_p * MAX_DEPTH),
@@ -73,6 +73,7 @@ def lib():
         l = C.CDLL(LIB_PATH)
         l.sdvar_last_error.restype = C.c_char_p
         l.sdvar_launch_count.restype = C.c_longlong
+        l.sdvar_verify_workspace_bytes.restype = C.c_longlong
         _LIB = l
     return _LIB
 
@@ -88,6 +89,10 @@ def ptr(t: Optional[torch.Tensor]):
     if not t.is_cuda:
         raise SdvarError("C-ABI arguments must be CUDA tensors: libsdvar_b200 has no CPU path")
     assert t.is_contiguous(), "C-ABI arguments must be contiguous"
+    if t.device.index != torch.cuda.current_device():
+        # the library launches on the CURRENT device and stream: a pointer of another GPU would be dereferenced there
+        raise SdvarError(f"tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                         f"wrap the call in torch.cuda.device({t.device.index})")
     return C.c_void_p(t.data_ptr())
 
 
@@ -109,16 +114,28 @@ def launch_count() -> int:
 
 # ---- thin typed wrappers (argument meaning: include/sdvar_b200.h) ---------------------------------
 def sample_cfg_topk_topp(logits_2BLV, B, L, V, seg_begin, t1, t2, top_k, one_minus_top_p, noise, idx_out, mixed_out,
-                         prob_out, in_ld=None, in_off=0):
-    _check(lib().sdvar_sample_cfg_topk_topp(ptr(logits_2BLV), B, L, L if in_ld is None else in_ld, in_off, V, _iarr(seg_begin), len(seg_begin) - 1, _farr(t1),
+                         prob_out, in_ld=None, in_off=0, out_ld=None, out_off=0):
+    _check(lib().sdvar_sample_cfg_topk_topp(ptr(logits_2BLV), B, L, L if in_ld is None else in_ld, in_off,
+                                            L if out_ld is None else out_ld, out_off, V, _iarr(seg_begin), len(seg_begin) - 1, _farr(t1),
                                             _farr(t2), int(top_k), C.c_float(one_minus_top_p), ptr(noise), ptr(idx_out),
                                             ptr(mixed_out), ptr(prob_out), stream_ptr()), "sdvar_sample_cfg_topk_topp")
 
 
+def verify_workspace_ints(B, S) -> int:
+    """number of int32 elements the verify workspace needs (sdvar_verify_workspace_bytes / 4); zero it once"""
+    n = int(lib().sdvar_verify_workspace_bytes(int(B), int(S)))
+    if n < 0:
+        raise SdvarError(f"sdvar_verify_workspace_bytes({B},{S}) failed ({n})")
+    return n // 4
+
+
 def verify_accept_resample(xt, xd, draft_idx, u, noise, B, L, V, seg_begin, out_idx, accept, p_d, q_d, first_reject,
-                           n_accept, accepted_stages, summary, workspace):
-    _check(lib().sdvar_verify_accept_resample(ptr(xt), ptr(xd), ptr(draft_idx), ptr(u), ptr(noise), B, L, V,
-                                              _iarr(seg_begin), len(seg_begin) - 1, ptr(out_idx), ptr(accept), ptr(p_d),
+                           n_accept, accepted_stages, summary, workspace, stage_major_aux=False):
+    S = len(seg_begin) - 1
+    if workspace.numel() < verify_workspace_ints(B, S):
+        raise SdvarError(f"verify workspace too small: {workspace.numel()} int32 < {verify_workspace_ints(B, S)}")
+    _check(lib().sdvar_verify_accept_resample(ptr(xt), ptr(xd), ptr(draft_idx), ptr(u), ptr(noise), int(bool(stage_major_aux)), B, L, V,
+                                              _iarr(seg_begin), S, ptr(out_idx), ptr(accept), ptr(p_d),
                                               ptr(q_d), ptr(first_reject), ptr(n_accept), ptr(accepted_stages),
                                               ptr(summary), ptr(workspace), stream_ptr()), "sdvar_verify_accept_resample")
 
@@ -128,9 +145,13 @@ def verify_top1(xt, draft_idx, B, L, V, seg_begin, match, n_match):
                                    ptr(n_match), stream_ptr()), "sdvar_verify_top1")
 
 
-def vq_next_input(idx_Bl, B, pn, HW, pn_next, Cvae, codebook, phi_w, phi_b, f_hat, next_map):
+def vq_next_input(idx_Bl, B, pn, HW, pn_next, Cvae, codebook, phi_w, phi_b, f_hat, next_map, resi_ratio=0.5, f_rest=None):
     _check(lib().sdvar_vq_next_input(ptr(idx_Bl), B, pn, HW, pn_next, Cvae, ptr(codebook), ptr(phi_w), ptr(phi_b),
-                                     ptr(f_hat), ptr(next_map), C.c_void_p(0), stream_ptr()), "sdvar_vq_next_input")
+                                     C.c_float(resi_ratio), ptr(f_hat), ptr(next_map), ptr(f_rest), stream_ptr()), "sdvar_vq_next_input")
+
+
+def vq_area_down(f_hat, B, HW, pn_next, Cvae, next_map):
+    _check(lib().sdvar_vq_area_down(ptr(f_hat), B, HW, pn_next, Cvae, ptr(next_map), stream_ptr()), "sdvar_vq_area_down")
 
 
 def vq_nearest_code(z_NC, codebook, N, Cvae, V, idx_out):
@@ -153,8 +174,8 @@ def first_map(cond, B2, first_l, Cm, pos_start, lvl_pos, x, ldx_tokens, tok_off)
                                  stream_ptr()), "sdvar_first_map")
 
 
-def ln_modulate(x, M, Cm, tokens_per_img, scale, shift, ld_mod, eps, out):
-    _check(lib().sdvar_ln_modulate(ptr(x), M, Cm, tokens_per_img, C.c_void_p(scale), C.c_void_p(shift), ld_mod,
+def ln_modulate(x, M, Cm, tokens_per_img, scale, shift, ld_mod, eps, out, slot_map=None):
+    _check(lib().sdvar_ln_modulate(ptr(x), M, Cm, tokens_per_img, C.c_void_p(scale), C.c_void_p(shift), ld_mod, ptr(slot_map),
                                    C.c_float(eps), ptr(out), stream_ptr()), "sdvar_ln_modulate")
 
 
@@ -170,9 +191,11 @@ def gemm_bf16(A, lda, W, ldw, M, N, K, epi: GemmEpilogue):
     _check(lib().sdvar_gemm_bf16(ptr(A), lda, ptr(W), ldw, M, N, K, C.byref(epi), stream_ptr()), "sdvar_gemm_bf16")
 
 
-def attention(q, k_cache, vT_cache, imgs, H, Lq, Lmax, Lmax_pad, kv_off, seg_begin, scale, out, logit_bound_log=None):
+def attention(q, k_cache, vT_cache, imgs, H, Lq, Lmax, Lmax_pad, kv_off, seg_begin, scale, out, logit_bound_log=None,
+              slot_map=None, cache_slots=0):
     _check(lib().sdvar_attention(ptr(q), ptr(k_cache), ptr(vT_cache), imgs, H, Lq, Lmax, Lmax_pad, kv_off,
-                                 _iarr(seg_begin), len(seg_begin) - 1, C.c_float(scale), ptr(logit_bound_log), ptr(out), stream_ptr()),
+                                 _iarr(seg_begin), len(seg_begin) - 1, C.c_float(scale), ptr(logit_bound_log), ptr(slot_map),
+                                 int(cache_slots), ptr(out), stream_ptr()),
            "sdvar_attention")
 
 

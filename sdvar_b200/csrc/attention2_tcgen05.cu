@@ -42,6 +42,7 @@ struct Params {
   int H, Lq, kv_off, C, nqt, n_items;
   float log2e_scale;
   const float* scale_mul;  // [H] raw log-scale parameter
+  const int* slot_map;     // pass-image -> KV-cache slot (nullptr: identity)
   __nv_bfloat16* out;
   SegTable seg;
 };
@@ -53,7 +54,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 struct Item {
-  int qt, bh, h, img, q0, nk;
+  int qt, bh, h, img, q0, nk, kvbh;   // kvbh: (cache slot, head) coordinate of the K / V tensor maps
 };
 __device__ __forceinline__ Item decode(const Params& p, int it) {
   Item w;
@@ -62,6 +63,7 @@ __device__ __forceinline__ Item decode(const Params& p, int it) {
   w.img = w.bh / p.H;
   w.h = w.bh - w.img * p.H;
   w.q0 = w.qt * BQ;
+  w.kvbh = (p.slot_map != nullptr ? __ldg(p.slot_map + w.img) : w.img) * p.H + w.h;
   const int t_last = min(w.q0 + BQ, p.Lq) - 1;
   w.nk = (p.kv_off + p.seg.begin[seg_of(p.seg, t_last) + 1] + BKV - 1) / BKV;
   return w;
@@ -129,7 +131,7 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           const uint32_t b = tn % kKS, par = (tn / kKS) & 1;
           ptx::mbar_wait(&k_empty[b], par ^ 1);
           ptx::mbar_expect_tx(&k_full[b], K_BYTES);
-          ptx::tma_load_3d(sK + b * K_BYTES, &tmK, &k_full[b], 0, j * BKV, w.bh);
+          ptx::tma_load_3d(sK + b * K_BYTES, &tmK, &k_full[b], 0, j * BKV, w.kvbh);
         }
       }
     }
@@ -142,8 +144,8 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           const uint32_t b = tn % kVS, par = (tn / kVS) & 1;
           ptx::mbar_wait(&v_empty[b], par ^ 1);
           ptx::mbar_expect_tx(&v_full[b], V_BYTES);
-          ptx::tma_load_3d(sV + b * V_BYTES, &tmV, &v_full[b], j * BKV, 0, w.bh);
-          ptx::tma_load_3d(sV + b * V_BYTES + V_BYTES / 2, &tmV, &v_full[b], j * BKV + 64, 0, w.bh);
+          ptx::tma_load_3d(sV + b * V_BYTES, &tmV, &v_full[b], j * BKV, 0, w.kvbh);
+          ptx::tma_load_3d(sV + b * V_BYTES + V_BYTES / 2, &tmV, &v_full[b], j * BKV + 64, 0, w.kvbh);
         }
       }
     }
@@ -327,7 +329,8 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 int launch_onepass(const void* q, const void* k_cache, const void* vT_cache, int imgs, int H, int Lq, int Lmax, int Lmax_pad, int kv_off,
-                   const int* seg_begin_host, int S, float scale, const float* scale_mul, __nv_bfloat16* out, cudaStream_t st) {
+                   const int* seg_begin_host, int S, float scale, const float* scale_mul, const int* slot_map, int cache_slots,
+                   __nv_bfloat16* out, cudaStream_t st) {
   // tensor maps clipped to the valid kv length: rows past it are zero-filled by TMA without touching HBM
   const int kv_total = kv_off + Lq;
   CUtensorMap tmQ, tmK, tmV;
@@ -335,10 +338,10 @@ int launch_onepass(const void* q, const void* k_cache, const void* vT_cache, int
     const uint64_t dq[3] = {64, (uint64_t)Lq, (uint64_t)imgs * H}, sq[2] = {128, (uint64_t)Lq * 128};
     const uint32_t bq[3] = {64, (uint32_t)BQ, 1};
     if (int rc = make_tmap_bf16(&tmQ, q, 3, dq, sq, bq)) return rc;
-    const uint64_t dk[3] = {64, (uint64_t)kv_total, (uint64_t)imgs * H}, sk[2] = {128, (uint64_t)Lmax * 128};
+    const uint64_t dk[3] = {64, (uint64_t)kv_total, (uint64_t)cache_slots * H}, sk[2] = {128, (uint64_t)Lmax * 128};
     const uint32_t bk[3] = {64, (uint32_t)BKV, 1};
     if (int rc = make_tmap_bf16(&tmK, k_cache, 3, dk, sk, bk)) return rc;
-    const uint64_t dv[3] = {(uint64_t)kv_total, 64, (uint64_t)imgs * H}, sv[2] = {(uint64_t)Lmax_pad * 2, (uint64_t)Lmax_pad * 128};
+    const uint64_t dv[3] = {(uint64_t)kv_total, 64, (uint64_t)cache_slots * H}, sv[2] = {(uint64_t)Lmax_pad * 2, (uint64_t)Lmax_pad * 128};
     const uint32_t bv[3] = {64, 64, 1};
     if (int rc = make_tmap_bf16(&tmV, vT_cache, 3, dv, sv, bv)) return rc;
   }
@@ -348,14 +351,11 @@ int launch_onepass(const void* q, const void* k_cache, const void* vT_cache, int
   p.n_items = p.nqt * H * imgs;
   p.log2e_scale = scale * 1.4426950408889634f;
   p.scale_mul = scale_mul;
+  p.slot_map = slot_map;
   p.out = out;
   p.seg.S = S;
   for (int j = 0; j <= S; ++j) p.seg.begin[j] = seg_begin_host[j];
-  static bool attr_set = false;
-  if (!attr_set) {
-    SDVAR_CUDA(cudaFuncSetAttribute(attention_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_set = true;
-  }
+  SDVAR_SET_SMEM_ONCE(attention_onepass_kernel, kSmemBytes);
   const int sms = sm_count();
   const int grid = p.n_items < sms ? p.n_items : sms;
   attention_onepass_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmQ, tmK, tmV, p);

@@ -35,6 +35,7 @@ struct Params {
   int H, Lq, kv_off, C;
   float scale_log2e;  // softmax scale * log2(e)
   __nv_bfloat16* out;
+  const int* slot_map;  // pass-image -> KV-cache slot (nullptr: identity)
   SegTable seg;
 };
 
@@ -64,6 +65,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, img = blockIdx.z;
   const int bh = img * p.H + h;
+  const int kvbh = (p.slot_map != nullptr ? __ldg(p.slot_map + img) : img) * p.H + h;   // (cache slot, head) of K / V
   const int q0 = qt * BQ;
   // keys visible to the last valid query row of this tile bound the key loop
   const int t_last = min(q0 + BQ, p.Lq) - 1;
@@ -101,12 +103,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int ks = it & 1;
         ptx::mbar_wait(&k_empty[ks], ((it >> 1) & 1) ^ 1);
         ptx::mbar_expect_tx(&k_full[ks], K_BYTES);
-        ptx::tma_load_3d(sK + ks * K_BYTES, &tmK, &k_full[ks], 0, j * BKV, bh);
+        ptx::tma_load_3d(sK + ks * K_BYTES, &tmK, &k_full[ks], 0, j * BKV, kvbh);
         if (it >= nk) {
           ptx::mbar_wait(v_empty, (j & 1) ^ 1);
           ptx::mbar_expect_tx(v_full, V_BYTES);
-          ptx::tma_load_3d(sV, &tmV, v_full, j * BKV, 0, bh);
-          ptx::tma_load_3d(sV + V_BYTES / 2, &tmV, v_full, j * BKV + 64, 0, bh);
+          ptx::tma_load_3d(sV, &tmV, v_full, j * BKV, 0, kvbh);
+          ptx::tma_load_3d(sV + V_BYTES / 2, &tmV, v_full, j * BKV + 64, 0, kvbh);
         }
       }
     }
@@ -242,7 +244,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 namespace sdvar {
 namespace attn2 {
 int launch_onepass(const void* q, const void* k_cache, const void* vT_cache, int imgs, int H, int Lq, int Lmax, int Lmax_pad, int kv_off,
-                   const int* seg_begin_host, int S, float scale, const float* scale_mul, __nv_bfloat16* out, cudaStream_t st);
+                   const int* seg_begin_host, int S, float scale, const float* scale_mul, const int* slot_map, int cache_slots,
+                   __nv_bfloat16* out, cudaStream_t st);
 }
 }  // namespace sdvar
 
@@ -250,7 +253,7 @@ using namespace sdvar;
 
 extern "C" int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, const sdvar_bf16* vT_cache, int imgs, int H,
                                int Lq, int Lmax, int Lmax_pad, int kv_off, const int* seg_begin_host, int S, float scale,
-                               const float* logit_bound_log, sdvar_bf16* out, void* stream) {
+                               const float* logit_bound_log, const int* slot_map, int cache_slots, sdvar_bf16* out, void* stream) {
   if (int rc = check_arch()) return rc;
   SDVAR_REQUIRE(q && k_cache && vT_cache && out, "NULL argument");
   SDVAR_REQUIRE(imgs > 0 && H > 0 && Lq > 0 && kv_off >= 0 && kv_off + Lq <= Lmax && Lmax <= Lmax_pad, "bad geometry");
@@ -258,10 +261,13 @@ extern "C" int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, c
   SDVAR_REQUIRE(S >= 1 && S <= SDVAR_MAX_SEG && seg_begin_host && seg_begin_host[0] == 0 && seg_begin_host[S] == Lq,
                 "segment table must cover [0,Lq)");
   SDVAR_REQUIRE(((uintptr_t)out & 15) == 0, "out alignment");
+  if (cache_slots <= 0) cache_slots = imgs;
+  SDVAR_REQUIRE(slot_map != nullptr || cache_slots == imgs, "cache_slots=%d without a slot map (imgs=%d)", cache_slots, imgs);
   attn::Params p{};
   p.H = H; p.Lq = Lq; p.kv_off = kv_off; p.C = H * attn::D;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.slot_map = slot_map;
   p.seg.S = S;
   for (int j = 0; j <= S; ++j) p.seg.begin[j] = seg_begin_host[j];
   double visible = 0;  // sum over query rows of visible keys
@@ -269,24 +275,20 @@ extern "C" int sdvar_attention(const sdvar_bf16* q, const sdvar_bf16* k_cache, c
   ProfileScope prof((cudaStream_t)stream, FAM_ATTN, 4.0 * 64.0 * visible * imgs * H);
   if (logit_bound_log != nullptr)
     return attn2::launch_onepass(q, k_cache, vT_cache, imgs, H, Lq, Lmax, Lmax_pad, kv_off, seg_begin_host, S, scale, logit_bound_log,
-                                 reinterpret_cast<__nv_bfloat16*>(out), (cudaStream_t)stream);
+                                 slot_map, cache_slots, reinterpret_cast<__nv_bfloat16*>(out), (cudaStream_t)stream);
   CUtensorMap tmQ, tmK, tmV;
   {
     const uint64_t dq[3] = {64, (uint64_t)Lq, (uint64_t)imgs * H}, sq[2] = {128, (uint64_t)Lq * 128};
     const uint32_t bq[3] = {64, (uint32_t)attn::BQ, 1};
     if (int rc = make_tmap_bf16(&tmQ, q, 3, dq, sq, bq)) return rc;
-    const uint64_t dk[3] = {64, (uint64_t)Lmax, (uint64_t)imgs * H}, sk[2] = {128, (uint64_t)Lmax * 128};
+    const uint64_t dk[3] = {64, (uint64_t)Lmax, (uint64_t)cache_slots * H}, sk[2] = {128, (uint64_t)Lmax * 128};
     const uint32_t bk[3] = {64, (uint32_t)attn::BKV, 1};
     if (int rc = make_tmap_bf16(&tmK, k_cache, 3, dk, sk, bk)) return rc;
-    const uint64_t dv[3] = {(uint64_t)Lmax_pad, 64, (uint64_t)imgs * H}, sv[2] = {(uint64_t)Lmax_pad * 2, (uint64_t)Lmax_pad * 128};
+    const uint64_t dv[3] = {(uint64_t)Lmax_pad, 64, (uint64_t)cache_slots * H}, sv[2] = {(uint64_t)Lmax_pad * 2, (uint64_t)Lmax_pad * 128};
     const uint32_t bv[3] = {64, 64, 1};
     if (int rc = make_tmap_bf16(&tmV, vT_cache, 3, dv, sv, bv)) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SDVAR_CUDA(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::kSmemBytes));
-    attr_set = true;
-  }
+  SDVAR_SET_SMEM_ONCE(attn::attention_kernel, attn::kSmemBytes);
   dim3 grid((Lq + attn::BQ - 1) / attn::BQ, H, imgs);
   attn::attention_kernel<<<grid, attn::kThreads, attn::kSmemBytes, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   SDVAR_LAUNCH_CHECK();

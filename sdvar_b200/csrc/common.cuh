@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "../../include/sdvar_b200.h"
 
 namespace sdvar {
@@ -41,6 +43,21 @@ int sm_count();    // multiprocessor count of the current device (cached per thr
       return SDVAR_ERR_CUDA;                                                                   \
     }                                                                                          \
     sdvar::count_launch();                                                                     \
+  } while (0)
+
+// cudaFuncSetAttribute applies to the CURRENT device only: the opt-in to > 48 KiB of dynamic shared memory is repeated
+// once per device (bit d of an atomic mask), so a second GPU driven from the same process gets it too; concurrent
+// first calls at worst set the attribute twice.
+#define SDVAR_SET_SMEM_ONCE(func, bytes)                                                                      \
+  do {                                                                                                        \
+    static std::atomic<unsigned long long> mask__{0};                                                         \
+    int dev__ = 0;                                                                                            \
+    SDVAR_CUDA(cudaGetDevice(&dev__));                                                                        \
+    const unsigned long long bit__ = 1ull << (dev__ & 63);                                                    \
+    if (!(mask__.load(std::memory_order_acquire) & bit__)) {                                                  \
+      SDVAR_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      mask__.fetch_or(bit__, std::memory_order_release);                                                      \
+    }                                                                                                         \
   } while (0)
 
 // ---- optional per-family device timing (bench.py's roofline leg).  Disabled by default: zero overhead on the

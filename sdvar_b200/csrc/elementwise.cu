@@ -11,7 +11,8 @@ constexpr int kLnWarps = 4;
 
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_modulate_kernel(const float* __restrict__ x, int M, int C, int tokens_per_img, const float* __restrict__ scale,
-                   const float* __restrict__ shift, int ld_mod, float eps, __nv_bfloat16* __restrict__ out) {
+                   const float* __restrict__ shift, int ld_mod, const int* __restrict__ slot_map, float eps,
+                   __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(16) float rowbuf[];  // [kLnWarps][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + warp;
@@ -37,7 +38,8 @@ ln_modulate_kernel(const float* __restrict__ x, int M, int C, int tokens_per_img
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) var += __shfl_xor_sync(0xffffffffu, var, off);
   const float rstd = rsqrtf(var / (float)C + eps);
-  const int img = row / tokens_per_img;
+  const int img0 = row / tokens_per_img;
+  const int img = slot_map != nullptr ? __ldg(slot_map + img0) : img0;
   const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)img * ld_mod);
   const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)img * ld_mod);
   uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * C);
@@ -57,7 +59,8 @@ ln_modulate_kernel(const float* __restrict__ x, int M, int C, int tokens_per_img
 template <int NITER>
 __global__ void __launch_bounds__(256, NITER > 15 ? 2 : NITER > 12 ? 3 : 4)   // cap registers: ptxas otherwise hoists all scale/shift loads (127 regs, 2 CTAs/SM)
 ln_modulate_reg_kernel(const float* __restrict__ x, int M, int tokens_per_img, const float* __restrict__ scale,
-                       const float* __restrict__ shift, int ld_mod, float eps, __nv_bfloat16* __restrict__ out) {
+                       const float* __restrict__ shift, int ld_mod, const int* __restrict__ slot_map, float eps,
+                       __nv_bfloat16* __restrict__ out) {
   constexpr int C = NITER * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -81,7 +84,8 @@ ln_modulate_reg_kernel(const float* __restrict__ x, int M, int tokens_per_img, c
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) var += __shfl_xor_sync(0xffffffffu, var, off);
   const float rstd = rsqrtf(var * (1.0f / (float)C) + eps);
-  const int img = row / tokens_per_img;
+  const int img0 = row / tokens_per_img;
+  const int img = slot_map != nullptr ? __ldg(slot_map + img0) : img0;
   const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)img * ld_mod);
   const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)img * ld_mod);
   uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * C);
@@ -112,7 +116,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, long long n, __n
 using namespace sdvar;
 
 extern "C" int sdvar_ln_modulate(const float* x, int M, int C, int tokens_per_img, const float* scale, const float* shift,
-                                 int ld_mod, float eps, sdvar_bf16* out, void* stream) {
+                                 int ld_mod, const int* slot_map, float eps, sdvar_bf16* out, void* stream) {
   if (int rc = check_arch()) return rc;
   SDVAR_REQUIRE(x && scale && shift && out, "NULL argument");
   SDVAR_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && tokens_per_img > 0 && ld_mod % 4 == 0, "bad geometry M=%d C=%d", M, C);
@@ -123,7 +127,7 @@ extern "C" int sdvar_ln_modulate(const float* x, int M, int C, int tokens_per_im
   ProfileScope prof((cudaStream_t)stream, FAM_LN, (double)M * C * 6.0);
 #define SDVAR_LN_REG(NITER)                                                                                              \
   case NITER * 128:                                                                                                      \
-    ln_modulate_reg_kernel<NITER><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, M, tokens_per_img, scale, shift, ld_mod, eps, \
+    ln_modulate_reg_kernel<NITER><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, M, tokens_per_img, scale, shift, ld_mod, slot_map, eps, \
                                                                                 reinterpret_cast<__nv_bfloat16*>(out)); \
     SDVAR_LAUNCH_CHECK();                                                                                                \
     return SDVAR_OK;
@@ -133,7 +137,7 @@ extern "C" int sdvar_ln_modulate(const float* x, int M, int C, int tokens_per_im
   }
 #undef SDVAR_LN_REG
   ln_modulate_kernel<<<(M + kLnWarps - 1) / kLnWarps, kLnWarps * 32, smem, (cudaStream_t)stream>>>(
-      x, M, C, tokens_per_img, scale, shift, ld_mod, eps, reinterpret_cast<__nv_bfloat16*>(out));
+      x, M, C, tokens_per_img, scale, shift, ld_mod, slot_map, eps, reinterpret_cast<__nv_bfloat16*>(out));
   SDVAR_LAUNCH_CHECK();
   return SDVAR_OK;
 }

@@ -250,7 +250,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
           [[maybe_unused]] const float4* g4 = nullptr;
           if constexpr (kResid)   // one gate row per image: warp-uniform most of the time, L1-resident
-            g4 = reinterpret_cast<const float4*>(ep.gate + (size_t)(row < M ? row / ep.tokens_per_img : 0) * ep.ld_gate + col0);
+          {
+            const int gimg = row < M ? row / ep.tokens_per_img : 0;
+            g4 = reinterpret_cast<const float4*>(ep.gate + (size_t)(ep.slot_map != nullptr ? __ldg(ep.slot_map + gimg) : gimg) * ep.ld_gate + col0);
+          }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float4* p = reinterpret_cast<float4*>(srow + ((q ^ (lane & 7)) << 4));   // SWIZZLE_128B: 16-byte unit ^ (row & 7)
@@ -316,11 +319,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 template <int EPI>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, int M, int N, int K, const Epi& ep, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SDVAR_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<EPI>::smem_bytes));
-    attr_set = true;
-  }
+  SDVAR_SET_SMEM_ONCE(gemm2_kernel<EPI>, Cfg<EPI>::smem_bytes);
   const int sms = sm_count();
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int clusters = tiles < sms / 2 ? tiles : sms / 2;

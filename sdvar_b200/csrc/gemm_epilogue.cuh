@@ -14,6 +14,7 @@ struct Epi {
   int ldo;
   const float* gate;
   int ld_gate, tokens_per_img;
+  const int* slot_map;   // pass-image -> gate row / KV-cache slot (nullptr: identity)
   __nv_bfloat16 *q_out, *k_cache, *vT_cache;
   const float* scale_mul;
   int H, Lq, Lmax, Lmax_pad, kv_off, l2norm, C;
@@ -56,7 +57,8 @@ template <int EPI, int BN>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row, int col_base, int M, int N, const Epi& ep, EpiPre& pre) {
   if constexpr (EPI == SDVAR_EPI_RESID_F32) {
     const bool rv = row < M;
-    const float* grow = ep.gate + (size_t)(rv ? row / ep.tokens_per_img : 0) * ep.ld_gate;
+    const int gimg = rv ? row / ep.tokens_per_img : 0;
+    const float* grow = ep.gate + (size_t)(ep.slot_map != nullptr ? __ldg(ep.slot_map + gimg) : gimg) * ep.ld_gate;
     float* xrow = ep.out_f32 + (size_t)row * ep.ldo;
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c) {
@@ -120,17 +122,18 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int row, int col_b
           for (int i = 0; i < 64; ++i) v[i] *= inv;
         }
         const int img = row / ep.Lq, t = row - img * ep.Lq;
+        const int simg = ep.slot_map != nullptr ? __ldg(ep.slot_map + img) : img;   // cache slot of this image
         if (sect < 2) {
           __nv_bfloat16* dst = (sect == 0)
               ? ep.q_out + (((size_t)img * ep.H + h) * ep.Lq + t) * 64
-              : ep.k_cache + (((size_t)img * ep.H + h) * ep.Lmax + ep.kv_off + t) * 64;
+              : ep.k_cache + (((size_t)simg * ep.H + h) * ep.Lmax + ep.kv_off + t) * 64;
           uint4* d = reinterpret_cast<uint4*>(dst);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             d[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                               pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
         } else {
-          __nv_bfloat16* dst = ep.vT_cache + ((size_t)img * ep.H + h) * 64 * ep.Lmax_pad + ep.kv_off + t;
+          __nv_bfloat16* dst = ep.vT_cache + ((size_t)simg * ep.H + h) * 64 * ep.Lmax_pad + ep.kv_off + t;
 #pragma unroll
           for (int i = 0; i < 64; ++i) dst[(size_t)i * ep.Lmax_pad] = __float2bfloat16_rn(v[i]);
         }

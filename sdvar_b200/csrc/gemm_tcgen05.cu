@@ -142,11 +142,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 template <int EPI>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epi& ep, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SDVAR_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_set = true;
-  }
+  SDVAR_SET_SMEM_ONCE(gemm_kernel<EPI>, kSmemBytes);
   const int sms = sm_count();
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sms ? tiles : sms;
@@ -191,6 +187,7 @@ extern "C" int sdvar_gemm_bf16(const sdvar_bf16* A, int lda, const sdvar_bf16* W
   ep.gate = e->gate;
   ep.ld_gate = e->ld_gate;
   ep.tokens_per_img = e->tokens_per_img;
+  ep.slot_map = e->slot_map;
   ep.q_out = reinterpret_cast<__nv_bfloat16*>(e->q_out);
   ep.k_cache = reinterpret_cast<__nv_bfloat16*>(e->k_cache);
   ep.vT_cache = reinterpret_cast<__nv_bfloat16*>(e->vT_cache);

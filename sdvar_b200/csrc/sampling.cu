@@ -207,203 +207,484 @@ __global__ void spec_expf_kernel(const float* __restrict__ x, long long n, float
 // ================================================================================================
 // K3
 // ================================================================================================
-// Register diet: a thread keeps only the order-preserving KEYS of its 4*NV mixed logits (the logit is the exact inverse of
-// its key) plus, during the top-p search, their probabilities; exponentials are recomputed (bit-identically) for the final
-// draw.  ~60 registers -> four 256-thread CTAs per SM, which is what hides the serial latency of the canonical reductions.
+// Two kernels, selected by the launch-uniform filter setting (the spec has the same two regimes):
+//   k3_plain_kernel     no top-k / top-p: CFG mix, softmax in the canonical 256-lane float order, exponential race.
+//   k3_filtered_kernel  top-k and/or top-p.  Round 1 searched the k-th largest key and the top-p threshold by bisection,
+//                       ~26 block-wide barrier rounds of 16 compares per thread each, and ran every exponential and division
+//                       on all V entries although only ~k survive (0.15-0.23 of HBM).  Now:
+//     1. the exact k-th largest value comes from ONE shared-memory histogram pass (512 value-space bins, integer atomics),
+//        a suffix scan over the bins, and an exact rank among the handful of candidates in the crossing bin;
+//     2. the survivors (~top_k of V) are compacted into shared memory together with their noise and vocabulary index, so
+//        exponentials, probabilities, divisions and the race touch ~k/256 entries per thread instead of V/256;
+//     3. every sum of the filtered regime is an integer sum of fixed-point terms (spec: E = rint(e 2^40), mass =
+//        rint(p 2^30)), so it does not depend on the order in which the atomics / the compaction happen to run: the kernel
+//        is free to reorder and still bit-exact to oracle/spec_c; the top-p cut is a second histogram (of masses) + scan +
+//        exact resolution inside the crossing bin.
+//     Degenerate rows (more than 256 candidates in a crossing bin, non-finite value range) take bisection fall-backs.
+constexpr int kBins = 512;
+constexpr float kFixE = 1099511627776.0f;   // 2^40
+constexpr float kFixM = 1073741824.0f;      // 2^30
+
 template <int NV>
 __global__ void __launch_bounds__(kThreads, 4)
-k3_sample_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int in_off, SegTable seg, int top_k, float thr,
-                 const float* __restrict__ noise, long long* __restrict__ idx_out, float* __restrict__ mixed_out,
-                 float* __restrict__ prob_out) {
+k3_plain_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int in_off, int out_ld, int out_off, SegTable seg,
+                const float* __restrict__ noise, long long* __restrict__ idx_out, float* __restrict__ mixed_out,
+                float* __restrict__ prob_out) {
   constexpr int V = NV * 1024;
   constexpr int E = NV * 4;
   __shared__ RedSmem sm;
   int slot = 0;
   const int tid = threadIdx.x;
   const long long rows = (long long)B * L;
-  const uint32_t kneg = fkey(-INFINITY);
   for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
     const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
     const int j = seg_of(seg, pos);
     const float t1 = seg.t1[j], t2 = seg.t2[j];
+    const long long orow = (long long)b * out_ld + out_off + pos;
     const float4* pc = reinterpret_cast<const float4*>(logits + ((long long)b * in_ld + in_off + pos) * V);
     const float4* pu = reinterpret_cast<const float4*>(logits + ((long long)(B + b) * in_ld + in_off + pos) * V);
-    uint32_t key[E];
+    float x[E];
     {
       float4 a[NV], c[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) { a[i] = ldg_stream(pc + i * kThreads + tid); c[i] = ldg_stream(pu + i * kThreads + tid); }
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        key[4 * i + 0] = fkey(__fsub_rn(__fmul_rn(a[i].x, t1), __fmul_rn(c[i].x, t2)));
-        key[4 * i + 1] = fkey(__fsub_rn(__fmul_rn(a[i].y, t1), __fmul_rn(c[i].y, t2)));
-        key[4 * i + 2] = fkey(__fsub_rn(__fmul_rn(a[i].z, t1), __fmul_rn(c[i].z, t2)));
-        key[4 * i + 3] = fkey(__fsub_rn(__fmul_rn(a[i].w, t1), __fmul_rn(c[i].w, t2)));
+        x[4 * i + 0] = __fsub_rn(__fmul_rn(a[i].x, t1), __fmul_rn(c[i].x, t2));
+        x[4 * i + 1] = __fsub_rn(__fmul_rn(a[i].y, t1), __fmul_rn(c[i].y, t2));
+        x[4 * i + 2] = __fsub_rn(__fmul_rn(a[i].z, t1), __fmul_rn(c[i].z, t2));
+        x[4 * i + 3] = __fsub_rn(__fmul_rn(a[i].w, t1), __fmul_rn(c[i].w, t2));
       }
     }
-
-    // ---- row max / min (exact, on keys) ----
-    uint32_t kmax = 0, kminc = 0;   // kminc = ~min
-#pragma unroll
-    for (int e = 0; e < E; ++e) { kmax = max(kmax, key[e]); kminc = max(kminc, ~key[e]); }
-    block_max_u32x2(kmax, kminc, sm, slot);
-    const float m = fkey_inv(kmax);
-
-    // ---- top-k: K = key of the k-th largest.  Midpoint bisection on the key VALUE range [min, max] with early exit:
-    // cL = #{key >= lo} (>= k) and cH = #{key >= hi} (< k) bracket the answer; once the bracket [lo,hi) holds exactly one key
-    // that key IS the k-th largest (one min-reduction fetches it); ~log2(V)+2 rounds instead of 32.  The result is the
-    // unique largest K with #{key >= K} >= k, i.e. exactly what the bit-serial search of the spec returns.
-    uint32_t klow = ~kminc;   // smallest key that can still carry probability mass
-    int alive = V;            // #{key >= klow}
-    if (top_k > 0 && top_k < V) {
-      uint32_t lo = ~kminc, hi = kmax + 1u;
-      int cL = V, cH = 0;
-#pragma unroll 1
-      while (cL - cH > 1 && hi - lo > 1u) {
-        // midpoint of the bracket in VALUE space when it is usable (logits straddle 0, and in key space the floats around 0
-        // occupy half of the range: a key-space midpoint spends ~7 rounds walking up the exponents), else in key space
-        uint32_t mid = lo + ((hi - lo) >> 1);
-        const float flo = fkey_inv(lo), fhi = fkey_inv(hi - 1u);
-        if (flo > -INFINITY) {
-          const uint32_t mv = fkey(__fadd_rn(__fmul_rn(0.5f, flo), __fmul_rn(0.5f, fhi)));
-          if (mv > lo && mv < hi) mid = mv;
-        }
-        int c = 0;
-#pragma unroll
-        for (int e = 0; e < E; ++e) c += (key[e] >= mid) ? 1 : 0;
-        c = block_sum_int(c, sm, slot);
-        if (c >= top_k) { lo = mid; cL = c; } else { hi = mid; cH = c; }
-      }
-      uint32_t K = lo;
-      if (cL - cH == 1 && hi - lo > 1u) {   // the smallest key that is still >= lo (min via max of the complement)
-        uint32_t mn = 0, z = 0;
-#pragma unroll
-        for (int e = 0; e < E; ++e) mn = max(mn, (key[e] >= lo) ? ~key[e] : 0u);
-        block_max_u32x2(mn, z, sm, slot);
-        K = ~mn;
-      }
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-        if (key[e] < K) key[e] = kneg;
-      klow = K;
-      alive = cL;             // #{key >= K}: the bracket [lo, hi) held no key below K
-    }
-
-    // ---- top-p: remove v iff mass{key <= key_v} <= thr, never the max ----
-    if (thr >= 0.0f) {
-      float p[E];
-      float z = 0.0f;
-#pragma unroll
-      for (int e = 0; e < E; e += 2) {
-        unpk2(spec_expf2(__fsub_rn(fkey_inv(key[e]), m), __fsub_rn(fkey_inv(key[e + 1]), m)), p[e], p[e + 1]);
-        z = __fadd_rn(__fadd_rn(z, p[e]), p[e + 1]);
-      }
-      const float Z = block_sum(z, sm, slot);
-      float tot = 0.0f;
-#pragma unroll
-      for (int e = 0; e < E; ++e) { p[e] = fdiv_nz(p[e], Z); tot = __fadd_rn(tot, p[e]); }
-      tot = block_sum(tot, sm, slot);      // canonical mass of the whole row = mass{key <= kmax}
-      // Midpoint bisection on the canonical masked mass with early exit: lo is good (mass{key<=lo} <= thr, nL = #{key<=lo}),
-      // hi is bad.  The mass only changes at key values, so once at most one key separates lo from hi no threshold in
-      // between can change the removed set {key <= lo}: the answer equals the spec's largest good threshold.
-      // start from the largest threshold that is certainly good: below the smallest surviving key the masked mass is an exact 0.
-      // (Starting from 0 spent ~11 of ~19 rounds bisecting the empty key range under the top-k cut.)
-      uint32_t lo = klow > 0u ? klow - 1u : 0u, hi = kmax;
-      int nL = V - alive, nH = V;
-      if (tot <= thr) lo = kmax;           // everything is removable (the max itself is always kept)
-#pragma unroll 1
-      while (lo != kmax && nH - nL > 1 && hi - lo > 1u) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        float a = 0.0f;
-        int c = 0;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const bool in = key[e] <= mid;
-          a = __fadd_rn(a, in ? p[e] : 0.0f);
-          c += in ? 1 : 0;
-        }
-        block_sum_fi(a, c, sm, slot);
-        if (a <= thr) { lo = mid; nL = c; } else { hi = mid; nH = c; }
-      }
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-        if (key[e] <= lo && key[e] != kmax) key[e] = kneg;
-    }
-
     if (mixed_out != nullptr) {
-      float4* po = reinterpret_cast<float4*>(mixed_out + row * V);
+      float4* po = reinterpret_cast<float4*>(mixed_out + orow * V);
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        stg_stream(po + i * kThreads + tid, make_float4(fkey_inv(key[4 * i]), fkey_inv(key[4 * i + 1]), fkey_inv(key[4 * i + 2]), fkey_inv(key[4 * i + 3])));
+      for (int i = 0; i < NV; ++i) stg_stream(po + i * kThreads + tid, make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]));
     }
+    if (noise == nullptr) continue;
+    const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
+    float4 nz[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) nz[i] = ldg_stream(pn + i * kThreads + tid);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < E; ++e) mx = fmaxf(mx, x[e]);
+    uint32_t kmax = fkey(mx), z0 = 0;
+    block_max_u32x2(kmax, z0, sm, slot);
+    const float m = fkey_inv(kmax);
+    float z = 0.0f;
+#pragma unroll
+    for (int e = 0; e < E; e += 2) {
+      unpk2(spec_expf2(__fsub_rn(x[e], m), __fsub_rn(x[e + 1], m)), x[e], x[e + 1]);   // x now holds the exponentials
+      z = __fadd_rn(__fadd_rn(z, x[e]), x[e + 1]);
+    }
+    const float Z2 = block_sum(z, sm, slot);
+    float best = -1.0f, bestp = 0.0f;
+    int bi = 0x7FFFFFFF;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float pv = __fdiv_rn(x[4 * i + c], Z2);
+        const float r = __fdiv_rn(pv, nn[c]);
+        if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; bestp = pv; }
+      }
+    }
+    const unsigned long long w = block_max_u64(pack_best(best, bi), sm, slot);
+    int win = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
+    if (win == 0x7FFFFFFF) win = 0;
+    if (bi == win || (tid == 0 && (uint32_t)(w >> 32) == fkey(-1.0f))) {
+      if (idx_out) idx_out[orow] = win;
+      if (prob_out) prob_out[orow] = (bi == win) ? bestp : 0.0f;
+    }
+  }
+}
 
-    if (noise != nullptr) {
+struct K3Smem {
+  uint32_t hist[kBins];
+  float cand[256];
+  uint32_t candm[256];
+  uint32_t wtot[kWarps];
+  uint32_t zhi[2][kWarps], zlo[2][kWarps];   // two buffers: consecutive sums may have no barrier in between
+  int bstar;
+  uint32_t above;
+  int ncand, n_alive;
+  float xK;
+  uint32_t tkey, minkey;
+  RedSmem red;
+};
+
+// inclusive warp scan of a u32
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, v, off);
+    if (lane >= off) v += o;
+  }
+  return v;
+}
+// block-wide inclusive scan over the 256 threads (thread order); `tot` receives the grand total.  One barrier.
+__device__ __forceinline__ uint32_t block_incl_scan(uint32_t v, K3Smem& s, uint32_t& tot) {
+  const int w = threadIdx.x >> 5;
+  uint32_t inc = warp_incl_scan(v);
+  if ((threadIdx.x & 31) == 31) s.wtot[w] = inc;
+  __syncthreads();
+  uint32_t base = 0, t = 0;
+#pragma unroll
+  for (int k = 0; k < kWarps; ++k) {
+    const uint32_t x = s.wtot[k];
+    base += (k < w) ? x : 0u;
+    t += x;
+  }
+  tot = t;
+  return inc + base;
+}
+// fixed-point exponential E = rint(e * 2^40) as two 20-bit limbs (hi * 2^20 + lo); e in [0, 1]
+__device__ __forceinline__ void fix_e(float e, uint32_t& hi, uint32_t& lo) {
+  const float a = __fmul_rn(e, 1048576.0f);                 // e * 2^20, exact
+  const float fh = floorf(a);
+  hi = (uint32_t)fh;
+  lo = __float2uint_rn(__fmul_rn(__fsub_rn(a, fh), 1048576.0f));   // both operations exact; one rounding in the conversion
+}
+// block sum of per-thread limb sums -> u64 total.  One barrier.  (per-thread sums < 2^25, warp sums < 2^30)
+__device__ __forceinline__ unsigned long long block_sum_fix(uint32_t hi, uint32_t lo, K3Smem& s, int buf) {
+  hi = __reduce_add_sync(0xffffffffu, hi);
+  lo = __reduce_add_sync(0xffffffffu, lo);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s.zhi[buf][w] = hi; s.zlo[buf][w] = lo; }
+  __syncthreads();
+  unsigned long long t = 0;
+#pragma unroll
+  for (int k = 0; k < kWarps; ++k) t += ((unsigned long long)s.zhi[buf][k] << 20) + (unsigned long long)s.zlo[buf][k];
+  return t;
+}
+
+// ---- the part of the filtered path that works on the compacted survivor list; QR = list entries per thread (n <= 256 * QR)
+template <int QR>
+__device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float* lx, const float* ln, const uint16_t* li, int n, float m,
+                                        float xK, float thr, bool sample, float& xB, bool& strictB, bool& all_but_max,
+                                        long long orow, long long* idx_out, float* prob_out) {
+  const int tid = threadIdx.x;
+  float ev[QR];
+  uint32_t hi = 0, lo = 0;
+#pragma unroll
+  for (int q = 0; q < QR; q += 2) {
+    const int i0 = q * kThreads + tid, i1 = i0 + kThreads;
+    const float x0 = i0 < n ? __fsub_rn(lx[i0], m) : -INFINITY;
+    const float x1 = (q + 1 < QR && i1 < n) ? __fsub_rn(lx[i1], m) : -INFINITY;
+    float e0, e1;
+    unpk2(spec_expf2(x0, x1), e0, e1);
+    ev[q] = e0;
+    if (q + 1 < QR) ev[q + 1] = e1;
+    uint32_t h, l;
+    fix_e(e0, h, l); hi += h; lo += l;
+    fix_e(e1, h, l); hi += h; lo += l;        // e1 == 0 when the slot does not exist
+  }
+  const unsigned long long Zi = block_sum_fix(hi, lo, s, 0);
+  unsigned long long Z2i = Zi;
+  xB = -INFINITY; strictB = true; all_but_max = false;      // "x < -inf": nothing removed
+  if (thr >= 0.0f) {
+    const float Z = __fmul_rn(__ull2float_rn(Zi), 1.0f / kFixE);
+    const uint32_t thr_i = (uint32_t)__fmul_rn(thr, kFixM);
+    const float range = __fsub_rn(m, xK);
+    uint32_t mass[QR];
+#pragma unroll
+    for (int q = 0; q < QR; ++q) mass[q] = ev[q] > 0.0f ? __float2uint_rn(__fmul_rn(__fdiv_rn(ev[q], Z), kFixM)) : 0u;
+    if (range > 0.0f && range < INFINITY) {
+      const float scale = __fdiv_rn(511.0f, range), off = __fmaf_rn(-xK, scale, 0.5f);
+#pragma unroll
+      for (int q = 0; q < QR; ++q) {
+        const int i = q * kThreads + tid;
+        if (i < n) atomicAdd(&s.hist[min(max(__float2int_rd(__fmaf_rn(lx[i], scale, off)), 0), kBins - 1)], mass[q]);
+      }
+      __syncthreads();
+      // ascending scan of the bin masses: the crossing bin is the first whose inclusive cumulation exceeds thr_i
+      const uint32_t m0 = s.hist[2 * tid], m1 = s.hist[2 * tid + 1];
+      uint32_t tot;
+      const uint32_t inc = block_incl_scan(m0 + m1, s, tot);
+      const uint32_t before = inc - (m0 + m1);
+      s.hist[2 * tid] = 0; s.hist[2 * tid + 1] = 0;
+      if (before <= thr_i && thr_i < before + m0) { s.bstar = 2 * tid; s.above = before; }
+      else if (before + m0 <= thr_i && thr_i < inc) { s.bstar = 2 * tid + 1; s.above = before + m0; }
+      __syncthreads();
+      if (tot <= thr_i) {
+        all_but_max = true;                  // the whole row is removable: only the maximum survives
+      } else {
+        const int bst = s.bstar;
+        const uint32_t below = s.above;
+#pragma unroll
+        for (int q = 0; q < QR; ++q) {
+          const int i = q * kThreads + tid;
+          if (i < n && min(max(__float2int_rd(__fmaf_rn(lx[i], scale, off)), 0), kBins - 1) == bst) {
+            const int p = atomicAdd(&s.ncand, 1);
+            if (p < 256) { s.cand[p] = lx[i]; s.candm[p] = mass[q]; }
+          }
+        }
+        __syncthreads();
+        const int nc = s.ncand;
+        if (nc <= 256) {
+          if (tid < nc) {
+            const float xi = s.cand[tid];
+            uint32_t le = below;
+            for (int jj = 0; jj < nc; ++jj) le += (s.cand[jj] <= xi) ? s.candm[jj] : 0u;
+            const uint32_t k = fkey(__fadd_rn(xi, 0.0f));
+            if (le <= thr_i) atomicMax(&s.tkey, k);
+            atomicMin(&s.minkey, k);
+          }
+          __syncthreads();
+          const uint32_t tk = s.tkey;
+          strictB = tk == 0u;
+          xB = fkey_inv(strictB ? s.minkey : tk);
+        } else {
+          // fall-back (a crossing bin with > 256 entries): bit-serial search of the largest key T with mass{key <= T} <= thr_i
+          uint32_t T = 0;
+#pragma unroll 1
+          for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t tr = T | (1u << bit);
+            int a = 0;
+#pragma unroll
+            for (int q = 0; q < QR; ++q) {
+              const int i = q * kThreads + tid;
+              if (i < n && fkey(__fadd_rn(lx[i], 0.0f)) <= tr) a += (int)mass[q];
+            }
+            a = block_sum_int(a, s.red, slot);      // masses sum to ~2^30: fits an int
+            if ((uint32_t)a <= thr_i) T = tr;
+          }
+          strictB = false;
+          xB = T ? fkey_inv(T) : -INFINITY;
+          if (T == 0u) strictB = true;
+        }
+      }
+    }
+    // survivors' fixed-point sum
+    hi = 0; lo = 0;
+#pragma unroll
+    for (int q = 0; q < QR; ++q) {
+      const int i = q * kThreads + tid;
+      if (i < n) {
+        const float xv = lx[i];
+        const bool rem = all_but_max ? (xv != m) : ((strictB ? xv < xB : xv <= xB) && xv != m);
+        if (rem) ev[q] = 0.0f;
+        uint32_t h, l;
+        fix_e(ev[q], h, l); hi += h; lo += l;
+      }
+    }
+    if (sample) Z2i = block_sum_fix(hi, lo, s, 1);
+  }
+  if (!sample) return;
+  const float Z2 = __fmul_rn(__ull2float_rn(Z2i), 1.0f / kFixE);
+  float best = -1.0f, bestp = 0.0f;
+  int bi = 0x7FFFFFFF;
+#pragma unroll
+  for (int q = 0; q < QR; ++q) {
+    const int i = q * kThreads + tid;
+    if (i < n && ev[q] > 0.0f) {
+      const float pv = __fdiv_rn(ev[q], Z2);
+      const float r = __fdiv_rn(pv, ln[i]);
+      const int v = (int)li[i];
+      if (r > best || (r == best && v < bi)) { best = r; bi = v; bestp = pv; }
+    }
+  }
+  const unsigned long long w = block_max_u64(pack_best(best, bi), s.red, slot);
+  int win = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
+  if (win == 0x7FFFFFFF) win = 0;
+  if (bi == win || (tid == 0 && (uint32_t)(w >> 32) == fkey(-1.0f))) {
+    if (idx_out) idx_out[orow] = win;
+    if (prob_out) prob_out[orow] = (bi == win) ? bestp : 0.0f;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kThreads, 4)
+k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int in_off, int out_ld, int out_off, SegTable seg,
+                   int top_k, float thr, const float* __restrict__ noise, long long* __restrict__ idx_out,
+                   float* __restrict__ mixed_out, float* __restrict__ prob_out) {
+  constexpr int V = NV * 1024;
+  constexpr int E = NV * 4;
+  constexpr int QF = E < 6 ? E : 6;     // fast tail: up to 1536 survivors
+  extern __shared__ __align__(16) unsigned char k3_dyn[];
+  float* lx = reinterpret_cast<float*>(k3_dyn);            // [V] survivor logits
+  float* ln = lx + V;                                      // [V] their noise
+  uint16_t* li = reinterpret_cast<uint16_t*>(ln + V);      // [V] their vocabulary index
+  __shared__ K3Smem s;
+  int slot = 0;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long rows = (long long)B * L;
+  for (int i = tid; i < kBins; i += kThreads) s.hist[i] = 0;
+  if (tid == 0) { s.ncand = 0; s.n_alive = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; }
+  __syncthreads();
+  const bool sample = noise != nullptr;
+  const bool use_k = top_k > 0 && top_k < V;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+    const int j = seg_of(seg, pos);
+    const float t1 = seg.t1[j], t2 = seg.t2[j];
+    const long long orow = (long long)b * out_ld + out_off + pos;
+    const float4* pc = reinterpret_cast<const float4*>(logits + ((long long)b * in_ld + in_off + pos) * V);
+    const float4* pu = reinterpret_cast<const float4*>(logits + ((long long)(B + b) * in_ld + in_off + pos) * V);
+    float x[E];
+    {
+      float4 a[NV], c[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { a[i] = ldg_stream(pc + i * kThreads + tid); c[i] = ldg_stream(pu + i * kThreads + tid); }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        x[4 * i + 0] = __fsub_rn(__fmul_rn(a[i].x, t1), __fmul_rn(c[i].x, t2));
+        x[4 * i + 1] = __fsub_rn(__fmul_rn(a[i].y, t1), __fmul_rn(c[i].y, t2));
+        x[4 * i + 2] = __fsub_rn(__fmul_rn(a[i].z, t1), __fmul_rn(c[i].z, t2));
+        x[4 * i + 3] = __fsub_rn(__fmul_rn(a[i].w, t1), __fmul_rn(c[i].w, t2));
+      }
+    }
+    float4 nz[NV];
+    if (sample) {
       const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
-      float4 nz[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) nz[i] = ldg_stream(pn + i * kThreads + tid);
-      float ex[E];
-      float z = 0.0f;
+    }
+    // ---- row max / min ----
+    float mx = -INFINITY, mn = INFINITY;
 #pragma unroll
-      for (int e = 0; e < E; e += 2) {
-        unpk2(spec_expf2(__fsub_rn(fkey_inv(key[e]), m), __fsub_rn(fkey_inv(key[e + 1]), m)), ex[e], ex[e + 1]);
-        z = __fadd_rn(__fadd_rn(z, ex[e]), ex[e + 1]);
-      }
-      const float Z2 = block_sum(z, sm, slot);
-      float best = -1.0f, bestp = 0.0f;
-      int bi = 0x7FFFFFFF;
-      const bool filtered = (top_k > 0 && top_k < V) || thr >= 0.0f;   // block-uniform: masked entries (exact zeros) exist
-      if (filtered) {
+    for (int e = 0; e < E; ++e) { mx = fmaxf(mx, x[e]); mn = fminf(mn, x[e]); }
+    uint32_t kmx = fkey(__fadd_rn(mx, 0.0f)), kmnc = ~fkey(__fadd_rn(mn, 0.0f));
+    block_max_u32x2(kmx, kmnc, s.red, slot);
+    const float m = fkey_inv(kmx), xmin = fkey_inv(~kmnc);
+
+    // ---- top-k: xK = k-th largest value (alive <=> x >= xK) ----
+    float xK = xmin;
+    if (use_k) {
+      const float range = __fsub_rn(m, xmin);
+      bool done = false;
+      if (range > 0.0f && range < INFINITY) {
+        const float scale = __fdiv_rn(511.0f, range), off = __fmaf_rn(-xmin, scale, 0.5f);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
+        for (int e = 0; e < E; ++e) atomicAdd(&s.hist[min(max(__float2int_rd(__fmaf_rn(x[e], scale, off)), 0), kBins - 1)], 1u);
+        __syncthreads();
+        // suffix scan: thread t owns bins 511-2t (first) and 510-2t
+        const uint32_t c0 = s.hist[kBins - 1 - 2 * tid], c1 = s.hist[kBins - 2 - 2 * tid];
+        uint32_t tot;
+        const uint32_t inc = block_incl_scan(c0 + c1, s, tot);
+        const uint32_t before = inc - (c0 + c1);
+        s.hist[kBins - 1 - 2 * tid] = 0; s.hist[kBins - 2 - 2 * tid] = 0;
+        const uint32_t k = (uint32_t)top_k;
+        if (before < k && k <= before + c0) { s.bstar = kBins - 1 - 2 * tid; s.above = before; }
+        else if (before + c0 < k && k <= inc) { s.bstar = kBins - 2 - 2 * tid; s.above = before + c0; }
+        __syncthreads();
+        const int bst = s.bstar;
+        const uint32_t above = s.above;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float pv = fdiv_nz(ex[4 * i + c], Z2);
-            const float r = fdiv_nz(pv, nn[c]);
-            if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; bestp = pv; }
+        for (int e = 0; e < E; ++e)
+          if (min(max(__float2int_rd(__fmaf_rn(x[e], scale, off)), 0), kBins - 1) == bst) {
+            const int p = atomicAdd(&s.ncand, 1);
+            if (p < 256) s.cand[p] = x[e];
           }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float pv = __fdiv_rn(ex[4 * i + c], Z2);
-            const float r = __fdiv_rn(pv, nn[c]);
-            if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; bestp = pv; }
+        __syncthreads();
+        const int nc = s.ncand;
+        if (nc <= 256) {
+          if (tid < nc) {
+            const float xi = s.cand[tid];
+            uint32_t g = 0, ge = 0;
+            for (int jj = 0; jj < nc; ++jj) { const float xj = s.cand[jj]; g += xj > xi; ge += xj >= xi; }
+            const uint32_t kk = k - above;
+            if (g < kk && kk <= ge) s.xK = xi;
           }
+          __syncthreads();
+          xK = s.xK;
+          done = true;
         }
+        if (tid == 0) s.ncand = 0;      // next use is behind at least one barrier
       }
-      const unsigned long long w = block_max_u64(pack_best(best, bi), sm, slot);
-      int win = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
-      if (win == 0x7FFFFFFF) win = 0;
-      if (bi == win || (tid == 0 && (uint32_t)(w >> 32) == fkey(-1.0f))) {
-        if (idx_out) idx_out[row] = win;
-        if (prob_out) prob_out[row] = (bi == win) ? bestp : 0.0f;
+      if (!done) {
+        // fall-back: bisection on the order-preserving keys (round-1 algorithm), any input
+        uint32_t key[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) key[e] = fkey(__fadd_rn(x[e], 0.0f));
+        uint32_t lo = ~kmnc, hi = kmx + 1u;
+        int cL = V, cH = 0;
+#pragma unroll 1
+        while (cL - cH > 1 && hi - lo > 1u) {
+          const uint32_t mid = lo + ((hi - lo) >> 1);
+          int c = 0;
+#pragma unroll
+          for (int e = 0; e < E; ++e) c += (key[e] >= mid) ? 1 : 0;
+          c = block_sum_int(c, s.red, slot);
+          if (c >= top_k) { lo = mid; cL = c; } else { hi = mid; cH = c; }
+        }
+        uint32_t K = lo;
+        if (cL - cH == 1 && hi - lo > 1u) {
+          uint32_t mnk = 0, z = 0;
+#pragma unroll
+          for (int e = 0; e < E; ++e) mnk = max(mnk, (key[e] >= lo) ? ~key[e] : 0u);
+          block_max_u32x2(mnk, z, s.red, slot);
+          K = ~mnk;
+        }
+        xK = fkey_inv(K);
       }
     }
+
+    // ---- compact the survivors (any order: every later sum is an integer sum) ----
+    {
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) cnt += (x[e] >= xK) ? 1u : 0u;
+      const uint32_t inc = warp_incl_scan(cnt);
+      int base = 0;
+      if (lane == 31) base = atomicAdd(&s.n_alive, (int)inc);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      int p = base + (int)(inc - cnt);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (x[4 * i + c] >= xK) {
+            lx[p] = x[4 * i + c];
+            li[p] = (uint16_t)(4 * (i * kThreads + tid) + c);
+            if (sample) ln[p] = nn[c];
+            ++p;
+          }
+      }
+    }
+    __syncthreads();
+    const int n = s.n_alive;
+    float xB;
+    bool strictB, all_but_max;
+    if (n <= QF * kThreads) k3_tail<QF>(s, slot, lx, ln, li, n, m, xK, thr, sample, xB, strictB, all_but_max, orow, idx_out, prob_out);
+    else k3_tail<E>(s, slot, lx, ln, li, n, m, xK, thr, sample, xB, strictB, all_but_max, orow, idx_out, prob_out);
+
+    if (mixed_out != nullptr) {
+      float4* po = reinterpret_cast<float4*>(mixed_out + orow * V);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float xv = x[4 * i + c];
+          const bool rem = all_but_max ? (xv != m) : ((strictB ? xv < xB : xv <= xB) && xv != m);
+          o[c] = (xv >= xK && !rem) ? xv : -INFINITY;
+        }
+        stg_stream(po + i * kThreads + tid, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+    __syncthreads();      // every thread is past its last read of the row's shared state
+    if (tid == 0) { s.ncand = 0; s.n_alive = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; }
   }
 }
 
 // ================================================================================================
 // K4
 // ================================================================================================
-__global__ void k4_init_kernel(int* first_reject, int* n_accept, int B, SegTable seg) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B * seg.S) {
-    const int j = i % seg.S;
-    first_reject[i] = seg.begin[j + 1] - seg.begin[j];
-    n_accept[i] = 0;
-  }
-}
-
-// K4 v2: the two logit rows of a token (2 x V fp32 = 32 KiB) are staged in shared memory by 1-D bulk TMA copies
-// (cp.async.bulk + mbarrier), double-buffered so row i+1 streams in while row i is processed; several CTAs per SM keep
-// >= 96 KiB in flight per SM.  The accept path touches each value once (max, exp, sum: nothing is kept in registers);
-// only a rejected row re-reads its staged logits to rebuild p and q for the residual resample.  Same arithmetic and
-// reduction order as v1, i.e. bit-exact to oracle/spec_c/sdvar_spec.c.
+// K4 v3.  One CTA per token row; the two logit rows of a token (2 x V fp32 = 32 KiB) are staged in shared memory by 1-D bulk
+// TMA copies (cp.async.bulk + mbarrier) into a 2-stage ring.  Each thread moves its 2 x 4NV values into REGISTERS in the
+// max pass; after the block-wide max reduction (a barrier every thread passes only after its last shared-memory read of the
+// stage) the stage is refilled with the row TWO iterations ahead, so ~1.7 rows per CTA are always in flight.  Exponentials
+// replace the logits in the registers: nothing is written back to shared memory (v2 stored them for the owner's lookup and
+// for the reject path: 8 STS.128 + 8 LDS.128 per thread-row and a generic->async proxy hazard on the refill).  The owner of
+// element d picks its two exponentials with a select chain (one warp pays); a rejected row resamples straight from the
+// registers.  Per-(image, stage) counters are integer atomics into the caller's zeroed workspace, copied out and re-zeroed by
+// the last CTA, so the launch needs no init kernel.  Arithmetic and reduction order are those of oracle/spec_c:
+// sdvar_spec_verify, bit for bit.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    (uint32_t)__cvta_generic_to_shared(smem_dst)),
@@ -430,14 +711,23 @@ __device__ __forceinline__ void mbar_wait_par(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// u / noise row of token (b, pos): dense (b*L + pos), or "stage-major" = the concatenation over stages j of (B*l_j) blocks,
+// i.e. exactly the tensors a caller draws stage by stage ((B*l_j, V) each) laid end to end
+__device__ __forceinline__ long long aux_row(int stage_major, int B, int L, const SegTable& seg, int b, int pos, int j) {
+  if (!stage_major) return (long long)b * L + pos;
+  const int lj = seg.begin[j + 1] - seg.begin[j];
+  return (long long)B * seg.begin[j] + (long long)b * lj + (pos - seg.begin[j]);
+}
+
 template <int NV>
 __global__ void __launch_bounds__(kThreads, 3)
 k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, const long long* __restrict__ draft_idx,
-                 const float* __restrict__ u, const float* __restrict__ noise, int B, int L, SegTable seg,
+                 const float* __restrict__ u, const float* __restrict__ noise, int stage_major, int B, int L, SegTable seg,
                  long long* __restrict__ out_idx, unsigned char* __restrict__ accept, float* __restrict__ p_d_out,
-                 float* __restrict__ q_d_out, int* first_reject, int* n_accept, int* accepted_stages, int* summary,
-                 int* counter) {
+                 float* __restrict__ q_d_out, int* __restrict__ first_reject, int* __restrict__ n_accept,
+                 int* __restrict__ accepted_stages, int* __restrict__ summary, int* ws) {
   constexpr int V = NV * 1024;
+  constexpr int E = NV * 4;
   extern __shared__ __align__(128) unsigned char k4_smem[];
   float* stage_buf = reinterpret_cast<float*>(k4_smem);                    // [2][2][V]
   uint64_t* full = reinterpret_cast<uint64_t*>(k4_smem + 2 * 2 * V * 4);   // [2]
@@ -446,151 +736,169 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
   int slot = 0;
   const int tid = threadIdx.x;
   const long long rows = (long long)B * L;
+  int* ws_acc = ws + 4;               // [B*S] accepted tokens per (image, stage)
+  int* ws_fr = ws + 4 + B * seg.S;    // [B*S] max over rejected tokens of (l_j - position): 0 = no reject
   if (tid == 0) {
     mbar_init1(&full[0]);
     mbar_init1(&full[1]);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if ((long long)blockIdx.x < rows) {
-      mbar_expect(&full[0], 2 * V * 4);
-      bulk_g2s(stage_buf, xt + (long long)blockIdx.x * V, V * 4, &full[0]);
-      bulk_g2s(stage_buf + V, xd + (long long)blockIdx.x * V, V * 4, &full[0]);
+#pragma unroll
+    for (int k0 = 0; k0 < 2; ++k0) {
+      const long long r0 = (long long)blockIdx.x + (long long)k0 * gridDim.x;
+      if (r0 < rows) {
+        mbar_expect(&full[k0], 2 * V * 4);
+        bulk_g2s(stage_buf + k0 * 2 * V, xt + r0 * V, V * 4, &full[k0]);
+        bulk_g2s(stage_buf + k0 * 2 * V + V, xd + r0 * V, V * 4, &full[k0]);
+      }
     }
   }
   __syncthreads();
   uint32_t k = 0;
   for (long long row = blockIdx.x; row < rows; row += gridDim.x, ++k) {
     const uint32_t st = k & 1;
-    // prefetch the next row into the other stage (all reads of that stage finished before the barrier closing iteration k-1)
-    const long long nrow = row + gridDim.x;
-    if (tid == 0 && nrow < rows) {
-      mbar_expect(&full[st ^ 1], 2 * V * 4);
-      bulk_g2s(stage_buf + (st ^ 1) * 2 * V, xt + nrow * V, V * 4, &full[st ^ 1]);
-      bulk_g2s(stage_buf + (st ^ 1) * 2 * V + V, xd + nrow * V, V * 4, &full[st ^ 1]);
-    }
     const int d = (int)draft_idx[row];
     mbar_wait_par(&full[st], (k >> 1) & 1);
-    float4* st4 = reinterpret_cast<float4*>(stage_buf + st * 2 * V);
-    float4* sd4 = st4 + V / 4;
-    // pass 1: row maxima (order-independent)
+    const float4* st4 = reinterpret_cast<const float4*>(stage_buf + st * 2 * V);
+    const float4* sd4 = st4 + V / 4;
+    // pass 1: values to registers, row maxima (order-independent)
+    float4 a[NV], c[NV];
     float mt = -INFINITY, md = -INFINITY;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float4 a = st4[i * kThreads + tid], c = sd4[i * kThreads + tid];
-      mt = fmaxf(fmaxf(mt, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
-      md = fmaxf(fmaxf(md, fmaxf(c.x, c.y)), fmaxf(c.z, c.w));
+      a[i] = st4[i * kThreads + tid];
+      c[i] = sd4[i * kThreads + tid];
+      mt = fmaxf(fmaxf(mt, fmaxf(a[i].x, a[i].y)), fmaxf(a[i].z, a[i].w));
+      md = fmaxf(fmaxf(md, fmaxf(c[i].x, c[i].y)), fmaxf(c[i].z, c[i].w));
     }
     uint32_t kt = fkey(mt), kd = fkey(md);
-    block_max_u32x2(kt, kd, sm, slot);
+    block_max_u32x2(kt, kd, sm, slot);      // barrier: every thread has read its part of stage st
     mt = fkey_inv(kt);
     md = fkey_inv(kd);
-    // pass 2: canonical exp sums; the owner of element d keeps its two exponentials
-    // two adjacent elements of the SAME row per packed instruction: the pairs are the register pairs LDS.128 delivers and
-    // STS.128 takes back, so no moves are spent on re-pairing; the row sums stay scalar, in element order (the canonical order)
+    {
+      const long long nrow = row + 2LL * gridDim.x;
+      if (tid == 0 && nrow < rows) {        // refill the stage just drained with the row two iterations ahead
+        mbar_expect(&full[st], 2 * V * 4);
+        bulk_g2s(stage_buf + st * 2 * V, xt + nrow * V, V * 4, &full[st]);
+        bulk_g2s(stage_buf + st * 2 * V + V, xd + nrow * V, V * 4, &full[st]);
+      }
+    }
+    // pass 2: exponentials in place (registers), canonical sums: scalar adds in element order, packed exponentials on the
+    // register pairs LDS.128 delivered
     float zt = 0.0f, zd = 0.0f;
     const f32x2 nmt = pk2(-mt, -mt), nmd = pk2(-md, -md);    // a - m == a + (-m) exactly
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      float4 a = st4[i * kThreads + tid], c = sd4[i * kThreads + tid];
       float x0, x1;
-      unpk2(add2(pk2(a.x, a.y), nmt), x0, x1);
-      unpk2(spec_expf2(x0, x1), a.x, a.y);
-      unpk2(add2(pk2(a.z, a.w), nmt), x0, x1);
-      unpk2(spec_expf2(x0, x1), a.z, a.w);
-      unpk2(add2(pk2(c.x, c.y), nmd), x0, x1);
-      unpk2(spec_expf2(x0, x1), c.x, c.y);
-      unpk2(add2(pk2(c.z, c.w), nmd), x0, x1);
-      unpk2(spec_expf2(x0, x1), c.z, c.w);
-      zt = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(zt, a.x), a.y), a.z), a.w);
-      zd = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(zd, c.x), c.y), c.z), c.w);
-      // the exponentials replace the staged logits (each thread rewrites only the chunks it owns), so neither the accept
-      // test nor a residual resample has to exponentiate again
-      st4[i * kThreads + tid] = a;
-      sd4[i * kThreads + tid] = c;
+      unpk2(add2(pk2(a[i].x, a[i].y), nmt), x0, x1);
+      unpk2(spec_expf2(x0, x1), a[i].x, a[i].y);
+      unpk2(add2(pk2(a[i].z, a[i].w), nmt), x0, x1);
+      unpk2(spec_expf2(x0, x1), a[i].z, a[i].w);
+      unpk2(add2(pk2(c[i].x, c[i].y), nmd), x0, x1);
+      unpk2(spec_expf2(x0, x1), c[i].x, c[i].y);
+      unpk2(add2(pk2(c[i].z, c[i].w), nmd), x0, x1);
+      unpk2(spec_expf2(x0, x1), c[i].z, c[i].w);
+      zt = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(zt, a[i].x), a[i].y), a[i].z), a[i].w);
+      zd = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(zd, c[i].x), c[i].y), c[i].z), c[i].w);
     }
     block_sum2(zt, zd, sm, slot);  // zt, zd now hold Zt, Zd
-    // the owner of element d evaluates the accept test and publishes the per-token outputs itself; everything only it needs
-    // (1/Z, image / position / stage of the row, u) is computed there and not by the other 255 threads
+    // the owner of element d evaluates the accept test and publishes the per-token outputs itself
     const bool owner = ((d >> 2) & (kThreads - 1)) == tid;
     int rej = 0;
     if (owner) {
+      float etd = 0.0f, edd = 0.0f;
+      const int di = d >> 10, dc = d & 3;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (i == di) {
+          etd = dc == 0 ? a[i].x : dc == 1 ? a[i].y : dc == 2 ? a[i].z : a[i].w;
+          edd = dc == 0 ? c[i].x : dc == 1 ? c[i].y : dc == 2 ? c[i].z : c[i].w;
+        }
+      }
       const float izt = __fdiv_rn(1.0f, zt), izd = __fdiv_rn(1.0f, zd);
       const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
       const int j = seg_of(seg, pos);
-      const float uu = u[row];
-      const float* rt = stage_buf + st * 2 * V;
-      const float pdv = __fmul_rn(rt[d], izt), qdv = __fmul_rn(rt[V + d], izd);
+      const float uu = u[aux_row(stage_major, B, L, seg, b, pos, j)];
+      const float pdv = __fmul_rn(etd, izt), qdv = __fmul_rn(edd, izd);
       rej = (__fmul_rn(uu, qdv) < pdv) ? 0 : 1;
       accept[row] = (unsigned char)(rej ^ 1);
       if (p_d_out) p_d_out[row] = pdv;
       if (q_d_out) q_d_out[row] = qdv;
       if (!rej) {
         out_idx[row] = d;
-        atomicAdd(&n_accept[b * seg.S + j], 1);
+        atomicAdd(&ws_acc[b * seg.S + j], 1);
       } else {
-        atomicMin(&first_reject[b * seg.S + j], pos - seg.begin[j]);
+        atomicMax(&ws_fr[b * seg.S + j], seg.begin[j + 1] - pos);
       }
     }
     const int acc = __syncthreads_or(rej) ? 0 : 1;
-    int out = d;
-    if (!acc) {  // block-uniform: residual resample from the staged logits
+    if (!acc) {  // block-uniform: residual resample straight from the registers
       const float izt = __fdiv_rn(1.0f, zt), izd = __fdiv_rn(1.0f, zd);
-      const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
+      const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+      const float4* pn = reinterpret_cast<const float4*>(noise + aux_row(stage_major, B, L, seg, b, pos, seg_of(seg, pos)) * V);
       float4 nz[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) nz[i] = ldg_stream(pn + i * kThreads + tid);
-      float pv[NV * 4], rv[NV * 4];
-      int anyp = 0;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float4 a = st4[i * kThreads + tid], c = sd4[i * kThreads + tid];
-        const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float p1 = __fmul_rn(av[q], izt);
-          float r1 = __fsub_rn(p1, __fmul_rn(cv[q], izd));
-          r1 = r1 > 0.0f ? r1 : 0.0f;
-          anyp |= (r1 > 0.0f) ? 1 : 0;
-          pv[4 * i + q] = p1;
-          rv[4 * i + q] = r1;
-        }
-      }
-      anyp = __syncthreads_or(anyp);
       float best = -1.0f;
       int bi = 0x7FFFFFFF;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
+        const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w}, cv[4] = {c[i].x, c[i].y, c[i].z, c[i].w};
         const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float r = fdiv_nz(anyp ? rv[4 * i + q] : pv[4 * i + q], nn[q]);
+          float r1 = __fsub_rn(__fmul_rn(av[q], izt), __fmul_rn(cv[q], izd));
+          r1 = r1 > 0.0f ? r1 : 0.0f;
+          const float r = fdiv_nz(r1, nn[q]);
           if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + q; }
         }
       }
-      const unsigned long long w = block_max_u64(pack_best(best, bi), sm, slot);
-      out = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
+      unsigned long long w = block_max_u64(pack_best(best, bi), sm, slot);
+      if ((uint32_t)(w >> 32) == fkey(0.0f)) {
+        // the residual is identically zero (p == q element-wise, a reject can then only come from rounding in the accept
+        // test): the spec resamples from p itself.  Detected from the winner (best ratio 0 <=> every residual is 0), so the
+        // common path needs no extra block-wide vote.
+        best = -1.0f;
+        bi = 0x7FFFFFFF;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+          const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float r = fdiv_nz(__fmul_rn(av[q], izt), nn[q]);
+            if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + q; }
+          }
+        }
+        w = block_max_u64(pack_best(best, bi), sm, slot);
+      }
+      int out = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
       if (out == 0x7FFFFFFF) out = 0;
       if (tid == 0) out_idx[row] = out;
     }
-    // (no trailing barrier: the last shared-memory reads of stage st are always followed by a block reduction barrier
-    //  before the next iteration's prefetch can target that stage)
   }
-  // ---- last CTA finalises the per-image / batch scan (integer atomics => deterministic) ----
+  // ---- last CTA finalises the per-image / batch scan (integer atomics => deterministic) and re-zeroes the workspace ----
   __threadfence();
-  if (tid == 0) s_last = (atomicAdd(counter, 1) == (int)gridDim.x - 1);
+  if (tid == 0) s_last = (atomicAdd(&ws[0], 1) == (int)gridDim.x - 1);
   __syncthreads();
   if (s_last) {
     __threadfence();
     int mn = seg.S, na = 0;
     for (int b = tid; b < B; b += kThreads) {
-      int a = 0;
+      int a2 = 0;
       bool open = true;
       for (int j2 = 0; j2 < seg.S; ++j2) {
-        const int n = __ldcg(&n_accept[b * seg.S + j2]);
+        const int lj = seg.begin[j2 + 1] - seg.begin[j2];
+        const int n = __ldcg(&ws_acc[b * seg.S + j2]);
+        const int f = __ldcg(&ws_fr[b * seg.S + j2]);
+        ws_acc[b * seg.S + j2] = 0;
+        ws_fr[b * seg.S + j2] = 0;
+        n_accept[b * seg.S + j2] = n;
+        first_reject[b * seg.S + j2] = lj - f;
         na += n;
-        if (open && n == seg.begin[j2 + 1] - seg.begin[j2]) ++a; else open = false;
+        if (open && n == lj) ++a2; else open = false;
       }
-      accepted_stages[b] = a;
-      mn = min(mn, a);
+      accepted_stages[b] = a2;
+      mn = min(mn, a2);
     }
     // min over images via max of (S - accepted)
     uint32_t neg = (uint32_t)(seg.S - mn), z = 0;
@@ -601,7 +909,7 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
       summary[1] = total_acc;
       summary[2] = (int)rows - total_acc;
       summary[3] = 0;
-      *counter = 0;
+      ws[0] = 0;
     }
   }
 }
@@ -664,14 +972,15 @@ static int row_grid(long long rows, int blocks_per_sm) {
 
 using namespace sdvar;
 
-extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L, int in_ld, int in_off, int V,
-                                          const int* seg_begin_host, int S,
+extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L, int in_ld, int in_off, int out_ld, int out_off,
+                                          int V, const int* seg_begin_host, int S,
                                           const float* t1_host, const float* t2_host, int top_k, float one_minus_top_p,
                                           const float* noise, long long* idx_out, float* mixed_out, float* prob_out,
                                           void* stream) {
   if (int rc = check_arch()) return rc;
   SDVAR_REQUIRE(logits_2BLV && B > 0 && L > 0, "bad logits/B/L");
   SDVAR_REQUIRE(in_off >= 0 && in_ld >= in_off + L, "bad row mapping in_ld=%d in_off=%d L=%d", in_ld, in_off, L);
+  SDVAR_REQUIRE(out_off >= 0 && out_ld >= out_off + L, "bad output row mapping out_ld=%d out_off=%d L=%d", out_ld, out_off, L);
   SDVAR_REQUIRE(V % 1024 == 0 && V >= 1024 && V <= 8192, "V=%d must be a multiple of 1024 in [1024,8192]", V);
   SDVAR_REQUIRE(((uintptr_t)logits_2BLV & 15) == 0 && ((uintptr_t)noise & 15) == 0 && ((uintptr_t)mixed_out & 15) == 0,
                 "row pointers must be 16-byte aligned");
@@ -682,10 +991,18 @@ extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L
   const int grid = row_grid(rows, 4);
   cudaStream_t st = (cudaStream_t)stream;
   ProfileScope prof(st, FAM_SAMPLE, (double)rows * (8.0 * V + (noise ? 4.0 * V + 8.0 : 0.0) + (mixed_out ? 4.0 * V : 0.0)));
-#define SDVAR_K3(NV)                                                                                          \
-  case NV:                                                                                                    \
-    k3_sample_kernel<NV><<<grid, kThreads, 0, st>>>(logits_2BLV, B, L, in_ld, in_off, seg, top_k, one_minus_top_p, noise,   \
-                                                    idx_out, mixed_out, prob_out);                           \
+  const bool filtered = (top_k > 0 && top_k < V) || one_minus_top_p >= 0.0f;
+  const size_t dyn = (size_t)V * 10;      // survivor list: logit + noise (fp32) + vocabulary index (u16)
+#define SDVAR_K3(NV)                                                                                                        \
+  case NV:                                                                                                                  \
+    if (filtered) {                                                                                                         \
+      SDVAR_SET_SMEM_ONCE(k3_filtered_kernel<NV>, dyn);                                                                     \
+      k3_filtered_kernel<NV><<<grid, kThreads, dyn, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, top_k,    \
+                                                          one_minus_top_p, noise, idx_out, mixed_out, prob_out);           \
+    } else {                                                                                                                \
+      k3_plain_kernel<NV><<<grid, kThreads, 0, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, noise, idx_out, \
+                                                     mixed_out, prob_out);                                                 \
+    }                                                                                                                       \
     break;
   switch (V / 1024) {
     SDVAR_K3(1) SDVAR_K3(2) SDVAR_K3(4) SDVAR_K3(8)
@@ -697,8 +1014,14 @@ extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L
   return SDVAR_OK;
 }
 
+extern "C" long long sdvar_verify_workspace_bytes(int B, int S) {
+  if (B <= 0 || S <= 0 || S > SDVAR_MAX_SEG) return SDVAR_ERR_ARG;
+  return (long long)sizeof(int) * (4 + 2LL * B * S);
+}
+
 extern "C" int sdvar_verify_accept_resample(const float* xt, const float* xd, const long long* draft_idx, const float* u,
-                                            const float* noise, int B, int L, int V, const int* seg_begin_host, int S,
+                                            const float* noise, int stage_major_aux, int B, int L, int V,
+                                            const int* seg_begin_host, int S,
                                             long long* out_idx, unsigned char* accept, float* p_d_out, float* q_d_out,
                                             int* first_reject, int* n_accept, int* accepted_stages, int* summary,
                                             int* workspace, void* stream) {
@@ -713,22 +1036,16 @@ extern "C" int sdvar_verify_accept_resample(const float* xt, const float* xd, co
   if (int rc = fill_seg(seg, seg_begin_host, S, L, nullptr, nullptr)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   ProfileScope prof(st, FAM_VERIFY, (double)B * L * (8.0 * V + 17.0));
-  k4_init_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(first_reject, n_accept, B, seg);
-  SDVAR_LAUNCH_CHECK();
   const size_t k4_smem = (size_t)2 * 2 * V * 4 + 64;          // two stages x (target row + draft row) + mbarriers
   const int per_sm = (int)((220 * 1024) / (k4_smem + 1024)) < 3 ? (int)((220 * 1024) / (k4_smem + 1024)) : 3;
   SDVAR_REQUIRE(per_sm >= 1, "V=%d rows do not fit the shared-memory ring", V);
   const int grid = row_grid((long long)B * L, per_sm);
-#define SDVAR_K4(NV)                                                                                               \
-  case NV: {                                                                                                       \
-    static bool attr = false;                                                                                      \
-    if (!attr) {                                                                                                   \
-      SDVAR_CUDA(cudaFuncSetAttribute(k4_verify_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem)); \
-      attr = true;                                                                                                 \
-    }                                                                                                              \
-    k4_verify_kernel<NV><<<grid, kThreads, k4_smem, st>>>(xt, xd, draft_idx, u, noise, B, L, seg, out_idx, accept, \
-                                                          p_d_out, q_d_out, first_reject, n_accept, accepted_stages, \
-                                                          summary, workspace);                                     \
+#define SDVAR_K4(NV)                                                                                                 \
+  case NV: {                                                                                                         \
+    SDVAR_SET_SMEM_ONCE(k4_verify_kernel<NV>, k4_smem);                                                              \
+    k4_verify_kernel<NV><<<grid, kThreads, k4_smem, st>>>(xt, xd, draft_idx, u, noise, stage_major_aux, B, L, seg, out_idx, \
+                                                          accept, p_d_out, q_d_out, first_reject, n_accept,         \
+                                                          accepted_stages, summary, workspace);                     \
   } break;
   switch (V / 1024) {
     SDVAR_K4(1) SDVAR_K4(2) SDVAR_K4(4) SDVAR_K4(8)

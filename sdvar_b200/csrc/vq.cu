@@ -1,7 +1,7 @@
 // vq.cu -- K5: VectorQuantizer2 next-input step and the stage input maps.
 //
 // Replaces models/var.py:205-211 + models/quant.py:187-196 (get_next_autoregressive_input),
-// :199-206 (Phi = 0.5*h + 0.5*conv3x3(h)), and models/var.py:179-188 (stage input maps).
+// :199-206 (Phi = (1-r)*h + r*conv3x3(h), r = |quant_resi|), and models/var.py:179-188 (stage input maps).
 //
 // f_hat is tiny (32 KiB per image at 256 px), so this step is latency-bound, not HBM-bound: the design
 // goal is few launches and on-chip staging.  Kernel A gives each CTA one output row of one image: it
@@ -40,7 +40,7 @@ __device__ __forceinline__ void cubic_src(int o, int pn, int HW, int& ix, float&
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 struct VqSmem {
-  float w[kC * 9 * kC];                       // [ci][tap][co]
+  float w[kC * 9 * (kC + 1)];                 // [ci][tap][co], rows padded to 33 floats: the transposing stores are conflict-free
   float bias[kC];
   float src[kMaxSrcRows][kMaxHW][kC];         // gathered codebook rows  [r][q][c]
   float tmp[kMaxSrcRows][kMaxHW][kC];         // after horizontal interpolation [r][x][c]
@@ -50,7 +50,8 @@ struct VqSmem {
 
 __global__ void __launch_bounds__(256)
 vq_accumulate_kernel(const long long* __restrict__ idx, int pn, int HW, const float* __restrict__ codebook,
-                     const float* __restrict__ phi_w, const float* __restrict__ phi_b, float* __restrict__ f_hat) {
+                     const float* __restrict__ phi_w, const float* __restrict__ phi_b, float resi, float* __restrict__ f_hat,
+                     float* __restrict__ f_rest) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VqSmem& s = *reinterpret_cast<VqSmem*>(smem_raw);
   const int b = blockIdx.y, y = blockIdx.x, tid = threadIdx.x;
@@ -60,7 +61,7 @@ vq_accumulate_kernel(const long long* __restrict__ idx, int pn, int HW, const fl
   // stage Phi weights as [ci][tap][co] (global layout is [co][ci][3][3])
   for (int i = tid; i < kC * kC * 9; i += 256) {
     const int co = i / (kC * 9), rem = i - co * kC * 9, ci = rem / 9, tap = rem - ci * 9;
-    s.w[(ci * 9 + tap) * kC + co] = phi_w[i];
+    s.w[(ci * 9 + tap) * (kC + 1) + co] = phi_w[i];
   }
   if (tid < kC) s.bias[tid] = phi_b[tid];
 
@@ -126,16 +127,18 @@ vq_accumulate_kernel(const long long* __restrict__ idx, int pn, int HW, const fl
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx)
-          acc += s.w[(ci * 9 + dy * 3 + dx) * kC + lane] * s.hup[dy][x + dx][ci];
+          acc += s.w[(ci * 9 + dy * 3 + dx) * (kC + 1) + lane] * s.hup[dy][x + dx][ci];
     }
-    s.outT[lane][x] = 0.5f * s.hup[1][x + 1][lane] + 0.5f * acc;
+    // Phi (models/quant.py:205-206): (1-r)*h + r*conv(h); r = 0.5 in every released checkpoint
+    s.outT[lane][x] = (1.0f - resi) * s.hup[1][x + 1][lane] + resi * acc;
   }
   __syncthreads();
   // f_hat[b, c, y, :] += outT[c][:]   (row-contiguous)
   for (int i = tid; i < kC * HW; i += 256) {
     const int c = i / HW, x = i - c * HW;
-    float* p = f_hat + (((long long)b * kC + c) * HW + y) * HW + x;
-    *p += s.outT[c][x];
+    const long long o = (((long long)b * kC + c) * HW + y) * HW + x;
+    f_hat[o] += s.outT[c][x];
+    if (f_rest != nullptr) f_rest[o] -= s.outT[c][x];   // encode side: the reference's running residual (models/quant.py:163)
   }
 }
 
@@ -286,28 +289,35 @@ extern "C" int sdvar_vq_nearest_code(const float* z_NC, const float* codebook, l
 }
 
 extern "C" int sdvar_vq_next_input(const long long* idx_Bl, int B, int pn, int HW, int pn_next, int Cvae,
-                                   const float* codebook, const float* phi_w, const float* phi_b, float* f_hat,
-                                   float* next_map, float* scratch, void* stream) {
-  (void)scratch;
+                                   const float* codebook, const float* phi_w, const float* phi_b, float resi_ratio,
+                                   float* f_hat, float* next_map, float* f_rest, void* stream) {
   if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(resi_ratio >= 0.0f && resi_ratio <= 1.0f, "resi_ratio=%f outside [0,1]", (double)resi_ratio);
   SDVAR_REQUIRE(idx_Bl && codebook && phi_w && phi_b && f_hat, "NULL argument");
   SDVAR_REQUIRE(Cvae == kC, "Cvae=%d unsupported (32)", Cvae);
   SDVAR_REQUIRE(B > 0 && pn >= 1 && pn <= HW && HW <= kMaxHW, "bad geometry pn=%d HW=%d", pn, HW);
   SDVAR_REQUIRE(pn_next >= 0 && pn_next <= HW, "bad pn_next=%d", pn_next);
   SDVAR_REQUIRE(pn_next == 0 || next_map != nullptr, "next_map is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SDVAR_CUDA(cudaFuncSetAttribute(vq_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VqSmem)));
-    attr_set = true;
-  }
+  SDVAR_SET_SMEM_ONCE(vq_accumulate_kernel, sizeof(VqSmem));
   ProfileScope prof(st, FAM_VQ, (double)B * (2.0 * Cvae * HW * HW * 4 + 8.0 * pn * pn + 4.0 * Cvae * pn_next * pn_next));
-  vq_accumulate_kernel<<<dim3(HW, B), 256, sizeof(VqSmem), st>>>(idx_Bl, pn, HW, codebook, phi_w, phi_b, f_hat);
+  vq_accumulate_kernel<<<dim3(HW, B), 256, sizeof(VqSmem), st>>>(idx_Bl, pn, HW, codebook, phi_w, phi_b, resi_ratio, f_hat, f_rest);
   SDVAR_LAUNCH_CHECK();
   if (pn_next > 0) {
     vq_area_down_kernel<<<B, 256, 0, st>>>(f_hat, HW, pn_next, next_map);
     SDVAR_LAUNCH_CHECK();
   }
+  return SDVAR_OK;
+}
+
+extern "C" int sdvar_vq_area_down(const float* f_hat, int B, int HW, int pn_next, int Cvae, float* next_map, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(f_hat && next_map, "NULL argument");
+  SDVAR_REQUIRE(Cvae == kC, "Cvae=%d unsupported (32)", Cvae);
+  SDVAR_REQUIRE(B > 0 && HW >= 1 && HW <= kMaxHW && pn_next >= 1 && pn_next <= HW, "bad geometry HW=%d pn_next=%d", HW, pn_next);
+  ProfileScope prof((cudaStream_t)stream, FAM_VQ, (double)B * Cvae * 4.0 * (HW * HW + pn_next * pn_next));
+  vq_area_down_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(f_hat, HW, pn_next, next_map);
+  SDVAR_LAUNCH_CHECK();
   return SDVAR_OK;
 }
 

@@ -115,6 +115,7 @@ class VarEngine:
             self._ws_key = key
         self.B, self.imgs, self.Lq_max = B, imgs, Lq_max
         self.kv_len = 0
+        self._slot_keep = []      # slot maps of the sub-batch passes in flight (kept alive until the next begin())
         # cond = class_emb(cat(label, num_classes))  (models/var.py:162) -- an index gather, plumbing
         lab = label_B.to(dev)
         self.cond = self.class_emb[torch.cat((lab, torch.full_like(lab, m.num_classes)))].contiguous()
@@ -133,28 +134,50 @@ class VarEngine:
                         E(epilogue=_cabi.EPI_F32, bias=self.b_headnm.data_ptr(), out_f32=self.head_mod.data_ptr(), ldo=2 * C))
 
     # ------------------------------------------------------------------ stage inputs
-    def put_first_map(self, Lq: int, tok_off: int = 0):
+    def slot_map(self, slots: torch.Tensor) -> torch.Tensor:
+        """int32 device map of a sub-batch pass: pass-image i < n is the conditional row of image slots[i], pass-image n+i its
+        unconditional row (cache / adaLN slots slots[i] and B + slots[i])."""
+        sl = slots.to(device=self.dev, dtype=torch.int32)
+        mp = torch.cat((sl, sl + self.B)).contiguous()
+        self._slot_keep.append(mp)
+        return mp
+
+    def put_first_map(self, Lq: int, tok_off: int = 0, slot_map: Optional[torch.Tensor] = None):
         m = self.m
-        _cabi.first_map(self.cond, self.imgs, m.first_l, m.C, self.pos_start, self.lvl_pos[:m.first_l], self.x, Lq, tok_off)
+        cond = self.cond if slot_map is None else self.cond[slot_map.long()].contiguous()
+        _cabi.first_map(cond, cond.shape[0], m.first_l, m.C, self.pos_start, self.lvl_pos[:m.first_l], self.x, Lq, tok_off)
 
     def put_embed_map(self, si: int, next_map: torch.Tensor, Lq: int, tok_off: int = 0):
         m = self.m
-        _cabi.embed_next_map(next_map, self.B, m.ls[si], m.Cvae, m.C, self.w_we, self.b_we,
+        _cabi.embed_next_map(next_map, next_map.shape[0], m.ls[si], m.Cvae, m.C, self.w_we, self.b_we,
                              self.lvl_pos[m.begins[si]:m.ends[si]], self.x, Lq, tok_off)
 
     # ------------------------------------------------------------------ one pass
-    def forward(self, stages: Sequence[int], want_logits: bool = True, check_position: bool = True) -> Optional[torch.Tensor]:
+    def forward(self, stages: Sequence[int], want_logits: bool = True, check_position: bool = True,
+                slot_map: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """Run the blocks (+head) over the inputs already placed in ``self.x`` for the consecutive ``stages``;
-        appends their K/V at kv_len.  Returns logits viewed as (imgs, Lq, V)."""
+        appends their K/V at the cache position.  Returns logits viewed as (imgs, Lq, V).
+
+        ``slot_map`` (from ``slot_map()``) runs the pass on a SUB-BATCH: its images keep their own cache / adaLN slots, the
+        pass itself is dense (per-image ragged acceptance).  A sub-batch pass writes at the stage's own
+        position ``begins[stages[0]]`` -- every image of the group has exactly its accepted prefix in the cache -- and does
+        not move the engine-wide ``kv_len``."""
         m = self.m
         assert list(stages) == list(range(stages[0], stages[0] + len(stages)))
-        # token positions live in lvl_pos, not in the cache: sd_test3's target starts mid-pyramid with an empty cache
-        assert not check_position or self.kv_len == m.begins[stages[0]], \
-            f"KV cache holds {self.kv_len} tokens, stage {stages[0]} starts at {m.begins[stages[0]]}"
+        imgs = self.imgs if slot_map is None else int(slot_map.shape[0])
+        if slot_map is None:
+            # token positions live in lvl_pos, not in the cache: sd_test3's target starts mid-pyramid with an empty cache
+            assert not check_position or self.kv_len == m.begins[stages[0]], \
+                f"KV cache holds {self.kv_len} tokens, stage {stages[0]} starts at {m.begins[stages[0]]}"
+            kv_off = self.kv_len
+        else:
+            kv_off = m.begins[stages[0]]
         Lq = sum(m.ls[s] for s in stages)
-        assert Lq <= self.Lq_max
+        assert Lq <= self.Lq_max and imgs <= self.imgs
         p = _cabi.Pass()
-        p.imgs, p.Lq, p.Lmax, p.Lmax_pad, p.kv_off, p.S = self.imgs, Lq, self.Lmax, self.Lmax_pad, self.kv_len, len(stages)
+        p.imgs, p.Lq, p.Lmax, p.Lmax_pad, p.kv_off, p.S = imgs, Lq, self.Lmax, self.Lmax_pad, kv_off, len(stages)
+        p.slot_map = 0 if slot_map is None else slot_map.data_ptr()
+        p.cache_slots = 0 if slot_map is None else self.imgs
         off = 0
         for j, s in enumerate(stages):
             p.seg_begin[j] = off
@@ -168,8 +191,9 @@ class VarEngine:
         p.xm, p.q, p.attn, p.hidden = self.xm.data_ptr(), self.q.data_ptr(), self.attn.data_ptr(), self.hidden.data_ptr()
         p.logits = self.logits.data_ptr() if want_logits else 0
         _cabi.var_forward(self.weights, p)
-        self.kv_len += Lq
-        return self.logits[:self.imgs * Lq].view(self.imgs, Lq, m.V) if want_logits else None
+        if slot_map is None:
+            self.kv_len += Lq
+        return self.logits[:imgs * Lq].view(imgs, Lq, m.V) if want_logits else None
 
     def kv_truncate(self, n: int):
         assert 0 <= n <= self.kv_len
@@ -191,11 +215,14 @@ class DeviceNoise:
             else:
                 self.g[k] = torch.Generator(device=device).manual_seed(seed * 4 + i)
 
-    def exponential(self, stream: str, rows: int, V: int) -> torch.Tensor:
-        return torch.empty(rows, V, device=self.device, dtype=torch.float32).exponential_(generator=self.g[stream])
+    def exponential(self, stream: str, rows: int, V: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``out`` (a contiguous (rows, V) slice of a larger buffer) receives exactly the values a fresh tensor would."""
+        t = torch.empty(rows, V, device=self.device, dtype=torch.float32) if out is None else out
+        return t.exponential_(generator=self.g[stream])
 
-    def uniform(self, stream: str, rows: int) -> torch.Tensor:
-        return torch.rand(rows, device=self.device, dtype=torch.float32, generator=self.g[stream])
+    def uniform(self, stream: str, rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        t = torch.empty(rows, device=self.device, dtype=torch.float32) if out is None else out
+        return t.uniform_(generator=self.g[stream])
 
 
 class SingleGeneratorNoise:

@@ -3,8 +3,9 @@ models/quant.py (embedding, quant_resi.qresi_ls.{i}, ema_vocab_hit_SV), with the
 done by the fused K5 kernel (``sdvar_vq_next_input``).
 
 In scope: ``embedding``, ``get_next_autoregressive_input``, ``embed_to_fhat`` /
-``idxBl_to_var_input`` built on the same kernel.  The VAE-training ``forward`` and the encode-side
-``f_to_idxBl_or_fhat`` are out of scope for this path and raise.
+``idxBl_to_var_input`` built on the same kernel, and the encode side ``f_to_idxBl_or_fhat`` (SURVEY.md 8f #3:
+nearest-code kernel + the same K5 step keeping the reference's running residual).  The VAE-training ``forward``
+is out of scope and raises.
 """
 from __future__ import annotations
 
@@ -73,7 +74,7 @@ class VectorQuantizer2(nn.Module):
         return self.quant_resi[si / (SN - 1)]
 
     def next_input_from_idx(self, si: int, f_hat: torch.Tensor, idx_Bl: torch.Tensor, next_map: Optional[torch.Tensor] = None,
-                            codebook: Optional[torch.Tensor] = None):
+                            codebook: Optional[torch.Tensor] = None, f_rest: Optional[torch.Tensor] = None):
         """K5: f_hat += Phi(bicubic_up(codebook[idx])) in place; returns (f_hat, area_down(f_hat) to the next stage).
         Replaces models/var.py:205,210-211 + models/quant.py:187-196."""
         SN = len(self.v_patch_nums)
@@ -83,7 +84,8 @@ class VectorQuantizer2(nn.Module):
         if next_map is None and pn2:
             next_map = torch.empty(B, self.Cvae, pn2, pn2, device=f_hat.device, dtype=torch.float32)
         cb = self.embedding.weight if codebook is None else codebook
-        _cabi.vq_next_input(idx_Bl, B, pn, HW, pn2, self.Cvae, cb, phi.weight, phi.bias, f_hat, next_map if pn2 else None)
+        _cabi.vq_next_input(idx_Bl, B, pn, HW, pn2, self.Cvae, cb, phi.weight, phi.bias, f_hat, next_map if pn2 else None,
+                            resi_ratio=phi.resi_ratio, f_rest=f_rest)
         return f_hat, (next_map if pn2 else f_hat)
 
     def get_next_autoregressive_input(self, si: int, SN: int, f_hat: torch.Tensor, h_BChw: torch.Tensor):
@@ -127,9 +129,9 @@ class VectorQuantizer2(nn.Module):
     def f_to_idxBl_or_fhat(self, f_BChw: torch.Tensor, to_fhat: bool, v_patch_nums=None):
         """Multi-scale residual quantisation of an encoder feature map (models/quant.py:135-166): per scale, area-downsample
         the residual, take the nearest codebook entry (``sdvar_vq_nearest_code``), add Phi(bicubic_up(embedding)) to f_hat
-        (``sdvar_vq_next_input``) and continue on ``f - f_hat``.  Returns the token lists (B, pn*pn) or the f_hat snapshots.
-        The reference subtracts each scale from a running residual; here the residual is recomputed as ``f - f_hat`` (one
-        rounding instead of a chain), so an index can differ from the reference's only on a near-tie of two code distances."""
+        (``sdvar_vq_next_input``), which also subtracts the same increment from the running residual ``f_rest`` exactly as
+        the reference does (``f_hat.add_(h); f_rest.sub_(h)``, models/quant.py:162-163).  Returns the token lists
+        (B, pn*pn) or the f_hat snapshots."""
         assert not self.using_znorm, "using_znorm=True (cosine nearest neighbour) is not supported"
         pns = tuple(v_patch_nums) if v_patch_nums is not None else self.v_patch_nums
         assert tuple(int(p if isinstance(p, int) else p[0]) for p in pns) == self.v_patch_nums, \
@@ -137,18 +139,16 @@ class VectorQuantizer2(nn.Module):
         B, C, H, W = f_BChw.shape
         HW, SN = self.v_patch_nums[-1], len(self.v_patch_nums)
         assert C == self.Cvae and H == HW and W == HW, f"feature map {tuple(f_BChw.shape)} does not match the {HW}x{HW} latent grid"
-        f = f_BChw.detach().float().contiguous()
-        f_rest = f.clone()
-        f_hat = torch.zeros_like(f)
+        f_rest = f_BChw.detach().float().contiguous().clone()
+        f_hat = torch.zeros_like(f_rest)
         cb = self.embedding.weight.detach().float().contiguous()
         out = []
         for si, pn in enumerate(self.v_patch_nums):
             z = torch.nn.functional.interpolate(f_rest, size=(pn, pn), mode="area") if si != SN - 1 else f_rest
             z_NC = z.permute(0, 2, 3, 1).reshape(-1, C).contiguous()
-            idx_N = torch.empty(z_NC.shape[0], dtype=torch.int64, device=f.device)
+            idx_N = torch.empty(z_NC.shape[0], dtype=torch.int64, device=f_rest.device)
             _cabi.vq_nearest_code(z_NC, cb, z_NC.shape[0], C, self.vocab_size, idx_N)
             idx_Bl = idx_N.view(B, pn * pn)
-            self.next_input_from_idx(si, f_hat, idx_Bl, codebook=cb)
-            torch.sub(f, f_hat, out=f_rest)
+            self.next_input_from_idx(si, f_hat, idx_Bl, codebook=cb, f_rest=f_rest)
             out.append(f_hat.clone() if to_fhat else idx_Bl)
         return out

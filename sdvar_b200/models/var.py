@@ -62,6 +62,21 @@ class _HeadNorm(nn.Module):
         self.ada_lin = nn.Sequential(nn.SiLU(), nn.Linear(D, 2 * C))
 
 
+def _on_model_device(fn):
+    """Run an inference entry with the model's GPU as the current CUDA device: libsdvar launches on the current device and
+    stream, so a model living on cuda:1 must not be driven while cuda:0 is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        dev = self.device if isinstance(self, VAR) else self.target_model.device
+        if dev.type != "cuda":
+            raise _cabi.SdvarError("sdvar_b200 runs on sm_100a only: move the model to a CUDA device (no CPU fallback)")
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 def _trunc(t: torch.Tensor, std: float):
     nn.init.trunc_normal_(t, mean=0.0, std=std)
 
@@ -76,7 +91,7 @@ class VAR(nn.Module):
         assert mlp_ratio == 4.0
         self.Cvae, self.V = vae_local.Cvae, vae_local.vocab_size
         self.depth, self.C, self.D, self.num_heads = depth, embed_dim, embed_dim, num_heads
-        self.cond_drop_rate, self.norm_eps = cond_drop_rate, norm_eps
+        self.cond_drop_rate, self.norm_eps, self.drop_path_rate = cond_drop_rate, norm_eps, drop_path_rate
         self.shared_aln, self.attn_l2_norm = shared_aln, attn_l2_norm
         self.prog_si = -1
         self.patch_nums: Tuple[int, ...] = tuple(patch_nums)
@@ -140,6 +155,20 @@ class VAR(nn.Module):
                 blk.ada_lin[-1].weight.data[2 * self.C:].mul_(init_adaln)
                 blk.ada_lin[-1].weight.data[:2 * self.C].mul_(init_adaln_gamma)
                 blk.ada_lin[-1].bias.data.zero_()
+        self.repack()      # .data writes do not bump tensor versions: drop the packed bf16 copy explicitly
+
+    def repack(self):
+        """Invalidate the engine's packed bf16 weights; call after mutating parameters through ``.data`` (EMA updates,
+        manual surgery).  ``load_state_dict`` and ``init_weights`` do it themselves."""
+        self._engine._packed_key = None
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        self.repack()
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
+    def extra_repr(self) -> str:
+        """reference models/var.py:313-314"""
+        return f"drop_path_rate={self.drop_path_rate:g}"
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -178,6 +207,21 @@ class VAR(nn.Module):
         _cabi.sample_cfg_topk_topp(logits_2BLV, B, l, V, [0, l], t1, t2, top_k, thr, noise, idx, mixed, None, in_ld=in_ld, in_off=in_off)
         return idx, mixed
 
+    def _stage_step(self, si, logits, B, cfg, top_k, top_p, n, more_smooth, rng, f_hat):
+        """sample stage ``si`` from its logits and fold it into f_hat (models/var.py:199-211): (idx, f_hat, next_map)."""
+        vq, K = self.vae_quant_proxy[0], len(self.patch_nums)
+        if not more_smooth:
+            idx, _ = self._sample_stage(logits, B, si, cfg, top_k, top_p, n)
+            f_hat, next_map = vq.next_input_from_idx(si, f_hat, idx)
+        else:  # visualisation-only branch (models/var.py:206-208), torch ops on the kernel's filtered logits
+            idx, mixed = self._sample_stage(logits, B, si, cfg, top_k, top_p, n, want_mixed=True)
+            ratio = si / self.num_stages_minus_1
+            gum = -torch.empty_like(mixed).exponential_(generator=rng).log()
+            y = ((mixed * (1 + ratio) + gum) / max(0.27 * (1 - ratio * 0.95), 0.005)).softmax(-1)
+            h = (y @ vq.embedding.weight.unsqueeze(0)).transpose(1, 2).reshape(B, self.Cvae, self.patch_nums[si], self.patch_nums[si])
+            f_hat, next_map = vq.get_next_autoregressive_input(si, K, f_hat, h.contiguous())
+        return idx, f_hat, next_map
+
     def get_logits(self, h_BLC: torch.Tensor, cond_BD: torch.Tensor) -> torch.Tensor:
         """head(head_nm(h, cond)) in fp32 out (models/var.py:119-125): LN-modulate kernel + tcgen05 GEMM."""
         e = self._engine
@@ -196,6 +240,7 @@ class VAR(nn.Module):
 
     # ------------------------------------------------------------------ baseline loop (models/var.py:128-215)
     @torch.no_grad()
+    @_on_model_device
     def autoregressive_infer_cfg(self, B: int, label_B: Optional[Union[int, torch.LongTensor]], g_seed: Optional[int] = None,
                                  cfg=1.5, top_k=0, top_p=0.0, more_smooth=False, noise=None, return_tokens=False,
                                  record: Optional[dict] = None) -> torch.Tensor:
@@ -220,22 +265,14 @@ class VAR(nn.Module):
             n = noise.exponential("target", B * l, self.V)
             if record is not None:
                 record.setdefault("logits", []).append(logits.clone()); record.setdefault("noise", []).append(n)
-            if not more_smooth:
-                idx, _ = self._sample_stage(logits, B, si, cfg, top_k, top_p, n)
-                f_hat, next_map = vq.next_input_from_idx(si, f_hat, idx)
-            else:  # visualisation-only branch (models/var.py:206-208), torch ops on the kernel's filtered logits
-                idx, mixed = self._sample_stage(logits, B, si, cfg, top_k, top_p, n, want_mixed=True)
-                ratio = si / self.num_stages_minus_1
-                gum = -torch.empty_like(mixed).exponential_(generator=rng).log()
-                y = ((mixed * (1 + ratio) + gum) / max(0.27 * (1 - ratio * 0.95), 0.005)).softmax(-1)
-                h = (y @ vq.embedding.weight.unsqueeze(0)).transpose(1, 2).reshape(B, self.Cvae, self.patch_nums[si], self.patch_nums[si])
-                f_hat, next_map = vq.get_next_autoregressive_input(si, K, f_hat, h.contiguous())
+            idx, f_hat, next_map = self._stage_step(si, logits, B, cfg, top_k, top_p, n, more_smooth, rng, f_hat)
             idxs.append(idx)
         img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5)
         return (img, idxs, f_hat) if return_tokens else img
 
     # ------------------------------------------------------------------ teacher-forced (models/var.py:217-259)
     @torch.no_grad()
+    @_on_model_device
     def forward(self, label_B: torch.LongTensor, x_BLCv_wo_first_l: torch.Tensor) -> torch.Tensor:
         """All-stage block-causal pass; returns logits (B, L, V).  Runs as one verify-style window over every stage.
         The reference drops labels at cond_drop_rate even in eval (var.py:226, not gated on training); training is
@@ -254,19 +291,28 @@ class VAR(nn.Module):
 
 # ---------------------------------------------------------------------------------------------------
 class SDVARInferenceState:
-    """State of one speculative generation (reference: inner class at models/var.py:912-945)."""
+    """State of one speculative generation (reference: inner class at models/var.py:912-945).
+
+    Committed state is per IMAGE (``stage[b]``, ``f_hat[b]``, ``final[s][b]``, the KV slots b / B+b of both engines); a round
+    works on one GROUP of images that share a stage -- the whole batch under ``schedule='lockstep'``, a sub-batch under
+    ``schedule='ragged'`` (SURVEY.md 8f #2) -- and ``current_stage`` / ``gamma`` / ``group`` describe that group."""
 
     def __init__(self, B, gamma, patch_nums, cfg, noise):
         self.B, self.gamma, self.patch_nums, self.cfg, self.noise = B, gamma, patch_nums, cfg, noise
         self.current_stage, self.total_stages = 0, len(patch_nums)
         self.accept_count = self.reject_count = self.target_calls = self.draft_stage_calls = self.rounds = 0
         self.top_k, self.top_p, self.more_smooth = 0, 0.0, False
-        self.f_hat = None             # accepted f_hat (B,Cvae,HW,HW)
-        self.next_map = None          # accepted stage input for current_stage (None for stage 0)
-        self.final_idx: List[torch.Tensor] = []
-        # per-round scratch
-        self.maps, self.snaps, self.mixed_d, self.out_idx = [], [], [], []
-        self.advance: List[int] = []
+        self.schedule, self.gamma_policy, self.record = "lockstep", "fixed", None
+        self.f_hat = None             # committed f_hat (B,Cvae,HW,HW)
+        self.final: List[torch.Tensor] = []     # committed tokens per stage, (B, l_s) int64
+        self.stage = [0] * B          # per image: next stage to produce
+        self.gammas = [gamma] * B     # per image window length (moves only under gamma_policy='reference')
+        self.group: Optional[torch.Tensor] = None   # image ids of the current group (None = all, dense fast path)
+        self.n = B                    # images in the current group
+        # per-round scratch of the current group
+        self.maps, self.snaps, self.out_idx = [], [], None
+        self.win_xd = self.win_xt = self.win_d = None
+        self.advance: List = []
         self.stage_tokens = [0] * len(patch_nums)
         self.stage_accept_tokens = [0] * len(patch_nums)
 
@@ -279,11 +325,27 @@ class SDVARInferenceState:
     def target_f_hat(self):
         return self.f_hat
 
+    @property
+    def final_idx(self) -> List[torch.Tensor]:
+        return self.final
+
     def stats(self) -> dict:
         acc = sum(self.stage_accept_tokens)
         return dict(rounds=self.rounds, target_passes=self.target_calls, draft_stages=self.draft_stage_calls,
                     accepted_tokens=acc, rejected_tokens=sum(self.stage_tokens) - acc, advance=list(self.advance),
-                    stage_accept_tokens=list(self.stage_accept_tokens), stage_tokens=list(self.stage_tokens))
+                    stage_accept_tokens=list(self.stage_accept_tokens), stage_tokens=list(self.stage_tokens),
+                    schedule=self.schedule, gamma_policy=self.gamma_policy)
+
+
+def _draw(noise, kind: str, stream: str, out: torch.Tensor):
+    """fill the contiguous slice ``out`` from a noise provider; providers without ``out=`` support return a tensor to copy"""
+    try:
+        if kind == "exp":
+            noise.exponential(stream, out.shape[0], out.shape[1], out=out)
+        else:
+            noise.uniform(stream, out.shape[0], out=out)
+    except TypeError:
+        out.copy_(noise.exponential(stream, out.shape[0], out.shape[1]) if kind == "exp" else noise.uniform(stream, out.shape[0]))
 
 
 class SDVAR(nn.Module):
@@ -307,6 +369,7 @@ class SDVAR(nn.Module):
 
     # ------------------------------------------------------------------ hand-over variant (models/var.py:605-865)
     @torch.no_grad()
+    @_on_model_device
     def sdvar_autoregressive_infer_cfg_sd_test3(self, B: int, label_B, g_seed: Optional[int] = None, cfg: float = 1.5,
                                                 top_k: int = 0, top_p: float = 0.0, more_smooth: bool = False,
                                                 entry_num: int = 10, sd_mask: int = 0, noise=None, return_tokens=False):
@@ -316,12 +379,10 @@ class SDVAR(nn.Module):
         no defined semantics and is refused."""
         if sd_mask != 0:
             raise NotImplementedError("sd_mask != 0 discards the masked pass in the reference (models/var.py:809-811); not supported")
-        assert not more_smooth, "more_smooth is only wired into autoregressive_infer_cfg"
         D, T = self.draft_model, self.target_model
         rng = T._rng(g_seed)
         label_B = T._labels(B, label_B, rng)
         noise = noise or SingleGeneratorNoise(rng, T.device)
-        vq = T.vae_quant_proxy[0]
         K = len(T.patch_nums)
         f_hat = torch.zeros(B, T.Cvae, T.patch_nums[-1], T.patch_nums[-1], device=T.device)
         next_map, idxs = None, []
@@ -334,8 +395,8 @@ class SDVAR(nn.Module):
                 l = model.ls[si]
                 e.put_first_map(l) if si == 0 else e.put_embed_map(si, next_map, l)
                 logits = e.forward([si], check_position=False)
-                idx, _ = model._sample_stage(logits, B, si, cfg, top_k, top_p, noise.exponential("target", B * l, model.V))
-                f_hat, next_map = vq.next_input_from_idx(si, f_hat, idx)
+                idx, f_hat, next_map = model._stage_step(si, logits, B, cfg, top_k, top_p, noise.exponential("target", B * l, model.V),
+                                                         more_smooth, rng, f_hat)
                 idxs.append(idx)
         img = T.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5)
         return (img, idxs, f_hat) if return_tokens else img
@@ -351,162 +412,271 @@ class SDVAR(nn.Module):
         win = max(sum(T.ls[s:s + gamma]) for s in range(K))
         D._engine.begin(B, label_B)
         T._engine.begin(B, label_B, max_window_tokens=win)
-        state.f_hat = torch.zeros(B, T.Cvae, T.patch_nums[-1], T.patch_nums[-1], device=T.device)
         dev = T.device
-        state.ws = torch.zeros(4, dtype=torch.int32, device=dev)
+        state.f_hat = torch.zeros(B, T.Cvae, T.patch_nums[-1], T.patch_nums[-1], device=dev)
+        state.final = [torch.zeros(B, l, dtype=torch.int64, device=dev) for l in T.ls]
+        state.ws = torch.zeros(_cabi.verify_workspace_ints(B, min(gamma, K)), dtype=torch.int32, device=dev)
         return state
 
+    def _window(self, state: SDVARInferenceState):
+        """(stages, per-stage token offsets, window length) of the current group's round"""
+        T = self.target_model
+        g = min(state.gamma, state.total_stages - state.current_stage)
+        stages = list(range(state.current_stage, state.current_stage + g))
+        offs = [0]
+        for si in stages:
+            offs.append(offs[-1] + T.ls[si])
+        return stages, offs, offs[-1]
+
+    def _group_f_hat(self, state: SDVARInferenceState) -> torch.Tensor:
+        return state.f_hat.clone() if state.group is None else state.f_hat.index_select(0, state.group)
+
     def draft_generate_batch(self, state: SDVARInferenceState, B: int) -> List[torch.Tensor]:
-        """Draft g = min(gamma, K - stage) stages incrementally (models/var.py:949-1024).  Each stage's input is
-        area_down(f_hat) of the previous DRAFTED stage (fixes D2), stage 0 is the sos map (D3); the draft's masked
-        mixed logits, f_hat snapshots and next maps are kept for verification and rollback."""
+        """Draft g = min(gamma, K - stage) stages incrementally for the current group (models/var.py:949-1024).  Each stage's
+        input is area_down(f_hat) of the previous DRAFTED stage (fixes D2), stage 0 is the sos map (D3); K3 writes the draft's
+        tokens and its mixed+filtered logits straight into the window-shaped buffers the verify kernel reads; f_hat
+        snapshots are kept for the commit."""
         D = self.draft_model
         e, vq = D._engine, D.vae_quant_proxy[0]
-        g = min(state.gamma, state.total_stages - state.current_stage)
-        state.maps, state.snaps, state.mixed_d, draft_tokens = [state.next_map], [], [], []
-        if g <= 0:
+        stages, offs, Lw = self._window(state)
+        n, V, dev = state.n, D.V, D.device
+        state.snaps, draft_tokens = [], []
+        if not stages:
             return draft_tokens
-        fh = state.f_hat.clone()
-        for j in range(g):
-            si = state.current_stage + j
+        smap = None if state.group is None else e.slot_map(state.group)
+        state.win_xd = torch.empty(n, Lw, V, dtype=torch.float32, device=dev)
+        state.win_d = torch.empty(n, Lw, dtype=torch.int64, device=dev)
+        fh = self._group_f_hat(state)
+        nm = None
+        if stages[0] > 0:      # stage input rebuilt from the committed f_hat (same kernel as the K5 step => same bits)
+            pn = D.patch_nums[stages[0]]
+            nm = torch.empty(n, D.Cvae, pn, pn, dtype=torch.float32, device=dev)
+            _cabi.vq_area_down(fh, n, D.patch_nums[-1], pn, D.Cvae, nm)
+        state.maps = [nm]
+        thr = float(np.float32(1.0 - state.top_p)) if state.top_p > 0 else -1.0
+        for j, si in enumerate(stages):
             l = D.ls[si]
-            e.put_first_map(l) if si == 0 else e.put_embed_map(si, state.maps[j], l)
-            logits = e.forward([si])
-            n = state.noise.exponential("draft", B * l, D.V)
-            idx, mixed = D._sample_stage(logits, B, si, state.cfg, state.top_k, state.top_p, n, want_mixed=True)
+            e.put_first_map(l, slot_map=smap) if si == 0 else e.put_embed_map(si, state.maps[j], l)
+            logits = e.forward([si], slot_map=smap)
+            nz = state.noise.exponential("draft", n * l, V)
+            t1, t2 = D._cfg_scalars(state.cfg, [si])
+            _cabi.sample_cfg_topk_topp(logits, n, l, V, [0, l], t1, t2, state.top_k, thr, nz, state.win_d, state.win_xd, None,
+                                       out_ld=Lw, out_off=offs[j])
+            idx = state.win_d[:, offs[j]:offs[j + 1]].contiguous()
             fh, nm = vq.next_input_from_idx(si, fh, idx)
-            draft_tokens.append(idx); state.mixed_d.append(mixed); state.snaps.append(fh.clone())
+            draft_tokens.append(idx); state.snaps.append(fh.clone())
             state.maps.append(nm if si != state.total_stages - 1 else None)
             state.draft_stage_calls += 1
         return draft_tokens
 
     def target_verify_batch(self, draft_tokens: List[torch.Tensor], state: SDVARInferenceState, B: int):
         """ONE block-causal target pass over the g drafted stages on top of the KV cache of accepted stages
-        (models/var.py:1026-1158 intent; fixes D1,D5,D6): returns ([mixed+filtered target logits (B,l,V) per stage], g)."""
+        (models/var.py:1026-1158 intent; fixes D1,D5,D6), then ONE K3 launch that CFG-mixes and filters the whole window with
+        its per-stage strengths: returns ([mixed+filtered target logits (n,l,V) per stage, views of one window buffer], g)."""
         if not draft_tokens:
             return [], 0
         T = self.target_model
         e = T._engine
-        g = len(draft_tokens)
-        stages = list(range(state.current_stage, state.current_stage + g))
-        Lw = sum(T.ls[s] for s in stages)
-        off = 0
+        stages, offs, Lw = self._window(state)
+        g, n = len(stages), state.n
+        smap = None if state.group is None else e.slot_map(state.group)
         for j, si in enumerate(stages):
-            e.put_first_map(Lw, off) if si == 0 else e.put_embed_map(si, state.maps[j], Lw, off)
-            off += T.ls[si]
-        logits = e.forward(stages)
+            e.put_first_map(Lw, offs[j], slot_map=smap) if si == 0 else e.put_embed_map(si, state.maps[j], Lw, offs[j])
+        logits = e.forward(stages, slot_map=smap)
         state.target_calls += 1
-        out, off = [], 0
-        for si in stages:
-            _, mixed = T._sample_stage(logits, B, si, state.cfg, state.top_k, state.top_p, None, in_ld=Lw, in_off=off, want_mixed=True)
-            out.append(mixed)
-            off += T.ls[si]
-        return out, g
+        t1, t2 = T._cfg_scalars(state.cfg, stages)
+        thr = float(np.float32(1.0 - state.top_p)) if state.top_p > 0 else -1.0
+        state.win_xt = torch.empty(n, Lw, T.V, dtype=torch.float32, device=T.device)
+        _cabi.sample_cfg_topk_topp(logits, n, Lw, T.V, offs, t1, t2, state.top_k, thr, None, None, state.win_xt, None)
+        return [state.win_xt[:, offs[j]:offs[j + 1]] for j in range(g)], g
 
-    def speculative_token_matching(self, draft_tokens, target_logits, state: SDVARInferenceState, B: int) -> int:
-        """K4 per stage: accept u*q[d] < p[d], residual resample on reject, first-reject scan.  Returns the number of
-        stages to commit: a = min(#leading stages with no reject in any image + 1, g); the last committed stage keeps the
-        accepted draft tokens plus the target's repairs."""
+    def _advance_from_counts(self, state, stages, n_ok_per_image, na_host, lockstep_n_ok):
+        """statistics + advance lengths from the per-(image, stage) accept counts of the round"""
         T = self.target_model
-        g, dev = len(draft_tokens), T.device
-        summ = torch.empty(g, 4, dtype=torch.int32, device=dev)
-        state.out_idx = []
-        for j in range(g):
-            l = T.ls[state.current_stage + j]
-            u = state.noise.uniform("u", B * l)
-            nr = state.noise.exponential("resample", B * l, T.V)
-            out = torch.empty(B, l, dtype=torch.int64, device=dev)
-            acc = torch.empty(B, l, dtype=torch.uint8, device=dev)
-            fr = torch.empty(B, 1, dtype=torch.int32, device=dev); na = torch.empty(B, 1, dtype=torch.int32, device=dev)
-            st = torch.empty(B, dtype=torch.int32, device=dev)
-            _cabi.verify_accept_resample(target_logits[j], state.mixed_d[j], draft_tokens[j], u, nr, B, l, T.V, [0, l], out, acc,
-                                         None, None, fr, na, st, summ[j], state.ws)
-            state.out_idx.append(out)
-        s = summ.cpu()      # the one host sync of the round
-        n_ok = 0
-        for j in range(g):   # stages after the first failing one were conditioned on unrepaired tokens: not counted
-            si = state.current_stage + j
-            state.stage_tokens[si] += B * T.ls[si]
-            state.stage_accept_tokens[si] += int(s[j, 1])
-            if int(s[j, 2]) != 0:
-                break
-            n_ok += 1
-        return min(n_ok + 1, g)
+        g, n = len(stages), state.n
+        if state.schedule == "lockstep":
+            for j, si in enumerate(stages):   # stages after the first failing one were conditioned on unrepaired tokens: not counted
+                if j > lockstep_n_ok:
+                    break
+                state.stage_tokens[si] += n * T.ls[si]
+                state.stage_accept_tokens[si] += int(na_host[:, j].sum())
+            return min(lockstep_n_ok + 1, g)
+        adv = []
+        for i in range(n):
+            ok = int(n_ok_per_image[i])
+            for j, si in enumerate(stages):
+                if j > ok:
+                    break
+                state.stage_tokens[si] += T.ls[si]
+                state.stage_accept_tokens[si] += int(na_host[i, j])
+            adv.append(min(ok + 1, g))
+        return adv
+
+    def speculative_token_matching(self, draft_tokens, target_logits, state: SDVARInferenceState, B: int):
+        """K4 over the whole window in ONE launch: accept u*q[d] < p[d], residual resample on reject, per-(image, stage)
+        first-reject scan.  Returns the number of stages to commit: lock-step a = min(#leading stages with no reject in ANY
+        image + 1, g) (an int, the reference's ``accept_length``); under ``schedule='ragged'`` one such number PER IMAGE
+        (a list).  The last committed stage keeps the accepted draft tokens plus the target's repairs."""
+        T = self.target_model
+        stages, offs, Lw = self._window(state)
+        g, n, V, dev = len(stages), state.n, T.V, T.device
+        u = torch.empty(n * Lw, dtype=torch.float32, device=dev)
+        nr = torch.empty(n * Lw, V, dtype=torch.float32, device=dev)
+        for j in range(g):       # the per-stage draws of the loop spec, laid end to end ("stage-major")
+            _draw(state.noise, "uni", "u", u[n * offs[j]:n * offs[j + 1]])
+            _draw(state.noise, "exp", "resample", nr[n * offs[j]:n * offs[j + 1]])
+        out = torch.empty(n, Lw, dtype=torch.int64, device=dev)
+        acc = torch.empty(n, Lw, dtype=torch.uint8, device=dev)
+        fr = torch.empty(n, g, dtype=torch.int32, device=dev); na = torch.empty(n, g, dtype=torch.int32, device=dev)
+        st = torch.empty(n, dtype=torch.int32, device=dev); summ = torch.empty(4, dtype=torch.int32, device=dev)
+        _cabi.verify_accept_resample(state.win_xt, state.win_xd, state.win_d, u, nr, n, Lw, V, offs, out, acc, None, None, fr, na,
+                                     st, summ, state.ws, stage_major_aux=True)
+        state.out_idx = out
+        if state.record is not None:
+            state.record.setdefault("rounds", []).append(dict(
+                stage=stages[0], seg=list(offs), group=None if state.group is None else state.group.clone(), xt=state.win_xt.clone(),
+                xd=state.win_xd.clone(), d=state.win_d.clone(), u=u.clone(), noise=nr.clone(), out=out.clone(), accept=acc.clone(),
+                first_reject=fr.clone(), n_accept=na.clone(), accepted_stages=st.clone(), summary=summ.clone()))
+        h = torch.cat((summ, st, na.flatten())).cpu()      # the one host sync of the round
+        st_h, na_h = h[4:4 + n], h[4 + n:].view(n, g)
+        res = self._advance_from_counts(state, stages, st_h, na_h, int(h[0]))
+        state.last_n_ok = st_h
+        return res
 
     def basic_token_matching(self, draft_tokens, target_logits, state: SDVARInferenceState, B: int) -> int:
         """Reference rule (models/var.py:1160-1227): stage accepted iff the batch-mean top-1 match rate >= 0.5, stop at
         the first rejected stage.  Departure (D8): the rejected stage is repaired by sampling it from the target's
-        distribution instead of breaking out of the loop with a truncated image."""
+        distribution instead of breaking out of the loop with a truncated image.  The rule is batch-global by definition
+        (D9), so it only runs under the lock-step schedule."""
         T = self.target_model
-        g, dev = len(draft_tokens), T.device
-        nm = torch.empty(g, B, dtype=torch.int32, device=dev)
-        for j in range(g):
-            l = T.ls[state.current_stage + j]
-            match = torch.empty(B, l, dtype=torch.uint8, device=dev)
-            _cabi.verify_top1(target_logits[j], draft_tokens[j], B, l, T.V, [0, l], match, nm[j].view(B, 1))
-        counts = nm.cpu().sum(dim=1).tolist()
-        n_ok, state.out_idx = 0, []
-        for j in range(g):
-            si = state.current_stage + j
+        stages, offs, Lw = self._window(state)
+        g, n, V, dev = len(stages), state.n, T.V, T.device
+        assert state.schedule == "lockstep", "accept_rule='reference' couples the batch (models/var.py:1203): lock-step only"
+        match = torch.empty(n, Lw, dtype=torch.uint8, device=dev)
+        nm = torch.empty(n, g, dtype=torch.int32, device=dev)
+        _cabi.verify_top1(state.win_xt, state.win_d, n, Lw, V, offs, match, nm)
+        counts = nm.cpu().sum(dim=0).tolist()
+        n_ok = 0
+        for j, si in enumerate(stages):
             l = T.ls[si]
-            rate = counts[j] / float(B * l)
             if j == n_ok:
-                state.stage_tokens[si] += B * l
-                if rate >= 0.5:
+                state.stage_tokens[si] += n * l
+                if counts[j] / float(n * l) >= 0.5:
                     n_ok += 1
                     state.stage_accept_tokens[si] += counts[j]
-        for j in range(g):
-            l = T.ls[state.current_stage + j]
-            u = state.noise.uniform("u", B * l)                      # drawn to keep the stream positions rule-independent
-            nr = state.noise.exponential("resample", B * l, T.V)
-            if j < n_ok:
-                state.out_idx.append(draft_tokens[j])
-            else:
-                # target_logits[j] is already mixed+filtered: sample it with K3 as x = x*1 - 0*0
-                out = torch.empty(B, l, dtype=torch.int64, device=dev)
-                both = torch.cat((target_logits[j], torch.zeros_like(target_logits[j])), 0)
-                _cabi.sample_cfg_topk_topp(both, B, l, T.V, [0, l], [1.0], [0.0], 0, -1.0, nr, out, None, None)
-                state.out_idx.append(out)
+        out = state.win_d.clone()
+        for j, si in enumerate(stages):
+            l = T.ls[si]
+            u = state.noise.uniform("u", n * l)                      # drawn to keep the stream positions rule-independent
+            nr = state.noise.exponential("resample", n * l, V)
+            if j == n_ok:
+                # the window buffer is already mixed+filtered: sample it with K3 as x = x*1 - 0*0
+                x = state.win_xt[:, offs[j]:offs[j + 1]].contiguous()
+                both = torch.cat((x, torch.zeros_like(x)), 0)
+                _cabi.sample_cfg_topk_topp(both, n, l, V, [0, l], [1.0], [0.0], 0, -1.0, nr, out, None, None, out_ld=Lw, out_off=offs[j])
+        state.out_idx = out
+        state.last_n_ok = torch.full((n,), n_ok, dtype=torch.int32)
         return min(n_ok + 1, g)
 
-    def update_state_with_accepted_tokens(self, draft_tokens, accept_length: int, state: SDVARInferenceState, B: int):
-        """Commit ``accept_length`` stages (models/var.py:1245-1282): f_hat = snapshot after the last unmodified stage +
-        the final tokens of the last committed stage (fixes the double add D7); both KV caches roll back to the end of
-        the last committed stage (D4)."""
-        if accept_length <= 0:
-            return
+    def advanced_token_matching(self, draft_tokens, target_logits, state: SDVARInferenceState, B: int) -> int:
+        """The reference's placeholder (models/var.py:1229-1243) returns the basic rule's result; so does this."""
+        return self.basic_token_matching(draft_tokens, target_logits, state, B)
+
+    def update_state_with_accepted_tokens(self, draft_tokens, accept_length, state: SDVARInferenceState, B: int):
+        """Commit ``accept_length`` stages of the current group (models/var.py:1245-1282): f_hat = snapshot after the last
+        unmodified stage + the final tokens of the last committed stage (fixes the double add D7); both KV caches roll back
+        to the end of the last committed stage (D4).  ``accept_length`` is an int (whole group) or a per-image list
+        (ragged): images are then committed in sub-groups of equal length."""
         T, D = self.target_model, self.draft_model
         vq = T.vae_quant_proxy[0]
-        s, a = state.current_stage, accept_length
-        for j in range(a - 1):
-            state.final_idx.append(draft_tokens[j])
-        state.final_idx.append(state.out_idx[a - 1])
-        base = state.snaps[a - 2].clone() if a >= 2 else state.f_hat
-        state.f_hat, nm = vq.next_input_from_idx(s + a - 1, base, state.out_idx[a - 1])
-        state.next_map = nm if s + a < state.total_stages else None
-        D._engine.kv_truncate(D.ends[s + a - 1])
-        T._engine.kv_truncate(T.ends[s + a - 1])
+        stages, offs, Lw = self._window(state)
+        s, n = state.current_stage, state.n
+        ids = list(range(state.B)) if state.group is None else state.group.tolist()
+        if isinstance(accept_length, int):
+            parts = [(accept_length, None)] if accept_length > 0 else []
+        else:
+            parts = [(a, [i for i in range(n) if accept_length[i] == a]) for a in sorted(set(accept_length)) if a > 0]
+        for a, rows in parts:
+            sel = None if rows is None else torch.tensor(rows, device=T.device, dtype=torch.int64)
+            dst = state.group if rows is None else torch.tensor([ids[i] for i in rows], device=T.device, dtype=torch.int64)
+            pick = (lambda t: t) if sel is None else (lambda t: t.index_select(0, sel))
+            last = pick(state.out_idx[:, offs[a - 1]:offs[a]]).contiguous()
+            base = pick(state.snaps[a - 2]).clone() if a >= 2 else (self._group_f_hat(state) if sel is None else
+                                                                     state.f_hat.index_select(0, dst))
+            fh, _ = vq.next_input_from_idx(s + a - 1, base, last)
+            if dst is None:
+                for j in range(a - 1):
+                    state.final[s + j].copy_(draft_tokens[j])
+                state.final[s + a - 1].copy_(last)
+                state.f_hat = fh
+            else:
+                for j in range(a - 1):
+                    state.final[s + j].index_copy_(0, dst, pick(draft_tokens[j]))
+                state.final[s + a - 1].index_copy_(0, dst, last)
+                state.f_hat.index_copy_(0, dst, fh)
+            for i in (range(n) if rows is None else rows):
+                state.stage[ids[i]] = s + a
+        if state.group is None and isinstance(accept_length, int) and accept_length > 0:
+            D._engine.kv_truncate(D.ends[s + accept_length - 1])     # sub-batch passes address the cache by stage position instead
+            T._engine.kv_truncate(T.ends[s + accept_length - 1])
 
     @torch.no_grad()
+    @_on_model_device
     def sdvar_autoregressive_infer_cfg_parallel_v1(self, B: int, label_B=None, g_seed: Optional[int] = None, cfg: float = 1.5,
                                                    gamma: int = 2, top_k: int = 0, top_p: float = 0.0, more_smooth: bool = False,
-                                                   accept_rule: str = "speculative", noise=None, return_tokens: bool = False):
+                                                   accept_rule: str = "speculative", schedule: str = "lockstep",
+                                                   gamma_policy: str = "fixed", noise=None, return_tokens: bool = False,
+                                                   record: Optional[dict] = None):
         """while stage < K: draft g stages -> one target pass -> verify -> commit a prefix (models/var.py:1285-1383).
-        Returns the image (B,3,H,W) in [0,1]; acceptance statistics are left in ``self.last_stats``."""
-        assert not more_smooth, "more_smooth is only wired into autoregressive_infer_cfg"
-        assert accept_rule in ("speculative", "reference")
+        Returns the image (B,3,H,W) in [0,1]; acceptance statistics are left in ``self.last_stats``.
+
+        schedule      'lockstep' (default; the reference's batch-global ``accept_length``, var.py:1349-1350): the whole batch
+                      advances by the minimum over images.  'ragged' (SURVEY.md 8f #2): every image keeps its own stage
+                      pointer and advances by its own accepted prefix; each round runs one dense pass per group of images that
+                      share a stage, addressed through a slot map, so accepted images do not wait for rejected ones.
+        gamma_policy  'fixed' (default) or 'reference' = the reference's controller (var.py:1352-1372): after a round in which
+                      no drafted stage survived intact the window shrinks by one (never below 1, never grows back).
+        more_smooth   accepted and stored like the reference does (var.py:1315); the drafting / verification path never reads
+                      it there either.
+        record        optional dict: receives every round's verify inputs and outputs (loop-replay tests)."""
+        assert accept_rule in ("speculative", "reference") and schedule in ("lockstep", "ragged") and gamma_policy in ("fixed", "reference")
+        assert gamma >= 1
         state = self._initialize_inference_state(B, label_B, g_seed, cfg, gamma, noise)
         state.top_k, state.top_p, state.more_smooth = top_k, top_p, more_smooth
+        state.schedule, state.gamma_policy, state.record = schedule, gamma_policy, record
         match = self.speculative_token_matching if accept_rule == "speculative" else self.basic_token_matching
-        while state.current_stage < state.total_stages:
-            draft_tokens = self.draft_generate_batch(state, B)
-            target_logits, _ = self.target_verify_batch(draft_tokens, state, B)
-            accept_length = match(draft_tokens, target_logits, state, B)
-            self.update_state_with_accepted_tokens(draft_tokens, accept_length, state, B)
-            state.accept_count += accept_length
-            state.current_stage += accept_length
+        K, dev = state.total_stages, self.target_model.device
+        while min(state.stage) < K:
+            if schedule == "lockstep":
+                groups = [(state.stage[0], state.gammas[0], None)]
+            else:
+                keys = sorted({(state.stage[b], state.gammas[b]) for b in range(B) if state.stage[b] < K})
+                groups = [(s, gm, [b for b in range(B) if state.stage[b] == s and state.gammas[b] == gm]) for s, gm in keys]
+            round_adv = []
+            for s, gm, members in groups:
+                state.current_stage, state.gamma = s, gm
+                state.group = None if members is None or len(members) == B else torch.tensor(members, device=dev, dtype=torch.int64)
+                state.n = B if state.group is None else len(members)
+                ids = list(range(B)) if state.group is None else members
+                draft_tokens = self.draft_generate_batch(state, state.n)
+                target_logits, _ = self.target_verify_batch(draft_tokens, state, state.n)
+                accept_length = match(draft_tokens, target_logits, state, state.n)
+                self.update_state_with_accepted_tokens(draft_tokens, accept_length, state, state.n)
+                per_img = [accept_length] * state.n if isinstance(accept_length, int) else accept_length
+                round_adv += per_img
+                if gamma_policy == "reference":      # var.py:1352-1358: shrink the window after a round with no intact stage
+                    n_ok = state.last_n_ok.tolist()
+                    if schedule == "lockstep":
+                        if min(n_ok) == 0:
+                            state.gammas = [max(1, gm - 1)] * B
+                    else:
+                        for i, b in enumerate(ids):
+                            if n_ok[i] == 0:
+                                state.gammas[b] = max(1, gm - 1)
+            state.accept_count += min(round_adv)
             state.rounds += 1
-            state.advance.append(accept_length)
+            state.advance.append(round_adv[0] if schedule == "lockstep" else round(sum(round_adv) / len(round_adv), 3))
+        state.current_stage = K
         self.last_stats = state.stats()
         img = self.target_model.vae_proxy[0].fhat_to_img(state.f_hat).add_(1).mul_(0.5)
-        return (img, state.final_idx, state.f_hat) if return_tokens else img
+        return (img, state.final, state.f_hat) if return_tokens else img

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert set(cabi.EXPORTS) <= declared
-    assert lib.sdvar_abi_version() == 1
+    assert lib.sdvar_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -230,3 +230,164 @@ def test_512px_pyramid_shared_aln_target_sd_loop(cuda_lib):
     scale = float(ref.abs().max())
     err = (got - ref).abs()
     assert float(err.max()) < 8e-3 * scale and float(err.mean()) < 1e-3 * scale, (float(err.max()), float(err.mean()), scale)
+
+
+@pytest.mark.parametrize("name,depth,C,H,seed", [("d16", 16, 1024, 16, 1), ("w30", 2, 1920, 30, 2)])
+def test_real_width_logits_vs_reference_golden(cuda_lib, name, depth, C, H, seed):
+    """north-star WIDTHS on the device: VAR.forward of VAR-d16 (C=1024, H=16, 16 blocks) and of a 2-block model at the d30
+    width (C=1920, H=30) against (a) the REAL reference's fp32 logits (tests/golden/real_width.npz) within the bf16-vs-fp32
+    tolerance of SURVEY.md A1 and (b) the bf16-emulating oracle within the tight tolerance that catches indexing bugs."""
+    import os
+    from oracle.ref_model import RefVAR
+    from sdvar_b200.models.var import VAR
+    from sdvar_b200.models.vqvae import VQVAE
+    from sdvar_b200.weights import hashed
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "real_width.npz"))
+    vae = VQVAE(vocab_size=4096, z_channels=32, ch=32, v_patch_nums=P256).to(DEV)
+    m = VAR(vae_local=vae, depth=depth, embed_dim=C, num_heads=H, attn_l2_norm=True, patch_nums=P256).to(DEV)
+    sd = var_state_dict(depth, patch_nums=P256, seed=seed, tag=name, embed_dim=C, num_heads=H, gamma_bias=0.5, init_head=1.0)
+    m.load_state_dict(sd)
+    lab = torch.tensor([int(z[f"{name}_label"])])
+    x_in = hashed(f"golden.width.{name}.x", 0, (1, 679, 32), 1.0)
+    got = m(lab.to(DEV), x_in.to(DEV)).cpu()
+    scale = float(z[f"{name}_absmax"])
+    ref32 = torch.from_numpy(z[f"{name}_logits_slice"])
+    e32 = (got[:, :, :96] - ref32).abs()
+    assert float(e32.max()) < 3e-2 * scale and float(e32.mean()) < 4e-3 * scale, (float(e32.max()), float(e32.mean()), scale)
+    ref16 = RefVAR(sd, P256, num_heads=H, mm="bf16").forward_teacher(lab, x_in)
+    e16 = (got - ref16).abs()
+    assert float(e16.max()) < 8e-3 * scale and float(e16.mean()) < 1e-3 * scale, (float(e16.max()), float(e16.mean()), scale)
+
+
+def _dense_aux(rec, n):
+    """stage-major u / noise of a recorded round -> dense (b, pos) order for the C spec"""
+    seg = rec["seg"]
+    Lw, V = seg[-1], rec["noise"].shape[1]
+    u, nz = torch.empty(n, Lw), torch.empty(n, Lw, V)
+    for j in range(len(seg) - 1):
+        l = seg[j + 1] - seg[j]
+        u[:, seg[j]:seg[j + 1]] = rec["u"][n * seg[j]:n * seg[j + 1]].cpu().view(n, l)
+        nz[:, seg[j]:seg[j + 1]] = rec["noise"][n * seg[j]:n * seg[j + 1]].cpu().view(n, l, V)
+    return u, nz.view(n * Lw, V)
+
+
+@pytest.mark.parametrize("schedule,gamma,top_k,top_p", [("lockstep", 2, 900, 0.96), ("lockstep", 3, 0, 0.0), ("ragged", 2, 0, 0.0)])
+def test_sd_loop_replay_against_spec(cuda_lib, schedule, gamma, top_k, top_p):
+    """LOOP-LEVEL replay (parity gap 4): every round's verify inputs (mixed target / draft logits, draft tokens, u,
+    resample noise) are recorded from the device loop and pushed through the C spec and the loop spec's advance rule
+    (DESIGN.md 3.4): accept flags, repaired tokens, first-reject scan and accepted-prefix lengths must be identical, the
+    committed tokens must be the draft tokens of the intact stages + the spec's output for the last committed stage, and
+    the stage pointers must advance by min(#intact leading stages + 1, g) -- per batch (lock-step) or per image (ragged)."""
+    from oracle import spec
+    from oracle.ref_model import ReplayNoise
+    vae, d, t, sd, _ = _build(P256, 2, 3, gamma_bias=0.5, init_head=1.0)
+    B, lab = 4, torch.tensor([1, 2, 3, 4], device=DEV)
+    rec = {}
+    _, final, _ = sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, gamma=gamma, cfg=1.5, top_k=top_k, top_p=top_p, schedule=schedule,
+                                                               noise=ReplayNoise(21, DEV), return_tokens=True, record=rec)
+    K = len(P256)
+    stage = [0] * B
+    assert len(rec["rounds"]) == sd.last_stats["target_passes"]
+    for r in rec["rounds"]:
+        ids = list(range(B)) if r["group"] is None else r["group"].tolist()
+        n, seg, s = len(ids), r["seg"], r["stage"]
+        g = len(seg) - 1
+        assert all(stage[b] == s for b in ids), "a group must hold images that share a stage"
+        u, nz = _dense_aux(r, n)
+        ref = spec.verify(r["xt"].cpu(), r["xd"].cpu(), r["d"].cpu(), u, nz, seg)
+        for k, name in (("out_idx", "out"), ("accept", "accept"), ("first_reject", "first_reject"), ("n_accept", "n_accept"),
+                        ("accepted_stages", "accepted_stages"), ("summary", "summary")):
+            assert torch.equal(r[name].cpu(), ref[k]), (k, s)
+        ok = ref["accepted_stages"].tolist()
+        adv = [min(min(ok) + 1, g)] * n if schedule == "lockstep" else [min(a + 1, g) for a in ok]
+        for i, b in enumerate(ids):
+            a = adv[i]
+            for j in range(a - 1):       # intact stages keep the draft tokens
+                assert torch.equal(final[s + j][b].cpu(), r["d"][i, seg[j]:seg[j + 1]].cpu()), (s, j, b)
+            assert torch.equal(final[s + a - 1][b].cpu(), ref["out_idx"][i, seg[a - 1]:seg[a]]), (s, b)
+            stage[b] += a
+    assert stage == [K] * B
+
+
+@pytest.mark.parametrize("gamma", [2, 3])
+def test_ragged_schedule_half_batch_identical_models(cuda_lib, gamma):
+    """Per-image ragged acceptance (VERDICT r1 'done means').  The target is a copy of the draft whose class
+    embedding differs for labels >= 500 only: images with labels < 500 see p == q bit for bit (every token accepted, they
+    advance gamma stages per round), the others see different distributions and advance by their own accepted prefix.
+    Checked: the identical-model images finish in ceil(K/gamma) rounds with zero rejected tokens while the batch as a whole
+    needs more rounds; f_hat == VQ(final tokens); the target's KV cache equals, bit for bit and per image, a clean
+    teacher-forced pass over the final tokens; the lock-step schedule on the same inputs needs at least as many target passes
+    per image."""
+    from oracle.ref_model import RefVQ, ReplayNoise
+    from sdvar_b200.models import SDVAR
+    vae, d, t, _, sds = _build(P256, 3, 3, gamma_bias=0.5, init_head=1.0)
+    tsd = {k: v.clone() for k, v in d.state_dict().items()}
+    tsd["class_emb.weight"][500:1000] += 0.5 * torch.randn(500, tsd["class_emb.weight"].shape[1], generator=torch.Generator().manual_seed(0)).to(DEV)
+    t.load_state_dict(tsd)
+    sd = SDVAR(d, t)
+    B = 6
+    lab = torch.tensor([3, 700, 41, 900, 77, 650], device=DEV)
+    same = [0, 2, 4]
+    rec = {}
+    img, final, f_hat = sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, gamma=gamma, cfg=1.5, top_k=0, top_p=0.0, schedule="ragged",
+                                                                     noise=ReplayNoise(5, DEV), return_tokens=True, record=rec)
+    st = dict(sd.last_stats)
+    K = len(P256)
+    # per-image history from the record
+    rounds_of = {b: 0 for b in range(B)}
+    rejected_of = {b: 0 for b in range(B)}
+    for r in rec["rounds"]:
+        ids = list(range(B)) if r["group"] is None else r["group"].tolist()
+        for i, b in enumerate(ids):
+            rounds_of[b] += 1
+            ok = int(r["accepted_stages"][i])
+            g = len(r["seg"]) - 1
+            upto = r["seg"][min(ok + 1, g)]
+            rejected_of[b] += int((r["accept"][i, :upto] == 0).sum())
+    for b in same:
+        assert rounds_of[b] == -(-K // gamma) and rejected_of[b] == 0, (b, rounds_of[b], rejected_of[b])
+    assert max(rounds_of.values()) > -(-K // gamma), "the perturbed images must have rejected something"
+    assert st["rounds"] == max(rounds_of.values())
+    assert torch.isfinite(img).all()
+    vq = RefVQ(sds["vae"], P256)
+    x_in, f_ref = _teacher_input(vq, [i.cpu() for i in final])
+    f_ref, _ = vq.next_input(K - 1, f_ref, final[-1].cpu())
+    assert torch.allclose(f_hat.cpu(), f_ref, rtol=1e-4, atol=1e-4)
+    e = t._engine
+    k_loop = [k.clone() for k in e.k_cache]
+    v_loop = [v.clone() for v in e.v_cache]
+    vqd = vae.quantize
+    fh = torch.zeros(B, 32, 16, 16, device=DEV)
+    e.begin(B, lab)
+    nm = None
+    for si in range(K):
+        l = t.ls[si]
+        e.put_first_map(l) if si == 0 else e.put_embed_map(si, nm, l)
+        e.forward([si], want_logits=False)
+        fh, nm = vqd.next_input_from_idx(si, fh, final[si])
+    for i in range(t.depth):
+        assert torch.equal(k_loop[i][:, :, :t.L], e.k_cache[i][:, :, :t.L]), i
+        assert torch.equal(v_loop[i][:, :, :, :t.L], e.v_cache[i][:, :, :, :t.L]), i
+    # lock-step on the same inputs: every image is held back by the slowest one
+    sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, gamma=gamma, cfg=1.5, top_k=0, top_p=0.0, schedule="lockstep", noise=ReplayNoise(5, DEV))
+    assert sd.last_stats["rounds"] >= max(rounds_of.values())
+
+
+def test_gamma_policy_reference_shrinks_window(cuda_lib):
+    """the reference's gamma controller (models/var.py:1352-1372): after a round in which no drafted stage survived intact
+    the window shrinks by one, never below 1; with the default 'fixed' policy it stays put."""
+    from oracle.ref_model import ReplayNoise
+    vae, d, t, sd, _ = _build(P256, 2, 3, gamma_bias=0.5, init_head=1.0)
+    B, lab = 3, torch.tensor([1, 2, 3], device=DEV)
+    rec = {}
+    sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, gamma=3, cfg=1.5, gamma_policy="reference", noise=ReplayNoise(9, DEV), record=rec)
+    widths = [len(r["seg"]) - 1 for r in rec["rounds"]]
+    g = 3
+    for r, w in zip(rec["rounds"], widths):
+        assert w == min(g, len(P256) - r["stage"])
+        if int(r["summary"][0]) == 0:
+            g = max(1, g - 1)
+    assert widths[-1] <= widths[0] and min(widths) >= 1 and sum(sd.last_stats["advance"]) == len(P256)
+    rec2 = {}
+    sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, gamma=3, cfg=1.5, gamma_policy="fixed", noise=ReplayNoise(9, DEV), record=rec2)
+    assert all(len(r["seg"]) - 1 == min(3, len(P256) - r["stage"]) for r in rec2["rounds"])

@@ -30,7 +30,7 @@ def test_verify_full_size_properties(cuda_lib, B, scale):
                  p=torch.empty(B, L, device=DEV), q=torch.empty(B, L, device=DEV),
                  fr=torch.empty(B, S, dtype=torch.int32, device=DEV), na=torch.empty(B, S, dtype=torch.int32, device=DEV),
                  st=torch.empty(B, dtype=torch.int32, device=DEV), sm=torch.empty(4, dtype=torch.int32, device=DEV))
-        ws = torch.zeros(4, dtype=torch.int32, device=DEV)
+        ws = torch.zeros(cuda_lib.verify_workspace_ints(B, S), dtype=torch.int32, device=DEV)
         cuda_lib.verify_accept_resample(xt, xd, d, u, noise, B, L, V, SEG, o["idx"], o["acc"], o["p"], o["q"], o["fr"], o["na"], o["st"], o["sm"], ws)
         torch.cuda.synchronize()
         outs.append(o)

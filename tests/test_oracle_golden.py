@@ -179,3 +179,18 @@ def test_nearest_code_spec_matches_reference_argmin():
     cb[9] = cb[3000]
     z = cb[[3000, 5, 9]].clone()
     assert spec.nearest_code(z, cb).tolist() == [7, 5, 7]
+
+
+@pytest.mark.parametrize("name,depth,C,H,seed", [("d16", 16, 1024, 16, 1), ("w30", 2, 1920, 30, 2)])
+def test_real_width_teacher_forced_logits_match_reference(name, depth, C, H, seed):
+    """north-star widths: the oracle's teacher-forced pass (fp32 regime) against the REAL reference's VAR.forward logits for
+    VAR-d16 and a 2-block model at the d30 width (tests/golden/real_width.npz, oracle/make_golden.py widths)."""
+    z = np.load(os.path.join(G, "real_width.npz"))
+    sd = var_state_dict(depth, patch_nums=P256, seed=seed, tag=name, embed_dim=C, num_heads=H, gamma_bias=0.5, init_head=1.0)
+    m = RefVAR(sd, P256, num_heads=H, mm="fp32")
+    x_in = hashed(f"golden.width.{name}.x", 0, (1, 679, 32), 1.0)
+    logits = m.forward_teacher(torch.tensor([int(z[f"{name}_label"])]), x_in)
+    ref = torch.from_numpy(z[f"{name}_logits_slice"])
+    scale = float(z[f"{name}_absmax"])
+    assert float((logits[:, :, :96] - ref).abs().max()) < 2e-5 * scale
+    assert float((logits.argmax(-1).numpy() == z[f"{name}_argmax"].astype(np.int64)).mean()) > 0.999

@@ -118,7 +118,7 @@ def bench_verify(out):
             o = torch.empty(B, L, dtype=torch.int64, device=DEV); a = torch.empty(B, L, dtype=torch.uint8, device=DEV)
             fr = torch.empty(B, S, dtype=torch.int32, device=DEV); na = torch.empty(B, S, dtype=torch.int32, device=DEV)
             st = torch.empty(B, dtype=torch.int32, device=DEV); sm = torch.empty(4, dtype=torch.int32, device=DEV)
-            ws = torch.zeros(4, dtype=torch.int32, device=DEV)
+            ws = torch.zeros(_cabi.verify_workspace_ints(B, S), dtype=torch.int32, device=DEV)
             f = lambda: _cabi.verify_accept_resample(xt, xd, d, u, noise, B, L, V, SEG, o, a, None, None, fr, na, st, sm, ws)
             ms = timeit(f, iters=5 if B >= 256 else 20)
             rej = int(sm[2])

@@ -17,7 +17,7 @@ noise = torch.empty(B * L, V, device="cuda").exponential_()
 o = torch.empty(B, L, dtype=torch.int64, device="cuda"); a = torch.empty(B, L, dtype=torch.uint8, device="cuda")
 fr = torch.empty(B, S, dtype=torch.int32, device="cuda"); na = torch.empty(B, S, dtype=torch.int32, device="cuda")
 st = torch.empty(B, dtype=torch.int32, device="cuda"); sm = torch.empty(4, dtype=torch.int32, device="cuda")
-ws = torch.zeros(4, dtype=torch.int32, device="cuda")
+ws = torch.zeros(_cabi.verify_workspace_ints(B, S), dtype=torch.int32, device="cuda")
 for _ in range(4):
     _cabi.verify_accept_resample(xt, xd, d, u, noise, B, L, V, SEG, o, a, None, None, fr, na, st, sm, ws)
 torch.cuda.synchronize()
