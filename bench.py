@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- images/sec of SDVAR draft-then-verify generation (d16 draft -> d30 target, 256 px) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling strong --global-batch 512 --depth-draft 20]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A "step" is one call of ``SDVAR.sdvar_autoregressive_infer_cfg_parallel_v1`` on a batch of B=64 synthetic class labels
-per GPU (BASELINE.json configs[1]); data-parallel replicas, weak scaling (per-GPU batch fixed), NCCL only to gather the
-images and the acceptance counters.  One JSON line is printed by rank 0:
+A "step" is one call of ``SDVAR.sdvar_autoregressive_infer_cfg_parallel_v1`` on a batch of synthetic class labels:
+B=64 per GPU (BASELINE.json configs[1]; weak scaling, the default) or a GLOBAL batch split over the ranks with
+``parallel.shard_range`` (``--scaling strong``, BASELINE.json configs[2]: rank r takes labels slice r and seed + r).
+Data-parallel replicas; NCCL only to gather the (uint8) images and to sum the acceptance counters.  Rank 0 prints ONE JSON line:
   value      images/s, labels already resident in HBM, result left in HBM          (device-timed, max over ranks)
   e2e        same metric through the public API with HOST labels (pinned) -> device and the images read back to host
-  roofline   the dominant kernel family (tcgen05 GEMM) : algorithmic FLOPs / CUDA-event time, vs the measured cuBLAS peak
+  roofline   the dominant kernel family (tcgen05 GEMM): algorithmic FLOPs / CUDA-event time, vs the measured cuBLAS peak
   kernels    the same figure for every kernel family (GB/s for the HBM-bound ones), incl. the verify kernel of the metric
-  cpu_baseline  the oracle restatement of the reference's loop timed on this box's host cores on a bounded sample
-``--impl reference`` times that CPU implementation alone (the reference is pure Python/PyTorch and does not travel to the
-GPU box; the oracle port under oracle/ is what is timed -- "kind": "port").
+  bounds     the acceptance-schedule bounds SURVEY.md 8(d) asks for, measured in the same run on the same models:
+             accept_all / reject_all (every window committed whole / one stage per round), target_only and draft_only
+             (``VAR.autoregressive_infer_cfg``), and the reference's gamma controller (``gamma_policy='reference'``)
+  cpu_baseline  the REFERENCE's own functions (oracle/_ref archive of its unmodified modules; ``kind: "reference"``) timed on
+             this box's host cores on a bounded sample, with the oracle port's loop beside it; ``kind: "port"`` only when
+             the archive is absent
+``--impl reference`` times that CPU implementation alone.
 """
 from __future__ import annotations
 
@@ -41,7 +46,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--global-batch", type=int, default=512, help="total images per step under --scaling strong")
+    ap.add_argument("--chunk", type=int, default=256, help="max images per generation call (KV rings must fit 180 GB)")
     ap.add_argument("--depth-draft", type=int, default=16)
     ap.add_argument("--depth-target", type=int, default=30)
     ap.add_argument("--gamma", type=int, default=2)
@@ -49,11 +57,14 @@ def parse():
     ap.add_argument("--top-k", type=int, default=900)
     ap.add_argument("--top-p", type=float, default=0.96)
     ap.add_argument("--accept-rule", default="speculative", choices=["speculative", "reference"])
+    ap.add_argument("--schedule", default="lockstep", choices=["lockstep", "ragged"])
+    ap.add_argument("--gamma-policy", default="fixed", choices=["fixed", "reference"])
     ap.add_argument("--px", type=int, default=256, choices=[256, 512], help="256: patch_nums 1..16 (L=680); 512: 1..32 (L=2240)")
     ap.add_argument("--shared-aln-target", action="store_true", help="target uses shared adaLN (the d36 layout, README.md:142-144)")
     ap.add_argument("--cpu-sample-images", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-bounds", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler runs only; such a line is not a bench value)")
     return ap.parse_args()
 
@@ -115,35 +126,69 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_run(args, n_images: int, steps: int, warmup: int, device_for_init):
-    """The oracle restatement of the reference loop (oracle/ref_model.py:sd_generate + decoder) on the host cores."""
+def _host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(args, n_images: int, steps: int, warmup: int, device_for_init, extras: bool):
+    """The reference's own CPU path on the host cores, on a bounded sample of the bench workload (same models, fp32).
+
+    kind "reference": the UNMODIFIED reference modules (oracle/_ref archive, oracle/build_ref.py).  Its draft->verify loop
+    ``sdvar_autoregressive_infer_cfg_parallel_v1`` crashes, so the timed entry is the reference's one SD loop
+    that runs, ``sdvar_autoregressive_infer_cfg_sd_test3(entry_num=5)`` (models/var.py:605: draft stages 0-4, target stages 5-9).
+    ``extras`` adds one timed run each of the reference's draft / target ``autoregressive_infer_cfg`` (models/var.py:128) and of
+    the oracle port of the repaired loop (oracle/ref_model.py:sd_generate), so the port number stays comparable with round 1.
+    kind "port": the archive is absent; only the oracle port is timed."""
+    from oracle import ref_runtime
     from oracle.ref_model import RefDecoder, RefVAR, RefVQ, ReplayNoise, sd_generate
     from sdvar_b200.weights import var_state_dict, vqvae_state_dict
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
+    cores = _host_cores()
     torch.set_num_threads(cores)
     cpu = lambda sd: {k: v.cpu() for k, v in sd.items()}
     vsd = cpu(vqvae_state_dict(ch=160, patch_nums=P256, device=device_for_init))
-    d = RefVAR(cpu(var_state_dict(args.depth_draft, patch_nums=P256, seed=1, tag="draft", device=device_for_init)), P256)
-    t = RefVAR(cpu(var_state_dict(args.depth_target, patch_nums=P256, seed=2, tag="target", device=device_for_init,
-                                  shared_aln=args.shared_aln_target)), P256)
-    vq, dec = RefVQ(vsd, P256), RefDecoder(vsd)
+    dsd = cpu(var_state_dict(args.depth_draft, patch_nums=P256, seed=1, tag="draft", device=device_for_init))
+    tsd = cpu(var_state_dict(args.depth_target, patch_nums=P256, seed=2, tag="target", device=device_for_init, shared_aln=args.shared_aln_target))
     lab = torch.randint(0, 1000, (n_images,), generator=torch.Generator().manual_seed(0))
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        f_hat, _, stats = sd_generate(d, t, vq, n_images, lab, ReplayNoise(i), cfg=args.cfg, gamma=args.gamma, top_k=args.top_k,
-                                      top_p=args.top_p, accept_rule=args.accept_rule)
-        dec.fhat_to_img(f_hat).add_(1).mul_(0.5)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    dt = sum(times) / len(times)
-    return dict(value=n_images / dt, unit="images/s", cores=cores, kind="port",
-                sample=f"{n_images} image(s)/step x {steps} step(s), fp32, d{args.depth_draft}->d{args.depth_target} SD gamma={args.gamma} "
-                       f"oracle/ref_model.py:sd_generate + decoder, {warmup} warm-up"), dt, stats
+    base = f"{n_images} image(s)/step, fp32, d{args.depth_draft}->d{args.depth_target}, {args.px}px, cfg={args.cfg}, top_k={args.top_k}, top_p={args.top_p}"
+
+    def port_once(warm, n):
+        d, t = RefVAR(dsd, P256), RefVAR(tsd, P256)
+        vq, dec = RefVQ(vsd, P256), RefDecoder(vsd)
+        ts, stats = [], None
+        for i in range(warm + n):
+            t0 = time.perf_counter()
+            f_hat, _, stats = sd_generate(d, t, vq, n_images, lab, ReplayNoise(i), cfg=args.cfg, gamma=args.gamma, top_k=args.top_k,
+                                          top_p=args.top_p, accept_rule=args.accept_rule)
+            dec.fhat_to_img(f_hat).add_(1).mul_(0.5)
+            if i >= warm:
+                ts.append(time.perf_counter() - t0)
+        return sum(ts) / len(ts), stats
+
+    if not ref_runtime.available():
+        dt, stats = port_once(warmup, steps)
+        return dict(value=n_images / dt, unit="images/s", cores=cores, kind="port",
+                    sample=f"{base}; {steps} step(s) after {warmup} warm-up of oracle/ref_model.py:sd_generate + decoder (gamma={args.gamma}); "
+                           f"oracle/_ref archive absent"), dt, stats
+    vae, draft, target, sd = ref_runtime.build_models(P256, args.depth_draft, args.depth_target, dsd, tsd, vsd, args.shared_aln_target)
+    kw = dict(cfg=args.cfg, top_k=args.top_k, top_p=args.top_p)
+    dt = ref_runtime.time_entry(lambda i: sd.sdvar_autoregressive_infer_cfg_sd_test3(n_images, lab, g_seed=i, entry_num=5, sd_mask=0, **kw),
+                                warmup, steps)
+    out = dict(value=n_images / dt, unit="images/s", cores=cores, kind="reference",
+               sample=f"{base}; {steps} step(s) after {warmup} warm-up of the reference's SDVAR.sdvar_autoregressive_infer_cfg_sd_test3("
+                      f"entry_num=5) (models/var.py:605; its parallel_v1 loop crashes, SURVEY.md 8a D1)")
+    if extras:
+        ex = {}
+        ex["reference_draft_autoregressive_infer_cfg"] = n_images / ref_runtime.time_entry(
+            lambda i: draft.autoregressive_infer_cfg(n_images, lab, g_seed=i, **kw), 0, 1)
+        ex["reference_target_autoregressive_infer_cfg"] = n_images / ref_runtime.time_entry(
+            lambda i: target.autoregressive_infer_cfg(n_images, lab, g_seed=i, **kw), 0, 1)
+        pdt, _ = port_once(0, 1)
+        ex["port_sd_generate_gamma%d" % args.gamma] = n_images / pdt
+        out["also_images_per_s"] = ex
+    return out, dt, None
 
 
 _REAL_STDOUT = None
@@ -178,20 +223,23 @@ def main():
     global P256
     if args.px == 512:
         P256 = P512          # every use below takes the selected pyramid
+    strong = args.scaling == "strong"
+    batch_txt = f"global batch {args.global_batch} split over {world} GPU(s)" if strong else f"batch {args.batch}/GPU"
     workload = (f"SDVAR VAR-d{args.depth_draft} draft + VAR-d{args.depth_target} target, random-init, {args.px}px, patch_nums 1..{P256[-1]}, "
-                f"batch {args.batch}/GPU, cfg={args.cfg}, top_k={args.top_k}, top_p={args.top_p}, gamma={args.gamma}, accept_rule={args.accept_rule}")
+                f"{batch_txt}, cfg={args.cfg}, top_k={args.top_k}, top_p={args.top_p}, gamma={args.gamma}, accept_rule={args.accept_rule}, "
+                f"schedule={args.schedule}, gamma_policy={args.gamma_policy}")
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        dev = f"cuda:{local}" if has_cuda else "cpu"
-        cb, dt, stats = cpu_reference_run(args, args.cpu_sample_images, args.steps, args.warmup, dev)
-        _emit({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-                          "config": {"workload": workload, "note": "CPU reference arm: bounded sample of the same workload"},
-                          "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0, "accept_stats": {k: stats[k] for k in ("rounds", "target_passes", "accepted_tokens", "rejected_tokens")}})
+        cb, dt, stats = cpu_reference_run(args, args.cpu_sample_images, args.steps, args.warmup, "cpu", extras=False)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": workload, "note": "CPU reference arm on the host cores: bounded sample of the same workload"},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        _emit(line)
         return 0
 
     if not has_cuda:
@@ -212,27 +260,45 @@ def main():
     vae.load_state_dict(vqvae_state_dict(ch=160, patch_nums=P256, device=dev))
     draft.load_state_dict(var_state_dict(args.depth_draft, patch_nums=P256, seed=1, tag="draft", device=dev))
     target.load_state_dict(var_state_dict(args.depth_target, patch_nums=P256, seed=2, tag="target", device=dev, shared_aln=args.shared_aln_target))
-    B = args.batch
     px = 16 * P256[-1]
-    lab_host = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(rank)).pin_memory()
+    if strong:      # BASELINE.json configs[2]: one global label vector, rank r owns slice r and uses seed + r
+        glob = torch.randint(0, 1000, (args.global_batch,), generator=torch.Generator().manual_seed(0))
+        lo, hi = parallel.shard_range(args.global_batch, rank, world)
+        lab_host = glob[lo:hi].clone().pin_memory()
+    else:
+        lab_host = torch.randint(0, 1000, (args.batch,), generator=torch.Generator().manual_seed(rank)).pin_memory()
+    B = int(lab_host.shape[0])
+    chunks = [(c, min(c + args.chunk, B)) for c in range(0, B, args.chunk)]
     lab_dev = lab_host.to(dev)
     img_host = torch.empty(B, 3, px, px, dtype=torch.float32).pin_memory()
+    gather_buf = parallel.GatherBuffer(world, B, (3, px, px), dev) if world > 1 else None
+    sd_kw = dict(cfg=args.cfg, gamma=args.gamma, top_k=args.top_k, top_p=args.top_p, accept_rule=args.accept_rule,
+                 schedule=args.schedule, gamma_policy=args.gamma_policy)
+
+    def generate(lab, seed, **over):
+        kw = dict(sd_kw); kw.update(over)
+        imgs, stats = [], []
+        for c0, c1 in chunks:
+            imgs.append(sd.sdvar_autoregressive_infer_cfg_parallel_v1(c1 - c0, lab[c0:c1], g_seed=seed + 7919 * c0, **kw))
+            stats.append(sd.last_stats)
+        st = stats[0] if len(stats) == 1 else {k: sum(s[k] for s in stats) for k in parallel.STAT_KEYS} | {"advance": stats[0]["advance"]}
+        return (imgs[0] if len(imgs) == 1 else torch.cat(imgs)), st
+
+    pending_stats = []
 
     def step(i: int, e2e: bool):
         lab = lab_host.to(dev, non_blocking=True) if e2e else lab_dev
-        img = sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, g_seed=1000 * rank + i, cfg=args.cfg, gamma=args.gamma,
-                                                           top_k=args.top_k, top_p=args.top_p, accept_rule=args.accept_rule)
-        st = sd.last_stats
-        if world > 1:   # the path's only collectives: images + acceptance counters
-            parallel.gather_images(img)
-            parallel.reduce_stats(st, dev)
+        img, st = generate(lab, 1000 * rank + i)
+        if world > 1:   # the path's only collectives: uint8 images + acceptance counters, no host sync
+            gather_buf.gather(img)
+            pending_stats.append(parallel.reduce_stats_async(st, dev))
         if e2e:
             img_host.copy_(img, non_blocking=True)
         return st
 
-    def timed(e2e: bool):
-        for i in range(args.warmup):
-            step(i, e2e)
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -244,8 +310,8 @@ def main():
         torch.cuda.synchronize()
         a.record()
         last = None
-        for i in range(args.steps):
-            last = step(args.warmup + i, e2e)
+        for i in range(steps):
+            last = fn(warmup + i)
         b.record()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
@@ -257,25 +323,50 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
             dist.barrier()
+        pending_stats.clear()
         return ms, launches, clocks, last
 
-    ms_dev, launches, clocks, last_stats = timed(False)
-    ms_e2e = timed(True)[0] if not args.no_e2e else float("nan")
-    total_imgs = world * B * args.steps
+    ms_dev, launches, clocks, last_stats = timed(lambda i: step(i, False), args.steps, args.warmup)
+    ms_e2e = timed(lambda i: step(i, True), args.steps, args.warmup)[0] if not args.no_e2e else float("nan")
+    gb = args.global_batch if strong else world * B
+    total_imgs = gb * args.steps
     value = total_imgs / (ms_dev * 1e-3)
     e2e_value = total_imgs / (ms_e2e * 1e-3)
 
     pk = peaks()
+    kv_gb = (2 * sum(p * p for p in P256) * 64 * 2 * 2 * (args.depth_draft ** 2 + args.depth_target ** 2)) * min(B, args.chunk) / 1e9
     out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+           "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16",
            "data": "synthetic",
-           "config": {"workload": workload, "global_batch": world * B, "parallelism": f"dp{world}",
-                      "l2": "no flush: per-step working set (bf16 weights 4.6 GB + KV ring ~27 GB + logits) >> 126 MB L2",
-                      "weights": "sdvar_b200.weights hashed init (seed 1 draft / 2 target / 0 vae)", "labels": "randint(0,1000) seed=rank"},
+           "config": {"workload": workload, "global_batch": gb, "per_gpu_batch": B, "calls_per_step": len(chunks), "parallelism": f"dp{world}",
+                      "l2": f"no flush: per-step working set (bf16 weights + KV rings ~{kv_gb:.0f} GB + logits) >> 126 MB L2",
+                      "weights": "sdvar_b200.weights hashed init (seed 1 draft / 2 target / 0 vae)",
+                      "labels": "randint(0,1000) seed 0, slice of rank" if strong else "randint(0,1000) seed=rank",
+                      "collectives": "all_gather of uint8 images + all_reduce of 5 int64 counters per step (none at N=1)"},
            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": B * 8,
                    "d2h_bytes_per_step": B * 3 * px * px * 4},
            "gpu_launches": launches, "clocks": clocks,
            "accept_stats": {k: last_stats[k] for k in ("rounds", "target_passes", "draft_stages", "accepted_tokens", "rejected_tokens", "advance")}}
+
+    if not args.no_bounds:
+        # acceptance-schedule bounds on the same models, labels and batch: 1 warm-up + 2 timed calls each
+        def ips(fn):
+            ms = timed(fn, 2, 1)[0]
+            return gb * 2 / (ms * 1e-3)
+
+        def only(model):
+            def f(i):
+                for c0, c1 in chunks:
+                    model.autoregressive_infer_cfg(c1 - c0, lab_dev[c0:c1], g_seed=1000 * rank + i, cfg=args.cfg, top_k=args.top_k, top_p=args.top_p)
+            return f
+        bounds = {"unit": "images/s", "how": "same run, same models / labels / batch; 1 warm-up + 2 timed calls each, device-timed",
+                  "accept_all": ips(lambda i: generate(lab_dev, i, _bound="accept_all")),
+                  "reject_all": ips(lambda i: generate(lab_dev, i, _bound="reject_all")),
+                  "gamma_policy_reference": ips(lambda i: generate(lab_dev, i, gamma_policy="reference")),
+                  "target_only": ips(only(target)), "draft_only": ips(only(draft)),
+                  "measured_schedule": value}
+        bounds["sd_speedup_vs_target_only"] = value / bounds["target_only"]
+        out["bounds"] = bounds
 
     if not args.no_profile:   # roofline leg: one extra step with per-family CUDA-event timing on the launch stream
         _cabi.profile_begin()
@@ -292,15 +383,18 @@ def main():
                 kern[fam] = {"bound": "hbm", "achieved": (work + extra) / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms": ms, "launches": n}
         g = kern.get("gemm")
         if g:
-            # DRAM bytes per launch of the GEMM family from the committed ncu launch list of this same default workload
-            # (profiles/traffic_r01.json <- profiles/launches_r01.md); null for any other workload
-            traffic = None
-            tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01.json")
-            default_workload = (args.batch, args.depth_draft, args.depth_target, args.gamma, args.px, args.top_k) == (64, 16, 30, 2, 256, 900)
-            if default_workload and os.path.exists(tpath):
-                traffic = json.load(open(tpath))["families"]["gemm"]["dram_bytes_per_launch"]
+            # DRAM bytes per launch of the GEMM family: STATIC, from the committed ncu launch list of this same default workload
+            # (profiles/traffic_r02.json if present, else r01); null for any other workload -- ncu cannot run inside a timed bench
+            traffic, tsrc = None, None
+            default_workload = (B, args.depth_draft, args.depth_target, args.gamma, args.px, args.top_k, args.scaling) == (64, 16, 30, 2, 256, 900, "weak")
+            for name in ("traffic_r02.json", "traffic_r01.json"):
+                tpath = os.path.join(ROOT, "profiles", name)
+                if default_workload and os.path.exists(tpath):
+                    traffic, tsrc = json.load(open(tpath))["families"]["gemm"]["dram_bytes_per_launch"], f"static: profiles/{name} (ncu launch list of this command, not measured in this run)"
+                    break
             out["roofline"] = {"bound": "tensor", "kernel": "sdvar::gemm2::gemm2_kernel<EPI> / gemm::gemm_kernel<EPI> (tcgen05, all epilogues)", "achieved": g["achieved"],
                                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": g["achieved"] / pk["tf_sustained"], "traffic": traffic,
+                               "traffic_source": tsrc,
                                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the family's launches)",
                                "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
                                "share_of_step_ms": g["ms"], "launches": g["launches"]}
@@ -309,7 +403,7 @@ def main():
         out["kernels"] = kern
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, _, _ = cpu_reference_run(args, args.cpu_sample_images, 1, 0, dev)
+        cb, _, _ = cpu_reference_run(args, args.cpu_sample_images, 1, 1, dev, extras=True)
         out["cpu_baseline"] = cb
     if rank == 0:
         _emit(out)

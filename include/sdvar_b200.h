@@ -146,6 +146,11 @@ int sdvar_ln_modulate(const float* x, int M, int C, int tokens_per_img, const fl
 int sdvar_silu_bf16(const float* x, long long n, sdvar_bf16* out, void* stream);
 int sdvar_f32_to_bf16(const float* x, long long n, sdvar_bf16* out, void* stream);
 
+/* image hand-over: fp32 images in [0,1] (B,3,H,W) -> uint8 = trunc(clamp(x,0,1)*255), what the reference's notebook writes
+ * to PNG (sdvar_colab_test.py:235-236) and what the data-parallel gather ships (4x fewer bytes than fp32).
+ * hwc == 0: out (B,3,H,W); hwc != 0: out (B,H,W,3), the layout of the FID .npz (utils/misc.py:360-381). */
+int sdvar_image_to_u8(const float* img_B3HW, int B, int H, int W, int hwc, uint8_t* out, void* stream);
+
 /* K1: D = epilogue(A[M,K] @ W[N,K]^T), bf16 operands, fp32 accumulation in TMEM (tcgen05.mma),
  * operands staged by TMA.  Replaces F.linear at models/basic_var.py:52,93,119,156 and
  * models/var.py:125.  K % 64 == 0, N % 32 == 0, A/W 16-byte aligned rows. */
@@ -265,6 +270,8 @@ int sdvar_profile_end(double* ms, double* work, long long* launches);
 
 /* number of kernels the library has launched since load (gpu_launches accounting in bench.py) */
 long long sdvar_launch_count(void);
+/* add n to that counter: called by a host that replays a captured CUDA graph of n library launches */
+void sdvar_count_launches(long long n);
 
 #ifdef __cplusplus
 }

@@ -265,10 +265,17 @@ class RefDecoder:
         h = torch.bmm(v, w.permute(0, 2, 1)).view(B, C, H, W)
         return x + self._conv(name + ".proj_out", h, 0)
 
-    def fhat_to_img(self, f_hat: torch.Tensor) -> torch.Tensor:
+    def fhat_to_img(self, f_hat: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        """``taps`` (optional dict) receives the feature map after conv_in, after the mid block and after every up level
+        (keys 'conv_in', 'mid', 'up.4' ... 'up.0'): per-layer parity targets for the device decoder."""
+        def tap(k, v):
+            if taps is not None:
+                taps[k] = v.clone()
         h = self._conv("post_quant_conv", f_hat.float(), 1)
         h = self._conv("decoder.conv_in", h, 1)
+        tap("conv_in", h)
         h = self._res("decoder.mid.block_2", self._attn("decoder.mid.attn_1", self._res("decoder.mid.block_1", h)))
+        tap("mid", h)
         nres = len(self.ch_mult)
         for i_level in reversed(range(nres)):
             for i_block in range(self.nrb + 1):
@@ -277,6 +284,7 @@ class RefDecoder:
                     h = self._attn(f"decoder.up.{i_level}.attn.{i_block}", h)
             if i_level != 0:
                 h = self._conv(f"decoder.up.{i_level}.upsample.conv", F.interpolate(h, scale_factor=2, mode="nearest"), 1)
+            tap(f"up.{i_level}", h)
         h = self._conv("decoder.conv_out", F.silu(self._gn("decoder.norm_out", h)), 1)
         return h.clamp_(-1, 1)
 

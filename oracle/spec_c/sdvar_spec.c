@@ -39,9 +39,12 @@ static inline uint32_t fkey(float f) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-/* exp(x) for x <= ~88: Cody-Waite reduction, degree-7 Taylor/Horner in fmaf, exact 2^n scaling */
+/* exp(x) for x <= 0 (softmax numerators): Cody-Waite reduction, degree-7 Taylor/Horner in fmaf, 2^n applied by an integer add
+ * to the exponent field.  Values below 2^-126 are flushed: exp(x) = 0 for x < -87.33 (and for -inf), which keeps every result a
+ * normal float, so the exponent add is exact and the kernels need neither a clamp nor denormal handling. */
+#define SDVAR_EXP_MIN (-87.33f)
 float sdvar_spec_expf(float x) {
-  if (x < -104.0f) return 0.0f; /* also -inf */
+  if (!(x >= SDVAR_EXP_MIN)) return 0.0f; /* also -inf and NaN */
   /* n = rint(x * log2 e) with ONE rounding: the product enters the 1.5 * 2^23 addition unrounded (a fused multiply-add), whose
    * result has ulp 1, so the addition itself rounds to the nearest integer (ties to even).  Stated as an fma on purpose: ptxas
    * contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, so a two-rounding definition could not be kept on the GPU. */
@@ -57,9 +60,9 @@ float sdvar_spec_expf(float x) {
   p = fmaf(p, r, 0.5f);
   p = fmaf(p, r, 1.0f);
   p = fmaf(p, r, 1.0f);
-  /* 2^n in two steps (exact, then rounded once if the result is denormal): identical to one multiplication by 2^n */
-  const int ni = (int)n;
-  return (p * u2f((uint32_t)(ni + 100 + 127) << 23)) * u2f((uint32_t)(-100 + 127) << 23);
+  /* p in [0.70, 1.42], n in [-126, 0]: p * 2^n is normal, so adding n to the exponent field is the exact product.
+   * bits(tm) = 0x4B400000 + n and 0x4B400000 << 23 == 0 (mod 2^32), hence bits(tm) << 23 == n << 23. */
+  return u2f(f2u(p) + (f2u(tm) << 23));
 }
 
 /* canonical sum of term[v] * (pred ? 1 : 0); `keys`==NULL means no predicate */
@@ -238,10 +241,12 @@ int sdvar_spec_verify(const float* xt, const float* xd, const long long* draft_i
       const int acc = (u[row] * qd) < pd;
       long long o = di;
       if (!acc) {
+        /* residual r = max(0, p - q) with p - q = fma(e_t, 1/Z_t, -(e_d * 1/Z_d)); the exponential race argmax r / noise is
+         * run as argmax r * (1 / noise): one IEEE reciprocal and one product per entry (no division chain), lowest index on
+         * ties.  Identically zero residual: the race is run on p itself. */
         int anypos = 0;
         for (int v = 0; v < V; ++v) {
-          const float pv = et[v] * iZt;
-          float rv = pv - ed[v] * iZd;
+          float rv = fmaf(et[v], iZt, -(ed[v] * iZd));
           rv = rv > 0.0f ? rv : 0.0f;
           r[v] = rv;
           anypos |= rv > 0.0f;
@@ -250,7 +255,7 @@ int sdvar_spec_verify(const float* xt, const float* xd, const long long* draft_i
         o = 0;
         for (int v = 0; v < V; ++v) {
           const float num = anypos ? r[v] : et[v] * iZt;
-          const float q = num / noise[row * V + v];
+          const float q = num * (1.0f / noise[row * V + v]);
           if (q > best) { best = q; o = v; }
         }
       }

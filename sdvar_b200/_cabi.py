@@ -20,9 +20,9 @@ MAX_DEPTH = 64
 EPI_F32, EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_QKV = range(5)
 
 EXPORTS = [
-    "sdvar_abi_version", "sdvar_last_error", "sdvar_arch_check", "sdvar_num_sms", "sdvar_launch_count",
+    "sdvar_abi_version", "sdvar_last_error", "sdvar_arch_check", "sdvar_num_sms", "sdvar_launch_count", "sdvar_count_launches",
     "sdvar_sample_cfg_topk_topp", "sdvar_verify_accept_resample", "sdvar_verify_workspace_bytes", "sdvar_verify_top1", "sdvar_vq_next_input", "sdvar_vq_area_down",
-    "sdvar_embed_next_map", "sdvar_first_map", "sdvar_ln_modulate", "sdvar_silu_bf16", "sdvar_f32_to_bf16",
+    "sdvar_embed_next_map", "sdvar_first_map", "sdvar_ln_modulate", "sdvar_silu_bf16", "sdvar_f32_to_bf16", "sdvar_image_to_u8",
     "sdvar_gemm_bf16", "sdvar_attention", "sdvar_var_forward", "sdvar_profile_begin", "sdvar_profile_end",
     "sdvar_groupnorm_silu_nhwc", "sdvar_bias_residual_nhwc", "sdvar_upsample2x_nhwc", "sdvar_vq_nearest_code",
     "sdvar_debug_spec_expf",
@@ -187,6 +187,11 @@ def f32_to_bf16(x, out):
     _check(lib().sdvar_f32_to_bf16(ptr(x), C.c_longlong(x.numel()), ptr(out), stream_ptr()), "sdvar_f32_to_bf16")
 
 
+def image_to_u8(img_B3HW, out, hwc=False):
+    B, _, H, W = img_B3HW.shape
+    _check(lib().sdvar_image_to_u8(ptr(img_B3HW), B, H, W, int(bool(hwc)), ptr(out), stream_ptr()), "sdvar_image_to_u8")
+
+
 def gemm_bf16(A, lda, W, ldw, M, N, K, epi: GemmEpilogue):
     _check(lib().sdvar_gemm_bf16(ptr(A), lda, ptr(W), ldw, M, N, K, C.byref(epi), stream_ptr()), "sdvar_gemm_bf16")
 
@@ -203,12 +208,23 @@ def var_forward(w: VarWeights, p: Pass):
     _check(lib().sdvar_var_forward(C.byref(w), C.byref(p), stream_ptr()), "sdvar_var_forward")
 
 
+PROFILING = False     # while on, engines launch eagerly (the per-family event brackets cannot live inside a CUDA graph)
+
+
+def count_launches(n: int):
+    lib().sdvar_count_launches(C.c_longlong(n))
+
+
 def profile_begin():
+    global PROFILING
     _check(lib().sdvar_profile_begin(), "sdvar_profile_begin")
+    PROFILING = True
 
 
 def profile_end() -> dict:
     """{family: (ms, algorithmic work [FLOP for gemm/attention, bytes otherwise], launches)}"""
+    global PROFILING
+    PROFILING = False
     n = len(PROFILE_FAMILIES)
     ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
     _check(lib().sdvar_profile_end(ms, work, cnt), "sdvar_profile_end")

@@ -95,6 +95,8 @@ extern "C" int sdvar_profile_end(double* ms, double* work, long long* launches) 
 extern "C" int sdvar_abi_version(void) { return SDVAR_ABI_VERSION; }
 extern "C" const char* sdvar_last_error(void) { return sdvar::g_err; }
 extern "C" long long sdvar_launch_count(void) { return sdvar::g_launches.load(); }
+// a replayed CUDA graph launches kernels the library never sees: the host adds the graph's kernel count per replay
+extern "C" void sdvar_count_launches(long long n) { sdvar::g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" int sdvar_arch_check(int device) {
   int major = 0;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) {

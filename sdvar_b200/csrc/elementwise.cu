@@ -111,9 +111,37 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, long long n, __n
     out[i] = __float2bfloat16_rn(x[i]);
 }
 
+// images in [0,1] fp32 (B,3,H,W) -> uint8, as the reference's notebook emits them (`.mul_(255)` ... `.astype(np.uint8)`,
+// sdvar_colab_test.py:235-236: truncation), either in place of layout (B,3,H,W) or as (B,H,W,3) rows for PNG / npz writers
+__global__ void image_to_u8_kernel(const float* __restrict__ img, int B, int HW, int hwc, uint8_t* __restrict__ out) {
+  const long long n = (long long)B * 3 * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = fminf(fmaxf(img[i], 0.0f), 1.0f) * 255.0f;
+    const uint8_t q = (uint8_t)(int)v;
+    if (!hwc) {
+      out[i] = q;
+    } else {
+      const long long b = i / (3LL * HW), r = i - b * 3LL * HW;
+      const int c = (int)(r / HW), p = (int)(r - (long long)c * HW);
+      out[(b * HW + p) * 3 + c] = q;
+    }
+  }
+}
+
 }  // namespace sdvar
 
 using namespace sdvar;
+
+extern "C" int sdvar_image_to_u8(const float* img_B3HW, int B, int H, int W, int hwc, uint8_t* out, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(img_B3HW && out && B > 0 && H > 0 && W > 0, "bad argument");
+  const long long n = (long long)B * 3 * H * W;
+  const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  ProfileScope prof((cudaStream_t)stream, FAM_MISC, (double)n * 5.0);
+  image_to_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img_B3HW, B, H * W, hwc, out);
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
 
 extern "C" int sdvar_ln_modulate(const float* x, int M, int C, int tokens_per_img, const float* scale, const float* shift,
                                  int ld_mod, const int* slot_map, float eps, sdvar_bf16* out, void* stream) {

@@ -8,6 +8,8 @@
 // bisection on the canonical masked mass, the sample an argmax with lowest-index tie break.
 //
 // Reference semantics: models/var.py:199-202, models/helpers.py:6-19; verify: SURVEY.md A7.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sdvar {
@@ -16,16 +18,17 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
 // exp(x) for x <= 0, bit-identical to sdvar_spec_expf.  Branch-free so the 16-32 independent exponentials of a thread
-// interleave: the input is clamped at -104 (the spec returns 0 below it) and the power-of-two scaling is always done in two
-// exact-or-once-rounded steps (2^(n+100) then 2^-100), which rounds identically to a single multiplication by 2^n.
+// interleave: no clamp (anything below -87.33, -inf and NaN included, is replaced by 0 with one select at the end) and the
+// power of two is applied by ONE integer add to the exponent field -- every surviving result is a normal float, so the add is
+// the exact product (round 1 clamped at -104 and multiplied twice to round denormal results like the C spec did).
+constexpr float kExpMin = -87.33f;
 __device__ __forceinline__ float spec_expf(float x) {
-  const float xc = fmaxf(x, -104.0f);
-  // n = rint(xc * log2 e) with one rounding and without the quarter-rate FRND / F2I conversions: the exact product is added to
+  // n = rint(x * log2 e) with one rounding and without the quarter-rate FRND / F2I conversions: the exact product is added to
   // 1.5*2^23 inside one fma (the spec is stated that way), the sum lands in the binade with ulp 1, so the fma itself rounds to
-  // nearest-even; the integer is the mantissa difference
-  const float tm = __fmaf_rn(xc, 1.44269504088896340736f, 12582912.0f);
+  // nearest-even; bits(tm) = 0x4B400000 + n
+  const float tm = __fmaf_rn(x, 1.44269504088896340736f, 12582912.0f);
   const float n = __fsub_rn(tm, 12582912.0f);
-  float r = __fmaf_rn(n, -0.693145751953125f, xc);
+  float r = __fmaf_rn(n, -0.693145751953125f, x);
   r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
   float p = 1.0f / 5040.0f;
   p = __fmaf_rn(p, r, 1.0f / 720.0f);
@@ -35,10 +38,8 @@ __device__ __forceinline__ float spec_expf(float x) {
   p = __fmaf_rn(p, r, 0.5f);
   p = __fmaf_rn(p, r, 1.0f);
   p = __fmaf_rn(p, r, 1.0f);
-  const int ni = __float_as_int(tm) - 0x4B400000;   // in [-151, 0]
-  // no select for x < -104: the clamped value scales to p * 2^-150 < 2^-150 * 1 = half of the smallest subnormal and the second
-  // (once-rounded) multiplication returns exactly 0, which is what the spec returns below -104
-  return __fmul_rn(__fmul_rn(p, u2f((uint32_t)(ni + 100 + 127) << 23)), u2f((uint32_t)(-100 + 127) << 23));
+  const float e = u2f(f2u(p) + (f2u(tm) << 23));      // (0x4B400000 << 23) == 0 mod 2^32: the shift leaves n << 23
+  return (x >= kExpMin) ? e : 0.0f;
 }
 
 // ---- two exponentials at once on the packed fp32x2 pipe (FFMA2 / FADD2 / FMUL2: one issue slot for two IEEE-RN operations, so
@@ -70,7 +71,7 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 __device__ __forceinline__ f32x2 splat2(float c) { return pk2(c, c); }
 // (exp(x0), exp(x1)), both x <= 0 (or -inf); every lane operation is the one spec_expf performs, in the same order
 __device__ __forceinline__ f32x2 spec_expf2(float x0, float x1) {
-  const f32x2 xc = pk2(fmaxf(x0, -104.0f), fmaxf(x1, -104.0f));
+  const f32x2 xc = pk2(x0, x1);
   const f32x2 tm = fma2(xc, splat2(1.44269504088896340736f), splat2(12582912.0f));
   const f32x2 n = add2(tm, splat2(-12582912.0f));
   f32x2 r = fma2(n, splat2(-0.693145751953125f), xc);
@@ -83,11 +84,11 @@ __device__ __forceinline__ f32x2 spec_expf2(float x0, float x1) {
   p = fma2(p, r, splat2(0.5f));
   p = fma2(p, r, splat2(1.0f));
   p = fma2(p, r, splat2(1.0f));
-  float tm0, tm1;
+  float tm0, tm1, p0, p1;
   unpk2(tm, tm0, tm1);
-  const uint32_t s0 = (uint32_t)(__float_as_int(tm0) - 0x4B400000 + 100 + 127) << 23;
-  const uint32_t s1 = (uint32_t)(__float_as_int(tm1) - 0x4B400000 + 100 + 127) << 23;
-  return mul2(mul2(p, pk2(u2f(s0), u2f(s1))), splat2(u2f((uint32_t)(-100 + 127) << 23)));
+  unpk2(p, p0, p1);
+  const float e0 = u2f(f2u(p0) + (f2u(tm0) << 23)), e1 = u2f(f2u(p1) + (f2u(tm1) << 23));
+  return pk2((x0 >= kExpMin) ? e0 : 0.0f, (x1 >= kExpMin) ? e1 : 0.0f);
 }
 
 // IEEE a / b for a >= 0 and b > 0.  ptxas' inline division has a fast path for operands with ordinary exponents and CALLs a
@@ -306,10 +307,10 @@ struct K3Smem {
   float cand[256];
   uint32_t candm[256];
   uint32_t wtot[kWarps];
-  uint32_t zhi[2][kWarps], zlo[2][kWarps];   // two buffers: consecutive sums may have no barrier in between
+  __align__(16) unsigned long long zpart[2][kWarps];   // per-warp fixed-point partial sums (two buffers: consecutive sums may have no barrier in between)
   int bstar;
   uint32_t above;
-  int ncand, n_alive;
+  int ncand, n_list;
   float xK;
   uint32_t tkey, minkey;
   RedSmem red;
@@ -348,43 +349,105 @@ __device__ __forceinline__ void fix_e(float e, uint32_t& hi, uint32_t& lo) {
   hi = (uint32_t)fh;
   lo = __float2uint_rn(__fmul_rn(__fsub_rn(a, fh), 1048576.0f));   // both operations exact; one rounding in the conversion
 }
-// block sum of per-thread limb sums -> u64 total.  One barrier.  (per-thread sums < 2^25, warp sums < 2^30)
+// block sum of per-thread limb sums -> u64 total: two warp reductions, one 64-bit partial per warp, one barrier, then every
+// thread adds the 8 partials (4 LDS.128).  Integer sums: any order gives the same total.  (per-thread sums < 2^25, warp < 2^30)
 __device__ __forceinline__ unsigned long long block_sum_fix(uint32_t hi, uint32_t lo, K3Smem& s, int buf) {
   hi = __reduce_add_sync(0xffffffffu, hi);
   lo = __reduce_add_sync(0xffffffffu, lo);
-  const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { s.zhi[buf][w] = hi; s.zlo[buf][w] = lo; }
+  if ((threadIdx.x & 31) == 0) s.zpart[buf][threadIdx.x >> 5] = ((unsigned long long)hi << 20) + (unsigned long long)lo;
   __syncthreads();
+  const ulonglong2* z2 = reinterpret_cast<const ulonglong2*>(s.zpart[buf]);
   unsigned long long t = 0;
 #pragma unroll
-  for (int k = 0; k < kWarps; ++k) t += ((unsigned long long)s.zhi[buf][k] << 20) + (unsigned long long)s.zlo[buf][k];
+  for (int k = 0; k < kWarps / 2; ++k) { const ulonglong2 v = z2[k]; t += v.x + v.y; }
   return t;
 }
 
-// ---- the part of the filtered path that works on the compacted survivor list; QR = list entries per thread (n <= 256 * QR)
+// value-space bin of x: floor(x * scale + off) with off = 0.5 - lo * scale; for lo <= x <= hi the fused multiply-add stays
+// inside (0, 512) as long as |lo| * scale < 2^18 (checked by the caller), so no clamp is needed.  Monotone in x.
+__device__ __forceinline__ int vbin(float x, float scale, float off) { return __float2int_rd(__fmaf_rn(x, scale, off)); }
+
+// ---- the part of the filtered path that works on the compacted list; QR = list entries per thread (n <= 256 * QR).
+// The list holds every entry whose top-k bin is >= the crossing bin: all survivors plus the few candidates below the exact
+// cut, which are dropped here (they contribute nothing once xK is known).
 template <int QR>
-__device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float* lx, const float* ln, const uint16_t* li, int n, float m,
-                                        float xK, float thr, bool sample, float& xB, bool& strictB, bool& all_but_max,
-                                        long long orow, long long* idx_out, float* prob_out) {
+__device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float2* lxn, const uint16_t* li, int n, float m, float xmin,
+                                        bool use_k, int top_k, bool hist_k, float kscale, float koff, float thr, bool sample,
+                                        float& xK_out, float& xlow, bool& incl, long long orow, long long* idx_out, float* prob_out) {
   const int tid = threadIdx.x;
+  float xv[QR], nzv[QR];
+#pragma unroll
+  for (int q = 0; q < QR; ++q) {
+    const int i = q * kThreads + tid;
+    const float2 t = i < n ? lxn[i] : make_float2(-INFINITY, 1.0f);
+    xv[q] = t.x; nzv[q] = t.y;
+  }
+  // ---- exact k-th largest value among the candidates of the crossing bin ----
+  float xK = xmin;
+  if (use_k && hist_k) {
+    const int bst = s.bstar;
+    const uint32_t above = s.above;
+#pragma unroll
+    for (int q = 0; q < QR; ++q)
+      if (q * kThreads + tid < n && vbin(xv[q], kscale, koff) == bst) {
+        const int p = atomicAdd(&s.ncand, 1);
+        if (p < 256) s.cand[p] = xv[q];
+      }
+    __syncthreads();
+    const int nc = s.ncand;
+    if (nc <= 256) {
+      if (tid < nc) {
+        const float xi = s.cand[tid];
+        uint32_t g = 0, ge = 0;
+        for (int jj = 0; jj < nc; ++jj) { const float xj = s.cand[jj]; g += xj > xi; ge += xj >= xi; }
+        const uint32_t kk = (uint32_t)top_k - above;
+        if (g < kk && kk <= ge) s.xK = xi;
+      }
+      __syncthreads();
+      xK = s.xK;
+    } else {
+      // fall-back: bisection over the candidates' keys (all other list entries are above the bin and count as `above`)
+      uint32_t lo = 0u, hi = 0xFFFFFFFFu;      // invariant: #{cand key >= lo} >= kk, #{cand key >= hi} < kk  (hi exclusive top)
+      const int kk = top_k - (int)above;
+      uint32_t key[QR];
+#pragma unroll
+      for (int q = 0; q < QR; ++q)
+        key[q] = (q * kThreads + tid < n && vbin(xv[q], kscale, koff) == bst) ? fkey(__fadd_rn(xv[q], 0.0f)) : 0u;   // 0: below every real key
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t tr = lo | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < QR; ++q) c += (key[q] >= tr) ? 1 : 0;
+        c = block_sum_int(c, s.red, slot);
+        if (c >= kk) lo = tr;
+      }
+      (void)hi;
+      xK = fkey_inv(lo);
+    }
+    if (tid == 0) s.ncand = 0;      // next use is behind at least one barrier
+  } else if (use_k) {
+    xK = s.xK;                        // found by the caller's fall-back
+  }
+  xK_out = xK;
+  // ---- exponentials of the survivors; dropped candidates get exp(-inf) = 0 and vanish from every sum ----
   float ev[QR];
   uint32_t hi = 0, lo = 0;
 #pragma unroll
   for (int q = 0; q < QR; q += 2) {
-    const int i0 = q * kThreads + tid, i1 = i0 + kThreads;
-    const float x0 = i0 < n ? __fsub_rn(lx[i0], m) : -INFINITY;
-    const float x1 = (q + 1 < QR && i1 < n) ? __fsub_rn(lx[i1], m) : -INFINITY;
+    const float x0 = (xv[q] >= xK) ? __fsub_rn(xv[q], m) : -INFINITY;
+    const float x1 = (q + 1 < QR && xv[q + 1] >= xK) ? __fsub_rn(xv[q + 1], m) : -INFINITY;
     float e0, e1;
     unpk2(spec_expf2(x0, x1), e0, e1);
     ev[q] = e0;
     if (q + 1 < QR) ev[q + 1] = e1;
     uint32_t h, l;
     fix_e(e0, h, l); hi += h; lo += l;
-    fix_e(e1, h, l); hi += h; lo += l;        // e1 == 0 when the slot does not exist
+    fix_e(e1, h, l); hi += h; lo += l;
   }
   const unsigned long long Zi = block_sum_fix(hi, lo, s, 0);
   unsigned long long Z2i = Zi;
-  xB = -INFINITY; strictB = true; all_but_max = false;      // "x < -inf": nothing removed
+  xlow = xK; incl = true;            // keep <=> x >= xK
   if (thr >= 0.0f) {
     const float Z = __fmul_rn(__ull2float_rn(Zi), 1.0f / kFixE);
     const uint32_t thr_i = (uint32_t)__fmul_rn(thr, kFixM);
@@ -392,13 +455,14 @@ __device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float* lx, c
     uint32_t mass[QR];
 #pragma unroll
     for (int q = 0; q < QR; ++q) mass[q] = ev[q] > 0.0f ? __float2uint_rn(__fmul_rn(__fdiv_rn(ev[q], Z), kFixM)) : 0u;
-    if (range > 0.0f && range < INFINITY) {
+    bool all_but_max = false, have = false;
+    float xB = -INFINITY;
+    bool strictB = true;
+    if (range > 0.0f && range < INFINITY && __fmul_rn(fabsf(xK), __fdiv_rn(511.0f, range)) < 262144.0f) {
       const float scale = __fdiv_rn(511.0f, range), off = __fmaf_rn(-xK, scale, 0.5f);
 #pragma unroll
-      for (int q = 0; q < QR; ++q) {
-        const int i = q * kThreads + tid;
-        if (i < n) atomicAdd(&s.hist[min(max(__float2int_rd(__fmaf_rn(lx[i], scale, off)), 0), kBins - 1)], mass[q]);
-      }
+      for (int q = 0; q < QR; ++q)
+        if (xv[q] >= xK) atomicAdd(&s.hist[vbin(xv[q], scale, off)], mass[q]);
       __syncthreads();
       // ascending scan of the bin masses: the crossing bin is the first whose inclusive cumulation exceeds thr_i
       const uint32_t m0 = s.hist[2 * tid], m1 = s.hist[2 * tid + 1];
@@ -415,13 +479,11 @@ __device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float* lx, c
         const int bst = s.bstar;
         const uint32_t below = s.above;
 #pragma unroll
-        for (int q = 0; q < QR; ++q) {
-          const int i = q * kThreads + tid;
-          if (i < n && min(max(__float2int_rd(__fmaf_rn(lx[i], scale, off)), 0), kBins - 1) == bst) {
+        for (int q = 0; q < QR; ++q)
+          if (xv[q] >= xK && vbin(xv[q], scale, off) == bst) {
             const int p = atomicAdd(&s.ncand, 1);
-            if (p < 256) { s.cand[p] = lx[i]; s.candm[p] = mass[q]; }
+            if (p < 256) { s.cand[p] = xv[q]; s.candm[p] = mass[q]; }
           }
-        }
         __syncthreads();
         const int nc = s.ncand;
         if (nc <= 256) {
@@ -437,39 +499,42 @@ __device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float* lx, c
           const uint32_t tk = s.tkey;
           strictB = tk == 0u;
           xB = fkey_inv(strictB ? s.minkey : tk);
-        } else {
-          // fall-back (a crossing bin with > 256 entries): bit-serial search of the largest key T with mass{key <= T} <= thr_i
-          uint32_t T = 0;
-#pragma unroll 1
-          for (int bit = 31; bit >= 0; --bit) {
-            const uint32_t tr = T | (1u << bit);
-            int a = 0;
-#pragma unroll
-            for (int q = 0; q < QR; ++q) {
-              const int i = q * kThreads + tid;
-              if (i < n && fkey(__fadd_rn(lx[i], 0.0f)) <= tr) a += (int)mass[q];
-            }
-            a = block_sum_int(a, s.red, slot);      // masses sum to ~2^30: fits an int
-            if ((uint32_t)a <= thr_i) T = tr;
-          }
-          strictB = false;
-          xB = T ? fkey_inv(T) : -INFINITY;
-          if (T == 0u) strictB = true;
+          have = true;
         }
       }
+    } else if (range > 0.0f || !(range == 0.0f)) {
+      have = false;                            // degenerate value range: bit-serial search below
+    } else {
+      have = true;                             // every survivor equals the maximum: one tie group holding the max, nothing removed
     }
-    // survivors' fixed-point sum
+    if (!all_but_max && !have) {
+      // fall-back (crossing bin with > 256 entries, or a value range the histogram cannot bin): bit-serial search of the
+      // largest key T with mass{key <= T} <= thr_i over the survivors
+      uint32_t T = 0;
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t tr = T | (1u << bit);
+        int a = 0;
+#pragma unroll
+        for (int q = 0; q < QR; ++q)
+          if (xv[q] >= xK && fkey(__fadd_rn(xv[q], 0.0f)) <= tr) a += (int)mass[q];
+        a = block_sum_int(a, s.red, slot);      // masses sum to ~2^30: fits an int
+        if ((uint32_t)a <= thr_i) T = tr;
+      }
+      strictB = T == 0u;
+      xB = T ? fkey_inv(T) : -INFINITY;
+    }
+    // one threshold for everything below: keep <=> incl ? x >= xlow : x > xlow  (the row maximum always satisfies it)
+    if (all_but_max) { xlow = m; incl = true; }
+    else if (strictB) { if (xB > xK) { xlow = xB; incl = true; } }        // removed <=> x < xB
+    else if (xB >= xK) { xlow = xB; incl = false; }                         // removed <=> x <= xB
     hi = 0; lo = 0;
 #pragma unroll
     for (int q = 0; q < QR; ++q) {
-      const int i = q * kThreads + tid;
-      if (i < n) {
-        const float xv = lx[i];
-        const bool rem = all_but_max ? (xv != m) : ((strictB ? xv < xB : xv <= xB) && xv != m);
-        if (rem) ev[q] = 0.0f;
-        uint32_t h, l;
-        fix_e(ev[q], h, l); hi += h; lo += l;
-      }
+      const bool keep = incl ? (xv[q] >= xlow) : (xv[q] > xlow);
+      if (!keep) ev[q] = 0.0f;
+      uint32_t h, l;
+      fix_e(ev[q], h, l); hi += h; lo += l;
     }
     if (sample) Z2i = block_sum_fix(hi, lo, s, 1);
   }
@@ -479,11 +544,10 @@ __device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float* lx, c
   int bi = 0x7FFFFFFF;
 #pragma unroll
   for (int q = 0; q < QR; ++q) {
-    const int i = q * kThreads + tid;
-    if (i < n && ev[q] > 0.0f) {
+    if (ev[q] > 0.0f) {
       const float pv = __fdiv_rn(ev[q], Z2);
-      const float r = __fdiv_rn(pv, ln[i]);
-      const int v = (int)li[i];
+      const float r = __fdiv_rn(pv, nzv[q]);
+      const int v = (int)li[q * kThreads + tid];
       if (r > best || (r == best && v < bi)) { best = r; bi = v; bestp = pv; }
     }
   }
@@ -496,29 +560,40 @@ __device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float* lx, c
   }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(kThreads, 4)
+// long lists (top-p without top-k, huge tie groups): kept out of line so that its 4*E-register working set does not
+// inflate the register allocation of the common path
+template <int E>
+__device__ __noinline__ void k3_tail_long(K3Smem& s, int& slot, const float2* lxn, const uint16_t* li, int n, float m, float xmin,
+                                          bool use_k, int top_k, bool hist_k, float kscale, float koff, float thr, bool sample,
+                                          float& xK_out, float& xlow, bool& incl, long long orow, long long* idx_out, float* prob_out) {
+  k3_tail<E>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, xK_out, xlow, incl, orow, idx_out, prob_out);
+}
+
+template <int NV, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC)
 k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int in_off, int out_ld, int out_off, SegTable seg,
                    int top_k, float thr, const float* __restrict__ noise, long long* __restrict__ idx_out,
                    float* __restrict__ mixed_out, float* __restrict__ prob_out) {
   constexpr int V = NV * 1024;
   constexpr int E = NV * 4;
-  constexpr int QF = E < 6 ? E : 6;     // fast tail: up to 1536 survivors
+  constexpr int QF = E < 6 ? E : 6;     // fast tail: lists of up to 1536 entries
   extern __shared__ __align__(16) unsigned char k3_dyn[];
-  float* lx = reinterpret_cast<float*>(k3_dyn);            // [V] survivor logits
-  float* ln = lx + V;                                      // [V] their noise
-  uint16_t* li = reinterpret_cast<uint16_t*>(ln + V);      // [V] their vocabulary index
+  float2* lxn = reinterpret_cast<float2*>(k3_dyn);           // [V] (logit, noise) of the listed entries
+  uint16_t* li = reinterpret_cast<uint16_t*>(lxn + V);       // [V] their vocabulary index
   __shared__ K3Smem s;
   int slot = 0;
   const int tid = threadIdx.x, lane = tid & 31;
   const long long rows = (long long)B * L;
   for (int i = tid; i < kBins; i += kThreads) s.hist[i] = 0;
-  if (tid == 0) { s.ncand = 0; s.n_alive = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; }
+  if (tid == 0) { s.ncand = 0; s.n_list = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; }
   __syncthreads();
   const bool sample = noise != nullptr;
   const bool use_k = top_k > 0 && top_k < V;
+  const bool small = rows < 0x7FFFFFFFLL;
   for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int b = (int)(row / L), pos = (int)(row - (long long)b * L);
+    int b, pos;
+    if (small) { b = (int)((uint32_t)row / (uint32_t)L); pos = (int)((uint32_t)row - (uint32_t)b * (uint32_t)L); }
+    else { b = (int)(row / L); pos = (int)(row - (long long)b * L); }
     const int j = seg_of(seg, pos);
     const float t1 = seg.t1[j], t2 = seg.t2[j];
     const long long orow = (long long)b * out_ld + out_off + pos;
@@ -537,12 +612,6 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
         x[4 * i + 3] = __fsub_rn(__fmul_rn(a[i].w, t1), __fmul_rn(c[i].w, t2));
       }
     }
-    float4 nz[NV];
-    if (sample) {
-      const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) nz[i] = ldg_stream(pn + i * kThreads + tid);
-    }
     // ---- row max / min ----
     float mx = -INFINITY, mn = INFINITY;
 #pragma unroll
@@ -551,15 +620,28 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
     block_max_u32x2(kmx, kmnc, s.red, slot);
     const float m = fkey_inv(kmx), xmin = fkey_inv(~kmnc);
 
-    // ---- top-k: xK = k-th largest value (alive <=> x >= xK) ----
-    float xK = xmin;
+    // ---- top-k, coarse: histogram of the value-space bins, suffix scan -> crossing bin b* (exact cut: in the tail) ----
+    bool hist_k = false;
+    float kscale = 0.0f, koff = 0.0f, xcut = xmin;      // list <=> vbin(x) >= b*  (hist) or x >= xcut (fall-back / no top-k)
+    int bst = 0;
     if (use_k) {
       const float range = __fsub_rn(m, xmin);
-      bool done = false;
-      if (range > 0.0f && range < INFINITY) {
-        const float scale = __fdiv_rn(511.0f, range), off = __fmaf_rn(-xmin, scale, 0.5f);
+      if (range > 0.0f && range < INFINITY && __fmul_rn(fabsf(xmin), __fdiv_rn(511.0f, range)) < 262144.0f) {
+        hist_k = true;
+        kscale = __fdiv_rn(511.0f, range);
+        koff = __fmaf_rn(-xmin, kscale, 0.5f);
 #pragma unroll
-        for (int e = 0; e < E; ++e) atomicAdd(&s.hist[min(max(__float2int_rd(__fmaf_rn(x[e], scale, off)), 0), kBins - 1)], 1u);
+        for (int e = 0; e < E; ++e) atomicAdd(&s.hist[vbin(x[e], kscale, koff)], 1u);
+      }
+    }
+    float4 nz[NV];
+    if (sample) {      // issued here so that the latency overlaps the scan
+      const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) nz[i] = ldg_stream(pn + i * kThreads + tid);
+    }
+    if (use_k) {
+      if (hist_k) {
         __syncthreads();
         // suffix scan: thread t owns bins 511-2t (first) and 510-2t
         const uint32_t c0 = s.hist[kBins - 1 - 2 * tid], c1 = s.hist[kBins - 2 - 2 * tid];
@@ -571,31 +653,8 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
         if (before < k && k <= before + c0) { s.bstar = kBins - 1 - 2 * tid; s.above = before; }
         else if (before + c0 < k && k <= inc) { s.bstar = kBins - 2 - 2 * tid; s.above = before + c0; }
         __syncthreads();
-        const int bst = s.bstar;
-        const uint32_t above = s.above;
-#pragma unroll
-        for (int e = 0; e < E; ++e)
-          if (min(max(__float2int_rd(__fmaf_rn(x[e], scale, off)), 0), kBins - 1) == bst) {
-            const int p = atomicAdd(&s.ncand, 1);
-            if (p < 256) s.cand[p] = x[e];
-          }
-        __syncthreads();
-        const int nc = s.ncand;
-        if (nc <= 256) {
-          if (tid < nc) {
-            const float xi = s.cand[tid];
-            uint32_t g = 0, ge = 0;
-            for (int jj = 0; jj < nc; ++jj) { const float xj = s.cand[jj]; g += xj > xi; ge += xj >= xi; }
-            const uint32_t kk = k - above;
-            if (g < kk && kk <= ge) s.xK = xi;
-          }
-          __syncthreads();
-          xK = s.xK;
-          done = true;
-        }
-        if (tid == 0) s.ncand = 0;      // next use is behind at least one barrier
-      }
-      if (!done) {
+        bst = s.bstar;
+      } else {
         // fall-back: bisection on the order-preserving keys (round-1 algorithm), any input
         uint32_t key[E];
 #pragma unroll
@@ -619,18 +678,23 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
           block_max_u32x2(mnk, z, s.red, slot);
           K = ~mnk;
         }
-        xK = fkey_inv(K);
+        xcut = fkey_inv(K);
+        if (tid == 0) s.xK = xcut;
       }
     }
 
-    // ---- compact the survivors (any order: every later sum is an integer sum) ----
+    // ---- compact the listed entries (any order: every later sum is an integer sum) ----
     {
+      bool in[E];
       uint32_t cnt = 0;
 #pragma unroll
-      for (int e = 0; e < E; ++e) cnt += (x[e] >= xK) ? 1u : 0u;
+      for (int e = 0; e < E; ++e) {
+        in[e] = hist_k ? (vbin(x[e], kscale, koff) >= bst) : (x[e] >= xcut);
+        cnt += in[e] ? 1u : 0u;
+      }
       const uint32_t inc = warp_incl_scan(cnt);
       int base = 0;
-      if (lane == 31) base = atomicAdd(&s.n_alive, (int)inc);
+      if (lane == 31) base = atomicAdd(&s.n_list, (int)inc);
       base = __shfl_sync(0xffffffffu, base, 31);
       int p = base + (int)(inc - cnt);
 #pragma unroll
@@ -638,78 +702,54 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
         const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (x[4 * i + c] >= xK) {
-            lx[p] = x[4 * i + c];
+          if (in[4 * i + c]) {
+            lxn[p] = make_float2(x[4 * i + c], sample ? nn[c] : 1.0f);
             li[p] = (uint16_t)(4 * (i * kThreads + tid) + c);
-            if (sample) ln[p] = nn[c];
             ++p;
           }
       }
     }
     __syncthreads();
-    const int n = s.n_alive;
-    float xB;
-    bool strictB, all_but_max;
-    if (n <= QF * kThreads) k3_tail<QF>(s, slot, lx, ln, li, n, m, xK, thr, sample, xB, strictB, all_but_max, orow, idx_out, prob_out);
-    else k3_tail<E>(s, slot, lx, ln, li, n, m, xK, thr, sample, xB, strictB, all_but_max, orow, idx_out, prob_out);
+    const int n = s.n_list;
+    float xK, xlow;
+    bool incl;
+    if (n <= QF * kThreads)
+      k3_tail<QF>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, xK, xlow, incl, orow, idx_out, prob_out);
+    else
+      k3_tail_long<E>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, xK, xlow, incl, orow, idx_out, prob_out);
 
     if (mixed_out != nullptr) {
       float4* po = reinterpret_cast<float4*>(mixed_out + orow * V);
+      if (incl) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        float o[4];
+        for (int i = 0; i < NV; ++i)
+          stg_stream(po + i * kThreads + tid, make_float4(x[4 * i] >= xlow ? x[4 * i] : -INFINITY, x[4 * i + 1] >= xlow ? x[4 * i + 1] : -INFINITY,
+                                                           x[4 * i + 2] >= xlow ? x[4 * i + 2] : -INFINITY, x[4 * i + 3] >= xlow ? x[4 * i + 3] : -INFINITY));
+      } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float xv = x[4 * i + c];
-          const bool rem = all_but_max ? (xv != m) : ((strictB ? xv < xB : xv <= xB) && xv != m);
-          o[c] = (xv >= xK && !rem) ? xv : -INFINITY;
-        }
-        stg_stream(po + i * kThreads + tid, make_float4(o[0], o[1], o[2], o[3]));
+        for (int i = 0; i < NV; ++i)
+          stg_stream(po + i * kThreads + tid, make_float4(x[4 * i] > xlow ? x[4 * i] : -INFINITY, x[4 * i + 1] > xlow ? x[4 * i + 1] : -INFINITY,
+                                                           x[4 * i + 2] > xlow ? x[4 * i + 2] : -INFINITY, x[4 * i + 3] > xlow ? x[4 * i + 3] : -INFINITY));
       }
     }
     __syncthreads();      // every thread is past its last read of the row's shared state
-    if (tid == 0) { s.ncand = 0; s.n_alive = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; }
+    if (tid == 0) { s.ncand = 0; s.n_list = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; }
   }
 }
 
 // ================================================================================================
 // K4
 // ================================================================================================
-// K4 v3.  One CTA per token row; the two logit rows of a token (2 x V fp32 = 32 KiB) are staged in shared memory by 1-D bulk
-// TMA copies (cp.async.bulk + mbarrier) into a 2-stage ring.  Each thread moves its 2 x 4NV values into REGISTERS in the
-// max pass; after the block-wide max reduction (a barrier every thread passes only after its last shared-memory read of the
-// stage) the stage is refilled with the row TWO iterations ahead, so ~1.7 rows per CTA are always in flight.  Exponentials
-// replace the logits in the registers: nothing is written back to shared memory (v2 stored them for the owner's lookup and
-// for the reject path: 8 STS.128 + 8 LDS.128 per thread-row and a generic->async proxy hazard on the refill).  The owner of
+// K4 v4.  One 256-thread CTA per token row, four CTAs per SM.  Each thread streams its 2 x 4NV values of the two logit
+// rows straight into REGISTERS with 128-bit no-allocate loads (the layout K3 uses, which runs at 0.8-0.99 of HBM): no
+// shared-memory staging, so occupancy is bounded by registers only and four independent rows per SM hide each other's
+// load and reduction latency.  (v2/v3 staged the rows through a bulk-TMA shared-memory ring -- 64 KiB per CTA, three CTAs
+// per SM -- and v2 additionally wrote the exponentials back to shared memory; v3's profile showed the kernel waiting on the
+// ring and on barriers with the issue slots 55 % busy.)  Exponentials replace the logits in the registers; the owner of
 // element d picks its two exponentials with a select chain (one warp pays); a rejected row resamples straight from the
-// registers.  Per-(image, stage) counters are integer atomics into the caller's zeroed workspace, copied out and re-zeroed by
-// the last CTA, so the launch needs no init kernel.  Arithmetic and reduction order are those of oracle/spec_c:
+// registers.  Per-(image, stage) counters are integer atomics into the caller's zeroed workspace, copied out and re-zeroed
+// by the last CTA, so the launch needs no init kernel.  Arithmetic and reduction order are those of oracle/spec_c:
 // sdvar_spec_verify, bit for bit.
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_init1(uint64_t* bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_par(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "K4_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra K4_DONE;\n"
-      "bra K4_WAIT;\n"
-      "K4_DONE:\n"
-      "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
-      "r"(parity)
-      : "memory");
-}
 
 // u / noise row of token (b, pos): dense (b*L + pos), or "stage-major" = the concatenation over stages j of (B*l_j) blocks,
 // i.e. exactly the tensors a caller draws stage by stage ((B*l_j, V) each) laid end to end
@@ -720,17 +760,13 @@ __device__ __forceinline__ long long aux_row(int stage_major, int B, int L, cons
 }
 
 template <int NV>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, NV <= 4 ? 4 : 2)
 k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, const long long* __restrict__ draft_idx,
                  const float* __restrict__ u, const float* __restrict__ noise, int stage_major, int B, int L, SegTable seg,
                  long long* __restrict__ out_idx, unsigned char* __restrict__ accept, float* __restrict__ p_d_out,
                  float* __restrict__ q_d_out, int* __restrict__ first_reject, int* __restrict__ n_accept,
                  int* __restrict__ accepted_stages, int* __restrict__ summary, int* ws) {
   constexpr int V = NV * 1024;
-  constexpr int E = NV * 4;
-  extern __shared__ __align__(128) unsigned char k4_smem[];
-  float* stage_buf = reinterpret_cast<float*>(k4_smem);                    // [2][2][V]
-  uint64_t* full = reinterpret_cast<uint64_t*>(k4_smem + 2 * 2 * V * 4);   // [2]
   __shared__ RedSmem sm;
   __shared__ int s_last;
   int slot = 0;
@@ -738,52 +774,26 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
   const long long rows = (long long)B * L;
   int* ws_acc = ws + 4;               // [B*S] accepted tokens per (image, stage)
   int* ws_fr = ws + 4 + B * seg.S;    // [B*S] max over rejected tokens of (l_j - position): 0 = no reject
-  if (tid == 0) {
-    mbar_init1(&full[0]);
-    mbar_init1(&full[1]);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-    for (int k0 = 0; k0 < 2; ++k0) {
-      const long long r0 = (long long)blockIdx.x + (long long)k0 * gridDim.x;
-      if (r0 < rows) {
-        mbar_expect(&full[k0], 2 * V * 4);
-        bulk_g2s(stage_buf + k0 * 2 * V, xt + r0 * V, V * 4, &full[k0]);
-        bulk_g2s(stage_buf + k0 * 2 * V + V, xd + r0 * V, V * 4, &full[k0]);
-      }
-    }
-  }
-  __syncthreads();
-  uint32_t k = 0;
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x, ++k) {
-    const uint32_t st = k & 1;
-    const int d = (int)draft_idx[row];
-    mbar_wait_par(&full[st], (k >> 1) & 1);
-    const float4* st4 = reinterpret_cast<const float4*>(stage_buf + st * 2 * V);
-    const float4* sd4 = st4 + V / 4;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float4* pt = reinterpret_cast<const float4*>(xt + row * V);
+    const float4* pd = reinterpret_cast<const float4*>(xd + row * V);
     // pass 1: values to registers, row maxima (order-independent)
     float4 a[NV], c[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { a[i] = ldg_stream(pt + i * kThreads + tid); c[i] = ldg_stream(pd + i * kThreads + tid); }
+    const int d = (int)draft_idx[row];
     float mt = -INFINITY, md = -INFINITY;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      a[i] = st4[i * kThreads + tid];
-      c[i] = sd4[i * kThreads + tid];
       mt = fmaxf(fmaxf(mt, fmaxf(a[i].x, a[i].y)), fmaxf(a[i].z, a[i].w));
       md = fmaxf(fmaxf(md, fmaxf(c[i].x, c[i].y)), fmaxf(c[i].z, c[i].w));
     }
     uint32_t kt = fkey(mt), kd = fkey(md);
-    block_max_u32x2(kt, kd, sm, slot);      // barrier: every thread has read its part of stage st
+    block_max_u32x2(kt, kd, sm, slot);
     mt = fkey_inv(kt);
     md = fkey_inv(kd);
-    {
-      const long long nrow = row + 2LL * gridDim.x;
-      if (tid == 0 && nrow < rows) {        // refill the stage just drained with the row two iterations ahead
-        mbar_expect(&full[st], 2 * V * 4);
-        bulk_g2s(stage_buf + st * 2 * V, xt + nrow * V, V * 4, &full[st]);
-        bulk_g2s(stage_buf + st * 2 * V + V, xd + nrow * V, V * 4, &full[st]);
-      }
-    }
     // pass 2: exponentials in place (registers), canonical sums: scalar adds in element order, packed exponentials on the
-    // register pairs LDS.128 delivered
+    // register pairs the 128-bit loads delivered
     float zt = 0.0f, zd = 0.0f;
     const f32x2 nmt = pk2(-mt, -mt), nmd = pk2(-md, -md);    // a - m == a + (-m) exactly
 #pragma unroll
@@ -846,9 +856,9 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
         const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float r1 = __fsub_rn(__fmul_rn(av[q], izt), __fmul_rn(cv[q], izd));
+          float r1 = __fmaf_rn(av[q], izt, -__fmul_rn(cv[q], izd));
           r1 = r1 > 0.0f ? r1 : 0.0f;
-          const float r = fdiv_nz(r1, nn[q]);
+          const float r = __fmul_rn(r1, __frcp_rn(nn[q]));
           if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + q; }
         }
       }
@@ -865,7 +875,7 @@ k4_verify_kernel(const float* __restrict__ xt, const float* __restrict__ xd, con
           const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float r = fdiv_nz(__fmul_rn(av[q], izt), nn[q]);
+            const float r = __fmul_rn(__fmul_rn(av[q], izt), __frcp_rn(nn[q]));
             if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + q; }
           }
         }
@@ -992,12 +1002,17 @@ extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L
   cudaStream_t st = (cudaStream_t)stream;
   ProfileScope prof(st, FAM_SAMPLE, (double)rows * (8.0 * V + (noise ? 4.0 * V + 8.0 : 0.0) + (mixed_out ? 4.0 * V : 0.0)));
   const bool filtered = (top_k > 0 && top_k < V) || one_minus_top_p >= 0.0f;
-  const size_t dyn = (size_t)V * 10;      // survivor list: logit + noise (fp32) + vocabulary index (u16)
+  static const int occ = [] { const char* e = getenv("SDVAR_K3_OCC"); return e && atoi(e) == 4 ? 4 : 3; }();   // CTAs per SM (A/B switch)
+  const size_t dyn = (size_t)V * 10;      // list: (logit, noise) fp32 pairs + vocabulary index (u16)
 #define SDVAR_K3(NV)                                                                                                        \
   case NV:                                                                                                                  \
-    if (filtered) {                                                                                                         \
-      SDVAR_SET_SMEM_ONCE(k3_filtered_kernel<NV>, dyn);                                                                     \
-      k3_filtered_kernel<NV><<<grid, kThreads, dyn, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, top_k,    \
+    if (filtered && occ == 3) {                                                                                             \
+      SDVAR_SET_SMEM_ONCE((k3_filtered_kernel<NV, 3>), dyn);                                                                \
+      k3_filtered_kernel<NV, 3><<<row_grid(rows, 3), kThreads, dyn, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, top_k, \
+                                                          one_minus_top_p, noise, idx_out, mixed_out, prob_out);           \
+    } else if (filtered) {                                                                                                  \
+      SDVAR_SET_SMEM_ONCE((k3_filtered_kernel<NV, 4>), dyn);                                                                \
+      k3_filtered_kernel<NV, 4><<<grid, kThreads, dyn, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, top_k, \
                                                           one_minus_top_p, noise, idx_out, mixed_out, prob_out);           \
     } else {                                                                                                                \
       k3_plain_kernel<NV><<<grid, kThreads, 0, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, noise, idx_out, \
@@ -1036,14 +1051,10 @@ extern "C" int sdvar_verify_accept_resample(const float* xt, const float* xd, co
   if (int rc = fill_seg(seg, seg_begin_host, S, L, nullptr, nullptr)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   ProfileScope prof(st, FAM_VERIFY, (double)B * L * (8.0 * V + 17.0));
-  const size_t k4_smem = (size_t)2 * 2 * V * 4 + 64;          // two stages x (target row + draft row) + mbarriers
-  const int per_sm = (int)((220 * 1024) / (k4_smem + 1024)) < 3 ? (int)((220 * 1024) / (k4_smem + 1024)) : 3;
-  SDVAR_REQUIRE(per_sm >= 1, "V=%d rows do not fit the shared-memory ring", V);
-  const int grid = row_grid((long long)B * L, per_sm);
+  const int grid = row_grid((long long)B * L, V <= 4096 ? 4 : 2);
 #define SDVAR_K4(NV)                                                                                                 \
   case NV: {                                                                                                         \
-    SDVAR_SET_SMEM_ONCE(k4_verify_kernel<NV>, k4_smem);                                                              \
-    k4_verify_kernel<NV><<<grid, kThreads, k4_smem, st>>>(xt, xd, draft_idx, u, noise, stage_major_aux, B, L, seg, out_idx, \
+    k4_verify_kernel<NV><<<grid, kThreads, 0, st>>>(xt, xd, draft_idx, u, noise, stage_major_aux, B, L, seg, out_idx, \
                                                           accept, p_d_out, q_d_out, first_reject, n_accept,         \
                                                           accepted_stages, summary, workspace);                     \
   } break;

@@ -17,6 +17,7 @@ Layout in HBM (per model, batch B, imgs = 2B for CFG):
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -30,6 +31,10 @@ class VarEngine:
         self._packed_key = None
         self._ws_key = None
         self.kv_len = 0
+        # stage-level CUDA graphs: a dense pass over given stages at a given cache position always
+        # launches the same kernels on the same buffers, so it is captured on its second use and replayed afterwards
+        self.use_graphs = os.environ.get("SDVAR_GRAPHS", "1") != "0"
+        self._graphs, self._graph_seen = {}, {}
 
     # ------------------------------------------------------------------ weights
     def _key(self):
@@ -113,6 +118,7 @@ class VarEngine:
             self.ada_shared = z(imgs, 6 * C, dt=torch.float32) if m.shared_aln else None
             self.head_mod = z(imgs, 2 * C, dt=torch.float32)
             self._ws_key = key
+            self._graphs, self._graph_seen = {}, {}      # the captured passes point at the old buffers
         self.B, self.imgs, self.Lq_max = B, imgs, Lq_max
         self.kv_len = 0
         self._slot_keep = []      # slot maps of the sub-batch passes in flight (kept alive until the next begin())
@@ -190,7 +196,23 @@ class VarEngine:
             p.vT_cache[i] = self.v_cache[i].data_ptr()
         p.xm, p.q, p.attn, p.hidden = self.xm.data_ptr(), self.q.data_ptr(), self.attn.data_ptr(), self.hidden.data_ptr()
         p.logits = self.logits.data_ptr() if want_logits else 0
-        _cabi.var_forward(self.weights, p)
+        gkey = (tuple(stages), kv_off, bool(want_logits), self._packed_key)
+        if slot_map is not None or not self.use_graphs or _cabi.PROFILING or torch.cuda.is_current_stream_capturing():
+            _cabi.var_forward(self.weights, p)
+        elif gkey in self._graphs:
+            g, n_launch = self._graphs[gkey]
+            g.replay()
+            _cabi.count_launches(n_launch)
+        elif self._graph_seen.get(gkey, 0) == 0:
+            self._graph_seen[gkey] = 1
+            _cabi.var_forward(self.weights, p)          # first use: eager (also the warm-up every capture needs)
+        else:
+            g = torch.cuda.CUDAGraph()
+            l0 = _cabi.launch_count()
+            with torch.cuda.graph(g):
+                _cabi.var_forward(self.weights, p)
+            self._graphs[gkey] = (g, _cabi.launch_count() - l0)
+            g.replay()                                   # capture records, it does not execute
         if slot_map is None:
             self.kv_len += Lq
         return self.logits[:imgs * Lq].view(imgs, Lq, m.V) if want_logits else None

@@ -626,7 +626,7 @@ class SDVAR(nn.Module):
                                                    gamma: int = 2, top_k: int = 0, top_p: float = 0.0, more_smooth: bool = False,
                                                    accept_rule: str = "speculative", schedule: str = "lockstep",
                                                    gamma_policy: str = "fixed", noise=None, return_tokens: bool = False,
-                                                   record: Optional[dict] = None):
+                                                   record: Optional[dict] = None, _bound: Optional[str] = None):
         """while stage < K: draft g stages -> one target pass -> verify -> commit a prefix (models/var.py:1285-1383).
         Returns the image (B,3,H,W) in [0,1]; acceptance statistics are left in ``self.last_stats``.
 
@@ -638,9 +638,11 @@ class SDVAR(nn.Module):
                       no drafted stage survived intact the window shrinks by one (never below 1, never grows back).
         more_smooth   accepted and stored like the reference does (var.py:1315); the drafting / verification path never reads
                       it there either.
-        record        optional dict: receives every round's verify inputs and outputs (loop-replay tests)."""
+        record        optional dict: receives every round's verify inputs and outputs (loop-replay tests).
+        _bound        measurement only (bench.py 'bounds'): 'accept_all' commits every drafted window whole, 'reject_all' commits
+                      one stage per round, whatever the verify kernel said -- the two ends of the acceptance schedule."""
         assert accept_rule in ("speculative", "reference") and schedule in ("lockstep", "ragged") and gamma_policy in ("fixed", "reference")
-        assert gamma >= 1
+        assert gamma >= 1 and _bound in (None, "accept_all", "reject_all")
         state = self._initialize_inference_state(B, label_B, g_seed, cfg, gamma, noise)
         state.top_k, state.top_p, state.more_smooth = top_k, top_p, more_smooth
         state.schedule, state.gamma_policy, state.record = schedule, gamma_policy, record
@@ -661,6 +663,10 @@ class SDVAR(nn.Module):
                 draft_tokens = self.draft_generate_batch(state, state.n)
                 target_logits, _ = self.target_verify_batch(draft_tokens, state, state.n)
                 accept_length = match(draft_tokens, target_logits, state, state.n)
+                if _bound == "accept_all":
+                    accept_length, state.out_idx = len(draft_tokens), state.win_d
+                elif _bound == "reject_all":
+                    accept_length = 1
                 self.update_state_with_accepted_tokens(draft_tokens, accept_length, state, state.n)
                 per_img = [accept_length] * state.n if isinstance(accept_length, int) else accept_length
                 round_adv += per_img

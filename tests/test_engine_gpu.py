@@ -391,3 +391,65 @@ def test_gamma_policy_reference_shrinks_window(cuda_lib):
     rec2 = {}
     sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, gamma=3, cfg=1.5, gamma_policy="fixed", noise=ReplayNoise(9, DEV), record=rec2)
     assert all(len(r["seg"]) - 1 == min(3, len(P256) - r["stage"]) for r in rec2["rounds"])
+
+
+def test_decoder_per_layer_parity(cuda_lib):
+    """fhat_to_img layer by layer (parity gap 5): the bf16 channels-last device decoder against the fp32 oracle
+    (reference models/basic_vae.py:163-226) at conv_in, after the mid block, after every up level and at the image.  Each
+    feature map must agree within bf16 round-off accumulated over the layers so far -- relative to that map's own scale --
+    so an indexing bug in ONE layer cannot hide under the final image tolerance."""
+    from oracle.ref_model import RefDecoder
+    from sdvar_b200.models.vqvae import VQVAE
+    sd = vqvae_state_dict(ch=32, patch_nums=P256)
+    vae = VQVAE(vocab_size=4096, z_channels=32, ch=32, v_patch_nums=P256).to(DEV)
+    vae.load_state_dict({k: v.to(DEV) for k, v in sd.items()})
+    f_hat = hashed("dec.fhat", 3, (2, 32, 16, 16), 1.0)
+    ref_taps = {}
+    ref_img = RefDecoder(sd).fhat_to_img(f_hat, taps=ref_taps)
+    mods = vae._decoder_exec()
+    dec = mods[1]
+    got = {}
+    hooks = [dec.conv_in.register_forward_hook(lambda m, i, o: got.__setitem__("conv_in_nobias", o)),
+             dec.mid.register_forward_hook(lambda m, i, o: got.__setitem__("mid", o.float().cpu()))]
+    for lv in range(len(dec.up)):
+        hooks.append(dec.up[lv].register_forward_hook(lambda m, i, o, lv=lv: got.__setitem__(f"up.{lv}", o.float().cpu())))
+    img = vae.fhat_to_img(f_hat.to(DEV)).cpu()
+    for h in hooks:
+        h.remove()
+    assert set(ref_taps) - {"conv_in"} <= set(got)
+    for k in ("mid", "up.4", "up.3", "up.2", "up.1", "up.0"):
+        r, g = ref_taps[k], got[k]
+        assert r.shape == g.shape, k
+        scale = float(r.abs().max())
+        err = (g - r).abs()
+        assert float(err.max()) < 4e-2 * scale and float(err.mean()) < 4e-3 * scale, (k, float(err.max()), float(err.mean()), scale)
+    err = (img - ref_img).abs()                      # images in [-1, 1]
+    assert float(err.max()) < 6e-2 and float(err.mean()) < 5e-3, (float(err.max()), float(err.mean()))
+
+
+def test_fid_pipeline_and_checkpoint_ingest(cuda_lib, tmp_path):
+    """SURVEY.md 8f #4 at toy size: state dicts saved like the released checkpoints (torch.save of the reference's key
+    surface) load with strict=True through sdvar_b200.fid.load_checkpoints; sample_fid_set batch-generates per-class images,
+    packs them as the DiT-style npz (arr_0: (N,H,W,3) uint8, utils/misc.py:360-381) and writes PNGs that decode to the same
+    pixels; the uint8 values are trunc(x*255) of the float images (sdvar_colab_test.py:235-236)."""
+    from sdvar_b200 import fid
+    pns = (1, 2, 3, 4)
+    vae, d, t, sd, sds = _build(pns, 2, 3, gamma_bias=0.5, init_head=1.0)
+    torch.save({k: v.cpu() for k, v in sds["vae"].items()}, tmp_path / "vae.pth")
+    torch.save({k: v.cpu() for k, v in sds["d"].items()}, tmp_path / "var_d2.pth")
+    torch.save({k: v.cpu() for k, v in sds["t"].items()}, tmp_path / "var_d3.pth")
+    fid.load_checkpoints(vae, str(tmp_path / "vae.pth"), draft=(d, str(tmp_path / "var_d2.pth")), target=(t, str(tmp_path / "var_d3.pth")))
+    kw = dict(cfg=1.5, top_k=900, top_p=0.96)
+    floats = []
+
+    def gen(B, lab, s):
+        img = sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, g_seed=s, gamma=2, **kw)
+        floats.append(img.clone())
+        return img
+    path = fid.sample_fid_set(gen, str(tmp_path / "s.npz"), classes=range(5), per_class=3, batch=4, device=DEV, png_dir=str(tmp_path / "png"))
+    arr = np.load(path)["arr_0"]
+    assert arr.shape == (15, 64, 64, 3) and arr.dtype == np.uint8
+    ref = (torch.cat(floats).clamp(0, 1) * 255).to(torch.uint8).permute(0, 2, 3, 1).cpu().numpy()
+    assert np.array_equal(arr, ref)
+    from PIL import Image
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "png" / "000007.png")), arr[7])

@@ -463,7 +463,9 @@ def test_spec_expf_bit_exact_on_adversarial_inputs(cuda_lib):
             for _ in range(abs(d)):
                 v = np.nextafter(v, np.float32(-200.0) if d < 0 else np.float32(0.0))
             halves.append(v)
-    special = np.array([0.0, -0.0, -104.0, -104.00001, -103.99999, -150.0, -1e30, -np.inf], dtype=np.float32)
+    e0 = np.float32(-87.33)
+    special = np.array([0.0, -0.0, e0, np.nextafter(e0, np.float32(0)), np.nextafter(e0, np.float32(-100)), -87.0, -87.5, -88.0,
+                        -104.0, -104.00001, -103.99999, -150.0, -1e30, -np.inf], dtype=np.float32)
     x = np.concatenate([dense.astype(np.float32), np.array(halves, dtype=np.float32), special])
     xt = torch.from_numpy(x)
     ref = spec.expf(xt)
