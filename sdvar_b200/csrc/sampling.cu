@@ -370,11 +370,17 @@ __device__ __forceinline__ int vbin(float x, float scale, float off) { return __
 // ---- the part of the filtered path that works on the compacted list; QR = list entries per thread (n <= 256 * QR).
 // The list holds every entry whose top-k bin is >= the crossing bin: all survivors plus the few candidates below the exact
 // cut, which are dropped here (they contribute nothing once xK is known).
+struct K3Tail {      // returned BY VALUE: reference parameters of the out-of-line instance would pin these in local memory
+  float xlow;
+  int incl, slot;
+};
 template <int QR>
-__device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float2* lxn, const uint16_t* li, int n, float m, float xmin,
-                                        bool use_k, int top_k, bool hist_k, float kscale, float koff, float thr, bool sample,
-                                        float& xK_out, float& xlow, bool& incl, long long orow, long long* idx_out, float* prob_out) {
+__device__ __forceinline__ K3Tail k3_tail(K3Smem& s, int slot, const float2* lxn, const uint16_t* li, int n, float m, float xmin,
+                                          bool use_k, int top_k, bool hist_k, float kscale, float koff, float thr, bool sample,
+                                          long long orow, long long* idx_out, float* prob_out) {
   const int tid = threadIdx.x;
+  float xlow;
+  bool incl;
   float xv[QR], nzv[QR];
 #pragma unroll
   for (int q = 0; q < QR; ++q) {
@@ -429,7 +435,6 @@ __device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float2* lxn,
   } else if (use_k) {
     xK = s.xK;                        // found by the caller's fall-back
   }
-  xK_out = xK;
   // ---- exponentials of the survivors; dropped candidates get exp(-inf) = 0 and vanish from every sum ----
   float ev[QR];
   uint32_t hi = 0, lo = 0;
@@ -538,7 +543,7 @@ __device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float2* lxn,
     }
     if (sample) Z2i = block_sum_fix(hi, lo, s, 1);
   }
-  if (!sample) return;
+  if (!sample) return K3Tail{xlow, incl ? 1 : 0, slot};
   const float Z2 = __fmul_rn(__ull2float_rn(Z2i), 1.0f / kFixE);
   float best = -1.0f, bestp = 0.0f;
   int bi = 0x7FFFFFFF;
@@ -558,15 +563,16 @@ __device__ __forceinline__ void k3_tail(K3Smem& s, int& slot, const float2* lxn,
     if (idx_out) idx_out[orow] = win;
     if (prob_out) prob_out[orow] = (bi == win) ? bestp : 0.0f;
   }
+  return K3Tail{xlow, incl ? 1 : 0, slot};
 }
 
 // long lists (top-p without top-k, huge tie groups): kept out of line so that its 4*E-register working set does not
 // inflate the register allocation of the common path
 template <int E>
-__device__ __noinline__ void k3_tail_long(K3Smem& s, int& slot, const float2* lxn, const uint16_t* li, int n, float m, float xmin,
-                                          bool use_k, int top_k, bool hist_k, float kscale, float koff, float thr, bool sample,
-                                          float& xK_out, float& xlow, bool& incl, long long orow, long long* idx_out, float* prob_out) {
-  k3_tail<E>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, xK_out, xlow, incl, orow, idx_out, prob_out);
+__device__ __noinline__ K3Tail k3_tail_long(K3Smem& s, int slot, const float2* lxn, const uint16_t* li, int n, float m, float xmin,
+                                            bool use_k, int top_k, bool hist_k, float kscale, float koff, float thr, bool sample,
+                                            long long orow, long long* idx_out, float* prob_out) {
+  return k3_tail<E>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, orow, idx_out, prob_out);
 }
 
 template <int NV, int OCC>
@@ -578,8 +584,8 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
   constexpr int E = NV * 4;
   constexpr int QF = E < 6 ? E : 6;     // fast tail: lists of up to 1536 entries
   extern __shared__ __align__(16) unsigned char k3_dyn[];
-  float2* lxn = reinterpret_cast<float2*>(k3_dyn);           // [V] (logit, noise) of the listed entries
-  uint16_t* li = reinterpret_cast<uint16_t*>(lxn + V);       // [V] their vocabulary index
+  float2* lxn = reinterpret_cast<float2*>(k3_dyn);           // [V + 2] (logit, noise) of the listed entries (+ the dummy slot)
+  uint16_t* li = reinterpret_cast<uint16_t*>(lxn + V + 2);   // [V + 2] their vocabulary index
   __shared__ K3Smem s;
   int slot = 0;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -683,14 +689,17 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
       }
     }
 
-    // ---- compact the listed entries (any order: every later sum is an integer sum) ----
+    // ---- compact the listed entries (any order: every later sum is an integer sum).  Branch-free: entries that are not
+    // listed are stored to a dummy slot (index V) instead of being jumped over -- a profile of the branchy version showed
+    // ~290 of ~2060 instructions per thread-row in BRA / BSSY / BSYNC and ~120 in spill traffic of the per-element flags.
     {
-      bool in[E];
       uint32_t cnt = 0;
+      if (hist_k) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        in[e] = hist_k ? (vbin(x[e], kscale, koff) >= bst) : (x[e] >= xcut);
-        cnt += in[e] ? 1u : 0u;
+        for (int e = 0; e < E; ++e) cnt += (vbin(x[e], kscale, koff) >= bst) ? 1u : 0u;
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) cnt += (x[e] >= xcut) ? 1u : 0u;
       }
       const uint32_t inc = warp_incl_scan(cnt);
       int base = 0;
@@ -701,22 +710,24 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
       for (int i = 0; i < NV; ++i) {
         const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (in[4 * i + c]) {
-            lxn[p] = make_float2(x[4 * i + c], sample ? nn[c] : 1.0f);
-            li[p] = (uint16_t)(4 * (i * kThreads + tid) + c);
-            ++p;
-          }
+        for (int c = 0; c < 4; ++c) {
+          const float xe = x[4 * i + c];
+          const bool a = hist_k ? (vbin(xe, kscale, koff) >= bst) : (xe >= xcut);
+          const int dst = a ? p : V;
+          lxn[dst] = make_float2(xe, sample ? nn[c] : 1.0f);
+          li[dst] = (uint16_t)(4 * (i * kThreads + tid) + c);
+          p += a ? 1 : 0;
+        }
       }
     }
     __syncthreads();
     const int n = s.n_list;
-    float xK, xlow;
-    bool incl;
-    if (n <= QF * kThreads)
-      k3_tail<QF>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, xK, xlow, incl, orow, idx_out, prob_out);
-    else
-      k3_tail_long<E>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, xK, xlow, incl, orow, idx_out, prob_out);
+    const K3Tail tl = (n <= QF * kThreads)
+        ? k3_tail<QF>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, orow, idx_out, prob_out)
+        : k3_tail_long<E>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, orow, idx_out, prob_out);
+    slot = tl.slot;
+    const float xlow = tl.xlow;
+    const bool incl = tl.incl != 0;
 
     if (mixed_out != nullptr) {
       float4* po = reinterpret_cast<float4*>(mixed_out + orow * V);
@@ -1003,7 +1014,7 @@ extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L
   ProfileScope prof(st, FAM_SAMPLE, (double)rows * (8.0 * V + (noise ? 4.0 * V + 8.0 : 0.0) + (mixed_out ? 4.0 * V : 0.0)));
   const bool filtered = (top_k > 0 && top_k < V) || one_minus_top_p >= 0.0f;
   static const int occ = [] { const char* e = getenv("SDVAR_K3_OCC"); return e && atoi(e) == 4 ? 4 : 3; }();   // CTAs per SM (A/B switch)
-  const size_t dyn = (size_t)V * 10;      // list: (logit, noise) fp32 pairs + vocabulary index (u16)
+  const size_t dyn = (size_t)(V + 2) * 10;      // list: (logit, noise) fp32 pairs + vocabulary index (u16), + a dummy slot
 #define SDVAR_K3(NV)                                                                                                        \
   case NV:                                                                                                                  \
     if (filtered && occ == 3) {                                                                                             \

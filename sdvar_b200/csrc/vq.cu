@@ -4,8 +4,8 @@
 // :199-206 (Phi = (1-r)*h + r*conv3x3(h), r = |quant_resi|), and models/var.py:179-188 (stage input maps).
 //
 // f_hat is tiny (32 KiB per image at 256 px), so this step is latency-bound, not HBM-bound: the design
-// goal is few launches and on-chip staging.  Kernel A gives each CTA one output row of one image: it
-// gathers only the codebook rows the bicubic taps of rows y-1..y+1 touch, interpolates separably in
+// goal is few launches and on-chip staging.  Kernel A gives each CTA four output rows of one image: it
+// gathers only the codebook rows the bicubic taps of rows y0-1..y0+4 touch, interpolates separably in
 // shared memory, runs the 3x3 Phi conv with the weights staged in shared memory ([ci][tap][co], bank =
 // co) and adds into f_hat through a transposing shared tile so the global update is row-contiguous.
 // Kernel B is the overlapping-window area pooling (adaptive average) to the next stage's resolution.
@@ -15,7 +15,6 @@ namespace sdvar {
 
 constexpr int kC = 32;       // Cvae
 constexpr int kMaxHW = 32;   // 512 px pyramid
-constexpr int kMaxSrcRows = 8;
 
 // Keys cubic convolution coefficients, A = -0.75 (ATen upsample_bicubic2d, align_corners=False)
 __device__ __forceinline__ void cubic_coeffs(float t, float w[4]) {
@@ -39,24 +38,32 @@ __device__ __forceinline__ void cubic_src(int o, int pn, int HW, int& ix, float&
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-struct VqSmem {
-  float w[kC * 9 * (kC + 1)];                 // [ci][tap][co], rows padded to 33 floats: the transposing stores are conflict-free
+// One CTA computes R consecutive output rows of one image, so the 36 KiB of Phi weights are staged once per R rows (round 1:
+// one row per CTA, 7 waves of CTAs that each re-staged the weights with 32-way bank-conflicting transposing stores; ~130 us per
+// launch at B=64).  HWMAX sizes the staging buffers for the pyramid in use (16: 256 px, 32: 512 px).
+template <int HWMAX, int R>
+struct VqSmemT {
+  static constexpr int kSrcRows = R + 5;         // output rows y0-1 .. y0+R need at most R+2+3 source rows when upsampling
+  float w[kC * 9 * (kC + 1)];                    // [ci][tap][co], rows padded to 33 floats: the transposing stores are conflict-free
   float bias[kC];
-  float src[kMaxSrcRows][kMaxHW][kC];         // gathered codebook rows  [r][q][c]
-  float tmp[kMaxSrcRows][kMaxHW][kC];         // after horizontal interpolation [r][x][c]
-  float hup[3][kMaxHW + 2][kC];               // rows y-1,y,y+1 with one zero column on each side [dy][x+1][c]
-  float outT[kC][kMaxHW + 1];                 // conv result transposed [co][x]
+  float src[kSrcRows][HWMAX][kC];                // gathered codebook rows  [r][q][c]
+  float tmp[kSrcRows][HWMAX][kC];                // after horizontal interpolation [r][x][c]
+  float hup[R + 2][HWMAX + 2][kC];               // rows y0-1 .. y0+R with one zero column on each side [dy][x+1][c]
+  float outT[R][kC][HWMAX + 1];                  // conv result transposed [row][co][x]
 };
 
+template <int HWMAX, int R>
 __global__ void __launch_bounds__(256)
 vq_accumulate_kernel(const long long* __restrict__ idx, int pn, int HW, const float* __restrict__ codebook,
                      const float* __restrict__ phi_w, const float* __restrict__ phi_b, float resi, float* __restrict__ f_hat,
                      float* __restrict__ f_rest) {
+  using Smem = VqSmemT<HWMAX, R>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  VqSmem& s = *reinterpret_cast<VqSmem*>(smem_raw);
-  const int b = blockIdx.y, y = blockIdx.x, tid = threadIdx.x;
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const int b = blockIdx.y, y0 = blockIdx.x * R, tid = threadIdx.x;
   const int lane = tid & 31, grp = tid >> 5;
   const bool up = (pn != HW);
+  const int nrows = min(R, HW - y0);
 
   // stage Phi weights as [ci][tap][co] (global layout is [co][ci][3][3])
   for (int i = tid; i < kC * kC * 9; i += 256) {
@@ -65,19 +72,19 @@ vq_accumulate_kernel(const long long* __restrict__ idx, int pn, int HW, const fl
   }
   if (tid < kC) s.bias[tid] = phi_b[tid];
 
-  // source rows needed by output rows y-1..y+1
+  // source rows needed by output rows y0-1 .. y0+nrows
   int r0, r1;
   if (up) {
     int ixa, ixb; float t;
-    cubic_src(max(y - 1, 0), pn, HW, ixa, t);
-    cubic_src(min(y + 1, HW - 1), pn, HW, ixb, t);
+    cubic_src(max(y0 - 1, 0), pn, HW, ixa, t);
+    cubic_src(min(y0 + nrows, HW - 1), pn, HW, ixb, t);
     r0 = clampi(ixa - 1, 0, pn - 1);
     r1 = clampi(ixb + 2, 0, pn - 1);
   } else {
-    r0 = max(y - 1, 0);
-    r1 = min(y + 1, HW - 1);
+    r0 = max(y0 - 1, 0);
+    r1 = min(y0 + nrows, HW - 1);
   }
-  const int nr = r1 - r0 + 1;  // <= kMaxSrcRows (upscaling factor >= 1 => at most 6 rows)
+  const int nr = r1 - r0 + 1;  // <= kSrcRows
   // gather: one warp per token, lane = channel (128-byte coalesced codebook rows)
   for (int tk = grp; tk < nr * pn; tk += 8) {
     const int r = tk / pn, q = tk - r * pn;
@@ -99,10 +106,10 @@ vq_accumulate_kernel(const long long* __restrict__ idx, int pn, int HW, const fl
     }
     __syncthreads();
   }
-  // vertical + zero padding: hup[dy][x+1][c]
-  for (int i = grp; i < 3 * (HW + 2); i += 8) {
+  // vertical + zero padding: hup[dy][x+1][c], dy = 0 .. nrows+1  <->  output row y0-1+dy
+  for (int i = grp; i < (nrows + 2) * (HW + 2); i += 8) {
     const int dy = i / (HW + 2), xp = i - dy * (HW + 2);
-    const int yy = y - 1 + dy, x = xp - 1;
+    const int yy = y0 - 1 + dy, x = xp - 1;
     float v = 0.0f;
     if (yy >= 0 && yy < HW && x >= 0 && x < HW) {
       if (up) {
@@ -118,8 +125,9 @@ vq_accumulate_kernel(const long long* __restrict__ idx, int pn, int HW, const fl
     s.hup[dy][xp][lane] = v;
   }
   __syncthreads();
-  // conv: thread (co = lane, x = grp, grp+8, ..)
-  for (int x = grp; x < HW; x += 8) {
+  // conv: thread (co = lane, pixel = grp, grp+8, ..) over the R x HW pixels of this CTA
+  for (int px = grp; px < nrows * HW; px += 8) {
+    const int ry = px / HW, x = px - ry * HW;
     float acc = s.bias[lane];
 #pragma unroll 4
     for (int ci = 0; ci < kC; ++ci) {
@@ -127,18 +135,18 @@ vq_accumulate_kernel(const long long* __restrict__ idx, int pn, int HW, const fl
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx)
-          acc += s.w[(ci * 9 + dy * 3 + dx) * (kC + 1) + lane] * s.hup[dy][x + dx][ci];
+          acc += s.w[(ci * 9 + dy * 3 + dx) * (kC + 1) + lane] * s.hup[ry + dy][x + dx][ci];
     }
     // Phi (models/quant.py:205-206): (1-r)*h + r*conv(h); r = 0.5 in every released checkpoint
-    s.outT[lane][x] = (1.0f - resi) * s.hup[1][x + 1][lane] + resi * acc;
+    s.outT[ry][lane][x] = (1.0f - resi) * s.hup[ry + 1][x + 1][lane] + resi * acc;
   }
   __syncthreads();
-  // f_hat[b, c, y, :] += outT[c][:]   (row-contiguous)
-  for (int i = tid; i < kC * HW; i += 256) {
-    const int c = i / HW, x = i - c * HW;
-    const long long o = (((long long)b * kC + c) * HW + y) * HW + x;
-    f_hat[o] += s.outT[c][x];
-    if (f_rest != nullptr) f_rest[o] -= s.outT[c][x];   // encode side: the reference's running residual (models/quant.py:163)
+  // f_hat[b, c, y0+ry, :] += outT[ry][c][:]   (row-contiguous)
+  for (int i = tid; i < nrows * kC * HW; i += 256) {
+    const int ry = i / (kC * HW), rem = i - ry * kC * HW, c = rem / HW, x = rem - c * HW;
+    const long long o = (((long long)b * kC + c) * HW + y0 + ry) * HW + x;
+    f_hat[o] += s.outT[ry][c][x];
+    if (f_rest != nullptr) f_rest[o] -= s.outT[ry][c][x];   // encode side: the reference's running residual (models/quant.py:163)
   }
 }
 
@@ -299,9 +307,17 @@ extern "C" int sdvar_vq_next_input(const long long* idx_Bl, int B, int pn, int H
   SDVAR_REQUIRE(pn_next >= 0 && pn_next <= HW, "bad pn_next=%d", pn_next);
   SDVAR_REQUIRE(pn_next == 0 || next_map != nullptr, "next_map is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  SDVAR_SET_SMEM_ONCE(vq_accumulate_kernel, sizeof(VqSmem));
   ProfileScope prof(st, FAM_VQ, (double)B * (2.0 * Cvae * HW * HW * 4 + 8.0 * pn * pn + 4.0 * Cvae * pn_next * pn_next));
-  vq_accumulate_kernel<<<dim3(HW, B), 256, sizeof(VqSmem), st>>>(idx_Bl, pn, HW, codebook, phi_w, phi_b, resi_ratio, f_hat, f_rest);
+  constexpr int R = 4;
+  if (HW <= 16) {
+    using Smem = VqSmemT<16, R>;
+    SDVAR_SET_SMEM_ONCE((vq_accumulate_kernel<16, R>), sizeof(Smem));
+    vq_accumulate_kernel<16, R><<<dim3((HW + R - 1) / R, B), 256, sizeof(Smem), st>>>(idx_Bl, pn, HW, codebook, phi_w, phi_b, resi_ratio, f_hat, f_rest);
+  } else {
+    using Smem = VqSmemT<kMaxHW, R>;
+    SDVAR_SET_SMEM_ONCE((vq_accumulate_kernel<kMaxHW, R>), sizeof(Smem));
+    vq_accumulate_kernel<kMaxHW, R><<<dim3((HW + R - 1) / R, B), 256, sizeof(Smem), st>>>(idx_Bl, pn, HW, codebook, phi_w, phi_b, resi_ratio, f_hat, f_rest);
+  }
   SDVAR_LAUNCH_CHECK();
   if (pn_next > 0) {
     vq_area_down_kernel<<<B, 256, 0, st>>>(f_hat, HW, pn_next, next_map);

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from sdvar_b200.weights import var_state_dict, vqvae_state_dict
+from sdvar_b200.weights import hashed, var_state_dict, vqvae_state_dict
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
