@@ -640,3 +640,89 @@ def sd_generate(draft: RefVAR, target: RefVAR, vq: RefVQ, B: int, label_B: torch
     stats["accepted_tokens"] = sum(stats["stage_accept_tokens"])
     stats["rejected_tokens"] = sum(stats["stage_tokens"]) - stats["accepted_tokens"]
     return f_hat, final_idx, stats
+
+
+# --------------------------------------------------------------------------------------
+# per-image ragged schedule + the reference's gamma controller (PARITY UNPINNED like the loop above)
+# --------------------------------------------------------------------------------------
+@torch.no_grad()
+def sd_generate_ragged(draft: RefVAR, target: RefVAR, vq: RefVQ, B: int, label_B: torch.Tensor, noise, cfg=1.5, gamma=2,
+                       top_k=0, top_p=0.0, gamma_policy: str = "fixed"):
+    """Spec of ``schedule='ragged'``: every image keeps its own stage pointer (and, under ``gamma_policy='reference'``, its own
+    window length).  A round visits the groups of images that share (stage, gamma) in ascending order; each group runs the
+    round of ``sd_generate`` on its sub-batch -- draft g stages, one block-causal target pass, per-token verify -- and every
+    image of the group advances by ITS OWN accepted prefix: a_b = min(#leading window stages image b accepted whole + 1, g)
+    (replaces the batch-global accept_length of models/var.py:1349-1350).  gamma controller (models/var.py:1352-1358): an
+    image whose first drafted stage was not accepted whole shrinks its window by one, never below 1.
+
+    The oracle keeps no ragged KV cache: the caches of a group are rebuilt by teacher-forcing its committed stages (the
+    engine instead keeps per-image cache slots and runs the group through a slot map; the arithmetic is the same).
+    Noise: per group, per stage, in the order the groups are visited: 'draft' (n*l,V) per drafted stage, 'u' (n*l) and
+    'resample' (n*l,V) per verified stage.  Returns (f_hat, final idx per stage, stats)."""
+    K, V = len(draft.patch_nums), draft.V
+    HW = draft.patch_nums[-1]
+    f_hat = torch.zeros(B, draft.Cvae, HW, HW)
+    final = [torch.zeros(B, l, dtype=torch.int64) for l in draft.ls]
+    stage, gammas = [0] * B, [gamma] * B
+    stats = dict(rounds=0, target_passes=0, draft_stages=0, advance=[], image_rounds=[0] * B)
+
+    def prefill(model, cond, ids, s):
+        """rebuild the KV cache of the committed stages [0, s) of images ``ids``; returns (f_hat of the group, stage-s input map)"""
+        model.kv_caching(False); model.kv_caching(True)
+        fh = torch.zeros(len(ids), draft.Cvae, HW, HW)
+        nm = None
+        for si in range(s):
+            x = model.first_map(cond) if si == 0 else model.embed_map(si, nm)
+            model.blocks(x, cond, None)
+            fh, nm = vq.next_input(si, fh, final[si][ids])
+        return fh, nm
+
+    while min(stage) < K:
+        keys = sorted({(stage[b], gammas[b]) for b in range(B) if stage[b] < K})
+        adv_round = []
+        for s, gm in keys:
+            ids = [b for b in range(B) if stage[b] == s and gammas[b] == gm]
+            n, g = len(ids), min(gm, K - s)
+            lab = label_B[ids]
+            cond_d, cond_t = draft.cond(lab), target.cond(lab)
+            fh0, nm0 = prefill(draft, cond_d, ids, s)
+            prefill(target, cond_t, ids, s)
+            fh = fh0.clone()
+            maps, snaps, idx_d, mixed_d = [nm0], [], [], []
+            for j in range(g):
+                si = s + j
+                x = draft.first_map(cond_d) if si == 0 else draft.embed_map(si, maps[j])
+                mixed = cfg_mix(draft.get_logits(draft.blocks(x, cond_d, None), cond_d), n, cfg * si / (K - 1))
+                idx = sample_with_noise_(mixed, noise.exponential("draft", n * draft.ls[si], V), top_k, top_p)
+                fh, nm = vq.next_input(si, fh, idx)
+                idx_d.append(idx); mixed_d.append(mixed); snaps.append(fh.clone()); maps.append(nm)
+                stats["draft_stages"] += 1
+            xs = [target.first_map(cond_t) if s + j == 0 else target.embed_map(s + j, maps[j]) for j in range(g)]
+            logits_t = target.forward_window(s, xs, cond_t)
+            stats["target_passes"] += 1
+            out_idx, ok = [], torch.ones(n, g, dtype=torch.bool)
+            for j in range(g):
+                si, l = s + j, draft.ls[s + j]
+                mixed_t = filter_top_k_top_p_(cfg_mix(logits_t[j], n, cfg * si / (K - 1)), top_k, top_p)
+                u = noise.uniform("u", n * l)
+                n_r = noise.exponential("resample", n * l, V)
+                o, acc, _, _ = verify_tokens(mixed_t.view(-1, V), mixed_d[j].view(-1, V), idx_d[j].view(-1), u, n_r)
+                out_idx.append(o.view(n, l))
+                ok[:, j] = acc.view(n, l).all(dim=1)
+            n_ok = ok.long().cumprod(dim=1).sum(dim=1).tolist()      # leading stages accepted whole, per image
+            for i, b in enumerate(ids):
+                a = min(n_ok[i] + 1, g)
+                for j in range(a - 1):
+                    final[s + j][b] = idx_d[j][i]
+                final[s + a - 1][b] = out_idx[a - 1][i]
+                base = snaps[a - 2][i:i + 1].clone() if a >= 2 else fh0[i:i + 1].clone()
+                f_hat[b:b + 1], _ = vq.next_input(s + a - 1, base, out_idx[a - 1][i:i + 1])
+                stage[b] = s + a
+                stats["image_rounds"][b] += 1
+                adv_round.append(a)
+                if gamma_policy == "reference" and n_ok[i] == 0:
+                    gammas[b] = max(1, gm - 1)
+        stats["rounds"] += 1
+        stats["advance"].append(sum(adv_round) / len(adv_round))
+    draft.kv_caching(False); target.kv_caching(False)
+    return f_hat, final, stats

@@ -110,3 +110,26 @@ def test_shard_range_partitions_exactly():
         for w in (1, 2, 4, 8):
             r = [shard_range(G, k, w) for k in range(w)]
             assert r[0][0] == 0 and r[-1][1] == G and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+@pytest.mark.parametrize("policy", ["fixed", "reference"])
+def test_ragged_schedule_spec(policy):
+    """oracle of the per-image ragged schedule (oracle.ref_model.sd_generate_ragged): the target equals the draft except for
+    the class embedding of labels >= 500, so images with smaller labels accept every drafted stage (ceil(K/gamma) rounds, the
+    draft's own tokens) while the others advance by their own accepted prefixes; f_hat == VQ(final tokens) for every image; a
+    B=1 lock-step run of an image that never rejects commits the same number of stages per round."""
+    from oracle.ref_model import sd_generate_ragged
+    vq, d, _ = _models()
+    tsd = {k: v.clone() for k, v in var_state_dict(2, patch_nums=P4, seed=1, tag="draft", **KW).items()}
+    tsd["class_emb.weight"][500:1000] += 0.5 * torch.randn(500, tsd["class_emb.weight"].shape[1], generator=torch.Generator().manual_seed(0))
+    t = RefVAR(tsd, P4)
+    B, lab = 4, torch.tensor([3, 700, 41, 900])
+    f, idxs, st = sd_generate_ragged(d, t, vq, B, lab, ReplayNoise(3), cfg=1.5, gamma=2, gamma_policy=policy)
+    K = len(P4)
+    assert st["image_rounds"][0] == st["image_rounds"][2] == -(-K // 2)
+    assert max(st["image_rounds"]) <= K and st["rounds"] == max(st["image_rounds"])
+    fr = torch.zeros(B, 32, 4, 4)
+    for si, ix in enumerate(idxs):
+        fr, _ = vq.next_input(si, fr, ix)
+    assert torch.allclose(f, fr, atol=1e-6)
+    assert [i.shape for i in idxs] == [(B, l) for l in d.ls]
