@@ -31,9 +31,15 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ p
 #pragma unroll
   for (int k = 0; k < 8; ++k) { acc_s[k] = 0.f; acc_q[k] = 0.f; }
   const int v = threadIdx.x % vec_per_pix;
+  // conv bias folded in (statistics of x + b), and every value is taken relative to a per-(image, group) PIVOT -- the group's
+  // first element -- so that the one-pass variance E[d^2] - E[d]^2 does not cancel when |mean| >> std
   float pb[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) pb[k] = pre_bias ? pre_bias[v * 8 + k] : 0.f;   // conv bias folded in: statistics of x + b
+  for (int k = 0; k < 8; ++k) {
+    const int c = v * 8 + k, c0 = (c / cg) * cg;
+    const float piv = __bfloat162float(x[base + c0]) + (pre_bias ? pre_bias[c0] : 0.f);
+    pb[k] = (pre_bias ? pre_bias[c] : 0.f) - piv;
+  }
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int pix = p0 + i / vec_per_pix;
     const uint4 raw = *reinterpret_cast<const uint4*>(x + base + (long long)pix * C + v * 8);
@@ -82,8 +88,11 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ p
     const float* pp = partial + (long long)n * nblk_stats * 64 + 2 * threadIdx.x;
     for (int b = 0; b < nblk_stats; ++b) { s += pp[b * 64]; q += pp[b * 64 + 1]; }   // fixed order => deterministic
     const float cnt = (float)HW * (float)cg;
-    const float mean = s / cnt;
-    const float var = fmaxf(q / cnt - mean * mean, 0.f);
+    const int c0 = threadIdx.x * cg;
+    const float piv = __bfloat162float(x[(long long)n * HW * C + c0]) + (pre_bias ? pre_bias[c0] : 0.f);   // the pivot gn_stats used
+    const float dm = s / cnt;
+    const float mean = piv + dm;
+    const float var = fmaxf(q / cnt - dm * dm, 0.f);
     s_mean[threadIdx.x] = mean;
     s_rstd[threadIdx.x] = rsqrtf(var + eps);
   }

@@ -168,7 +168,7 @@ vq_area_down_kernel(const float* __restrict__ f_hat, int HW, int pn2, float* __r
 }
 
 // x[r,t,:] = W @ nm[b,:,t] + bias + lvl_pos[t,:], r in {b, B+b}   (models/var.py:185-188)
-constexpr int kEmbTok = 8;
+constexpr int kEmbTok = 32;   // tokens per CTA: W_we (C x 32 fp32) is re-read from L2 once per CTA, so few large CTAs beat many small ones
 __global__ void __launch_bounds__(256)
 embed_next_map_kernel(const float* __restrict__ nm, int B, int l, int C, const float* __restrict__ W,
                       const float* __restrict__ bias, const float* __restrict__ lvl_pos, float* __restrict__ x,

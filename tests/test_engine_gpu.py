@@ -17,13 +17,13 @@ P4 = (1, 2, 3, 4)
 P256 = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)
 
 
-def _build(pns, depth_d, depth_t, ch=32, shared_t=False, **kw):
+def _build(pns, depth_d, depth_t, ch=32, shared_t=False, sd_device="cpu", **kw):
     from sdvar_b200.models import build_vae_var_speculative_decoding
     vae, d, t, sd = build_vae_var_speculative_decoding(DEV, patch_nums=pns, ch=ch, depth_draft=depth_d, depth_target=depth_t,
                                                        shared_aln_target=shared_t)
-    sds = dict(vae=vqvae_state_dict(ch=ch, patch_nums=pns),
-               d=var_state_dict(depth_d, patch_nums=pns, seed=1, tag="draft", **kw),
-               t=var_state_dict(depth_t, patch_nums=pns, seed=2, tag="target", shared_aln=shared_t, **kw))
+    sds = dict(vae=vqvae_state_dict(ch=ch, patch_nums=pns, device=sd_device),
+               d=var_state_dict(depth_d, patch_nums=pns, seed=1, tag="draft", device=sd_device, **kw),
+               t=var_state_dict(depth_t, patch_nums=pns, seed=2, tag="target", shared_aln=shared_t, device=sd_device, **kw))
     vae.load_state_dict(sds["vae"]); d.load_state_dict(sds["d"]); t.load_state_dict(sds["t"])
     return vae, d, t, sd, sds
 
@@ -271,16 +271,20 @@ def _dense_aux(rec, n):
     return u, nz.view(n * Lw, V)
 
 
-@pytest.mark.parametrize("schedule,gamma,top_k,top_p", [("lockstep", 2, 900, 0.96), ("lockstep", 3, 0, 0.0), ("ragged", 2, 0, 0.0)])
-def test_sd_loop_replay_against_spec(cuda_lib, schedule, gamma, top_k, top_p):
+@pytest.mark.parametrize("schedule,gamma,top_k,top_p,depths", [("lockstep", 2, 900, 0.96, (2, 3)), ("lockstep", 3, 0, 0.0, (2, 3)),
+                                                                  ("ragged", 2, 0, 0.0, (2, 3)), ("lockstep", 2, 900, 0.96, (16, 20)),
+                                                                  ("ragged", 2, 0, 0.0, (16, 20))])
+def test_sd_loop_replay_against_spec(cuda_lib, schedule, gamma, top_k, top_p, depths):
     """LOOP-LEVEL replay (parity gap 4): every round's verify inputs (mixed target / draft logits, draft tokens, u,
     resample noise) are recorded from the device loop and pushed through the C spec and the loop spec's advance rule
     (DESIGN.md 3.4): accept flags, repaired tokens, first-reject scan and accepted-prefix lengths must be identical, the
     committed tokens must be the draft tokens of the intact stages + the spec's output for the last committed stage, and
-    the stage pointers must advance by min(#intact leading stages + 1, g) -- per batch (lock-step) or per image (ragged)."""
+    the stage pointers must advance by min(#intact leading stages + 1, g) -- per batch (lock-step) or per image (ragged).
+    depths (16, 20) is BASELINE.json configs[0] as stated: VAR-d16 draft + VAR-d20 target, 256 px, batch 4, cfg 1.5 (default init)."""
     from oracle import spec
     from oracle.ref_model import ReplayNoise
-    vae, d, t, sd, _ = _build(P256, 2, 3, gamma_bias=0.5, init_head=1.0)
+    kw = dict(gamma_bias=0.5, init_head=1.0) if depths == (2, 3) else {}
+    vae, d, t, sd, _ = _build(P256, depths[0], depths[1], sd_device="cpu" if depths == (2, 3) else DEV, **kw)
     B, lab = 4, torch.tensor([1, 2, 3, 4], device=DEV)
     rec = {}
     _, final, _ = sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, gamma=gamma, cfg=1.5, top_k=top_k, top_p=top_p, schedule=schedule,

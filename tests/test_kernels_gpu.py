@@ -582,3 +582,17 @@ def test_vq_resi_ratio_and_area_down(cuda_lib, resi):
             alone = torch.empty_like(nm)
             cuda_lib.vq_area_down(f, B, 16, P256[si + 1], 32, alone)
             assert torch.equal(alone, nm), si
+
+
+def test_groupnorm_large_mean_small_std(cuda_lib):
+    """a group whose mean dwarfs its standard deviation (here mean 60, std ~0.4 after bf16 rounding).  The plain
+    one-pass variance E[x^2] - E[x]^2 loses most of its bits there; the kernel accumulates around a per-group pivot instead."""
+    N, C, H = 2, 160, 32
+    x = (60.0 + hashed("gn.big", 0, (N, C, H, H), 0.4)).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    g = (1.0 + hashed("gn.big.g", 1, (C,), 0.2)).to(DEV)
+    b = hashed("gn.big.b", 2, (C,), 0.2).to(DEV)
+    ref = torch.nn.functional.group_norm(x.double(), 32, g.double(), b.double(), eps=1e-6).float()
+    y = torch.empty_like(x)
+    scratch = torch.empty(N * 128 * 64, device=DEV)
+    cuda_lib.groupnorm_silu_nhwc(x, N, H * H, C, g, b, 1e-6, False, y, scratch)
+    assert torch.allclose(y.float(), ref, rtol=2 ** -7, atol=2e-2), float((y.float() - ref).abs().max())

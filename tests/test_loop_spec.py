@@ -133,3 +133,34 @@ def test_ragged_schedule_spec(policy):
         fr, _ = vq.next_input(si, fr, ix)
     assert torch.allclose(f, fr, atol=1e-6)
     assert [i.shape for i in idxs] == [(B, l) for l in d.ls]
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sdvar_b200 import parallel
+    B = 3
+    img = torch.rand(B, 3, 8, 8, generator=torch.Generator().manual_seed(rank))
+    buf = parallel.GatherBuffer(world, B, (3, 8, 8), "cpu")
+    out = buf.gather(img).clone()
+    t = parallel.reduce_stats_async(dict(rounds=1 + rank, target_passes=2, draft_stages=3, accepted_tokens=10 * (rank + 1), rejected_tokens=1), "cpu")
+    q.put((rank, out, parallel.stats_from_tensor(t)))
+    dist.destroy_process_group()
+
+
+def test_uint8_gather_and_async_stats_gloo_world2():
+    """the path's only collectives on 2 gloo ranks: every rank's images land as uint8 = trunc(x*255) in its slot
+    of one preallocated buffer, the acceptance counters are summed without a host synchronisation inside the step"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400)
+    ps = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda x: x[0])
+    for p in ps:
+        p.join(timeout=60)
+    want = torch.cat([(torch.rand(3, 3, 8, 8, generator=torch.Generator().manual_seed(r)).clamp(0, 1) * 255).to(torch.uint8) for r in range(2)])
+    for rank, out, st in res:
+        assert out.dtype == torch.uint8 and torch.equal(out, want)
+        assert st == dict(rounds=3, target_passes=4, draft_stages=6, accepted_tokens=30, rejected_tokens=2)
