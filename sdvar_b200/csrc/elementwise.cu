@@ -3,6 +3,8 @@
 // ln_modulate replaces `ln_wo_grad(x).mul(scale.add(1)).add_(shift)` at models/basic_var.py:157-158 and
 // :173-174.  HBM-bound: one warp per row, the row is staged once in shared memory (single global read),
 // mean and centred variance are reduced with warp shuffles, the bf16 result is written with 8-byte stores.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sdvar {
@@ -100,6 +102,105 @@ ln_modulate_reg_kernel(const float* __restrict__ x, int M, int tokens_per_img, c
   }
 }
 
+// Persistent variant for large M: one 256-thread CTA per SM, every warp streams ITS rows through a private 3-deep shared-memory
+// ring filled by 1-D bulk TMA copies (cp.async.bulk + mbarrier), so 8 x 3 rows (184 KiB at C = 1920) are in flight per SM at
+// all times, independent of the register file.  The register-resident kernel above is limited to 24 warps per SM by its 80
+// registers and showed long-scoreboard stalls with the issue slots 24 % busy and DRAM at 56 % of peak (profiles/ncu_ln_r02.md).
+constexpr int kLnStages = 3;
+__device__ __forceinline__ void ln_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void ln_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LN_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LN_DONE;\n"
+      "bra LN_WAIT;\n"
+      "LN_DONE:\n"
+      "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int NITER>
+__global__ void __launch_bounds__(256, 1)
+ln_modulate_tma_kernel(const float* __restrict__ x, int M, int tokens_per_img, const float* __restrict__ scale,
+                       const float* __restrict__ shift, int ld_mod, const int* __restrict__ slot_map, float eps,
+                       __nv_bfloat16* __restrict__ out) {
+  constexpr int C = NITER * 128;
+  constexpr uint32_t kRowBytes = C * 4;
+  extern __shared__ __align__(128) unsigned char ln_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ring = reinterpret_cast<float*>(ln_smem) + (size_t)warp * kLnStages * C;          // [kLnStages][C] of this warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)8 * kLnStages * kRowBytes) + warp * kLnStages;
+  const long long stride = (long long)gridDim.x * 8;
+  const long long first = (long long)blockIdx.x * 8 + warp;
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < kLnStages; ++st)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bars[st])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int st = 0; st < kLnStages; ++st) {
+      const long long r = first + st * stride;
+      if (r < M) ln_bulk_g2s(ring + st * C, x + r * C, kRowBytes, &bars[st]);
+    }
+  }
+  __syncwarp();
+  uint32_t k = 0;
+  for (long long row = first; row < M; row += stride, ++k) {
+    const uint32_t st = k % kLnStages;
+    ln_mbar_wait(&bars[st], (k / kLnStages) & 1);
+    const float4* src = reinterpret_cast<const float4*>(ring + st * C);
+    float4 v[NITER];
+#pragma unroll
+    for (int i = 0; i < NITER; ++i) v[i] = src[i * 32 + lane];
+    __syncwarp();                                   // every lane has its values: the stage can be refilled
+    if (lane == 0) {
+      const long long nr = row + (long long)kLnStages * stride;
+      if (nr < M) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        ln_bulk_g2s(ring + st * C, x + nr * C, kRowBytes, &bars[st]);
+      }
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NITER; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float mean = sum * (1.0f / (float)C);
+    float var = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NITER; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      var += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) var += __shfl_xor_sync(0xffffffffu, var, off);
+    const float rstd = rsqrtf(var * (1.0f / (float)C) + eps);
+    const int img0 = (int)(row / tokens_per_img);
+    const int img = slot_map != nullptr ? __ldg(slot_map + img0) : img0;
+    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)img * ld_mod);
+    const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)img * ld_mod);
+    uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * C);
+#pragma unroll
+    for (int i = 0; i < NITER; ++i) {
+      const float4 s4 = __ldg(sc + i * 32 + lane), h4 = __ldg(sh + i * 32 + lane);
+      const float y0 = (v[i].x - mean) * rstd * (1.0f + s4.x) + h4.x;
+      const float y1 = (v[i].y - mean) * rstd * (1.0f + s4.y) + h4.y;
+      const float y2 = (v[i].z - mean) * rstd * (1.0f + s4.z) + h4.z;
+      const float y3 = (v[i].w - mean) * rstd * (1.0f + s4.w) + h4.w;
+      o[i * 32 + lane] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    }
+  }
+}
+
 __global__ void silu_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
@@ -153,6 +254,26 @@ extern "C" int sdvar_ln_modulate(const float* x, int M, int C, int tokens_per_im
   const size_t smem = (size_t)kLnWarps * C * sizeof(float);
   SDVAR_REQUIRE(smem <= 48 * 1024, "C=%d too large for ln_modulate", C);
   ProfileScope prof((cudaStream_t)stream, FAM_LN, (double)M * C * 6.0);
+  // large M: persistent TMA-ring kernel (same arithmetic, same per-row order => bit-identical output)
+  static const int tma_min_rows = [] { const char* e = getenv("SDVAR_LN_TMA_MIN"); return e ? atoi(e) : 4096; }();
+  if (M >= tma_min_rows && ((uintptr_t)x & 15) == 0) {
+    const int sms = sm_count();
+    const int grid = (M + 7) / 8 < sms ? (M + 7) / 8 : sms;
+#define SDVAR_LN_TMA(NITER)                                                                                              \
+  case NITER * 128: {                                                                                                    \
+    const size_t smem = (size_t)8 * kLnStages * NITER * 128 * 4 + 8 * kLnStages * 8;                                     \
+    SDVAR_SET_SMEM_ONCE(ln_modulate_tma_kernel<NITER>, smem);                                                            \
+    ln_modulate_tma_kernel<NITER><<<grid, 256, smem, (cudaStream_t)stream>>>(x, M, tokens_per_img, scale, shift, ld_mod, slot_map, eps, \
+                                                                           reinterpret_cast<__nv_bfloat16*>(out));     \
+    SDVAR_LAUNCH_CHECK();                                                                                                \
+    return SDVAR_OK;                                                                                                     \
+  }
+    switch (C) {
+      SDVAR_LN_TMA(8) SDVAR_LN_TMA(10) SDVAR_LN_TMA(12) SDVAR_LN_TMA(15) SDVAR_LN_TMA(18)
+      default: break;
+    }
+#undef SDVAR_LN_TMA
+  }
 #define SDVAR_LN_REG(NITER)                                                                                              \
   case NITER * 128:                                                                                                      \
     ln_modulate_reg_kernel<NITER><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, M, tokens_per_img, scale, shift, ld_mod, slot_map, eps, \
