@@ -376,7 +376,7 @@ def main():
         for fam, (ms, work, n) in prof.items():
             if n == 0:
                 continue
-            if fam in ("gemm", "attention"):
+            if fam in ("gemm", "attention", "conv"):
                 kern[fam] = {"bound": "tensor", "achieved": work / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms": ms, "launches": n}
             else:
                 extra = st["rejected_tokens"] * 4096 * 4.0 if fam == "verify" else 0.0   # resample noise is read only on reject

@@ -211,6 +211,14 @@ int sdvar_groupnorm_silu_nhwc(const sdvar_bf16* x, const float* pre_bias, int N,
  * rows = N*H*W pixels, C % 8 == 0, channels-last bf16; res may be NULL; out may alias h or res. */
 int sdvar_bias_residual_nhwc(const sdvar_bf16* h, const float* bias, const sdvar_bf16* res, long long rows, int C, sdvar_bf16* out,
                              void* stream);
+/* Decoder convolution as a tcgen05 implicit GEMM (replaces nn.Conv2d(k=3,padding=1) / nn.Conv2d(k=1) at models/basic_vae.py:22-27,
+ * 44-52, 75-76, 171-196, models/vqvae.py:38-39).  x (N,H,W,Cin) channels-last bf16, Cin % 32 == 0; w_packed (taps, Cout, Cin) bf16
+ * = weight.permute(2,3,0,1) of the (Cout,Cin,kh,kw) parameter, taps = 9 or 1; bias fp32 [Cout] or NULL; res (N,H,W,Cout) bf16 skip
+ * connection or NULL.  Exactly one output: y (N,H,W,Cout) bf16 (Cout % 8 == 0), or y_f32_nchw (N,Cout,H,W) fp32 clamped to
+ * [lo,hi] (conv_out + the clamp of models/vqvae.py:63).  128 consecutive pixels in (n,y,x) order must form a box: W divides 128
+ * or is a multiple of it, H likewise for the rows left.  Zero padding comes from the TMA unit's out-of-bounds fill. */
+int sdvar_conv_nhwc(const sdvar_bf16* x, int N, int H, int W, int Cin, const sdvar_bf16* w_packed, int taps, int Cout,
+                    const float* bias, const sdvar_bf16* res, sdvar_bf16* y, float* y_f32_nchw, float lo, float hi, void* stream);
 /* nearest-neighbour 2x upsampling (models/basic_vae.py:31), channels-last bf16: x (N,H,W,C) -> y (N,2H,2W,C). */
 int sdvar_upsample2x_nhwc(const sdvar_bf16* x, int N, int H, int W, int C, sdvar_bf16* y, void* stream);
 
@@ -264,7 +272,7 @@ int sdvar_var_forward(const sdvar_var_weights* w_host, const sdvar_pass* pass_ho
  * sdvar_profile_begin() every entry point brackets its launches with a cudaEvent pair on the launch stream;
  * sdvar_profile_end() synchronises the device and returns, per family, the summed milliseconds, the summed
  * ALGORITHMIC work (FLOPs for GEMM/ATTN, bytes for the others, as defined in DESIGN.md) and the launch count. */
-#define SDVAR_PROFILE_FAMILIES 8 /* 0 GEMM, 1 ATTN, 2 LN, 3 SAMPLE, 4 VERIFY, 5 VQ, 6 EMBED, 7 MISC */
+#define SDVAR_PROFILE_FAMILIES 9 /* 0 GEMM, 1 ATTN, 2 LN, 3 SAMPLE, 4 VERIFY, 5 VQ, 6 EMBED, 7 MISC, 8 CONV */
 int sdvar_profile_begin(void);
 int sdvar_profile_end(double* ms, double* work, long long* launches);
 

@@ -24,10 +24,10 @@ EXPORTS = [
     "sdvar_sample_cfg_topk_topp", "sdvar_verify_accept_resample", "sdvar_verify_workspace_bytes", "sdvar_verify_top1", "sdvar_vq_next_input", "sdvar_vq_area_down",
     "sdvar_embed_next_map", "sdvar_first_map", "sdvar_ln_modulate", "sdvar_silu_bf16", "sdvar_f32_to_bf16", "sdvar_image_to_u8",
     "sdvar_gemm_bf16", "sdvar_attention", "sdvar_var_forward", "sdvar_profile_begin", "sdvar_profile_end",
-    "sdvar_groupnorm_silu_nhwc", "sdvar_bias_residual_nhwc", "sdvar_upsample2x_nhwc", "sdvar_vq_nearest_code",
+    "sdvar_groupnorm_silu_nhwc", "sdvar_conv_nhwc", "sdvar_bias_residual_nhwc", "sdvar_upsample2x_nhwc", "sdvar_vq_nearest_code",
     "sdvar_debug_spec_expf",
 ]
-PROFILE_FAMILIES = ("gemm", "attention", "ln_modulate", "sample", "verify", "vq", "embed", "misc")
+PROFILE_FAMILIES = ("gemm", "attention", "ln_modulate", "sample", "verify", "vq", "embed", "misc", "conv")
 
 
 class SdvarError(RuntimeError):
@@ -239,6 +239,13 @@ def groupnorm_silu_nhwc(x, N, HW, Cc, gamma, beta, eps, silu, y, scratch, pre_bi
 def bias_residual_nhwc(h, bias, res, rows, Cc, out):
     _check(lib().sdvar_bias_residual_nhwc(C.c_void_p(h.data_ptr()), ptr(bias), C.c_void_p(res.data_ptr() if res is not None else 0), C.c_longlong(rows), Cc,
                                           C.c_void_p(out.data_ptr()), stream_ptr()), "sdvar_bias_residual_nhwc")
+
+
+def conv_nhwc(x, N, H, W, Cin, w_packed, taps, Cout, bias, res, y=None, y_f32_nchw=None, lo=-1.0, hi=1.0):
+    """tcgen05 implicit-GEMM convolution (3x3 padding 1, or 1x1) on channels-last bf16; see include/sdvar_b200.h"""
+    vp = lambda t: C.c_void_p(t.data_ptr() if t is not None else 0)
+    _check(lib().sdvar_conv_nhwc(vp(x), N, H, W, Cin, vp(w_packed), taps, Cout, ptr(bias), vp(res), vp(y), ptr(y_f32_nchw),
+                                 C.c_float(lo), C.c_float(hi), stream_ptr()), "sdvar_conv_nhwc")
 
 
 def upsample2x_nhwc(x, N, H, W, Cc, y):

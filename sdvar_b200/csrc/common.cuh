@@ -62,7 +62,7 @@ int sm_count();    // multiprocessor count of the current device (cached per thr
 
 // ---- optional per-family device timing (bench.py's roofline leg).  Disabled by default: zero overhead on the
 // product path.  When enabled every entry point brackets its launches with a cudaEvent pair on the launch stream.
-enum Family { FAM_GEMM = 0, FAM_ATTN = 1, FAM_LN = 2, FAM_SAMPLE = 3, FAM_VERIFY = 4, FAM_VQ = 5, FAM_EMBED = 6, FAM_MISC = 7, FAM_COUNT = 8 };
+enum Family { FAM_GEMM = 0, FAM_ATTN = 1, FAM_LN = 2, FAM_SAMPLE = 3, FAM_VERIFY = 4, FAM_VQ = 5, FAM_EMBED = 6, FAM_MISC = 7, FAM_CONV = 8, FAM_COUNT = 9 };
 struct ProfileScope {
   ProfileScope(cudaStream_t st, int family, double work);
   ~ProfileScope();

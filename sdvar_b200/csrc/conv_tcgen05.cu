@@ -1,0 +1,344 @@
+// conv_tcgen05.cu -- decoder convolutions as an implicit GEMM on tcgen05, channels-last bf16.
+//
+// Replaces nn.Conv2d(k=3, padding=1) / nn.Conv2d(k=1) of the VQVAE decoder (reference models/basic_vae.py:18-61, 163-226,
+// models/vqvae.py:62-63).  out[p, co] = sum_{tap, ci} x[p + off(tap), ci] * w[tap, co, ci]  (+ bias[co]) (+ res[p, co]).
+//
+//   M = N*H*W output pixels, N = Cout, K = taps * Cin.  No im2col: the A operand of K block (tap, 32-channel chunk) is ONE
+//   4-D TMA box over the activation (C, W, H, N) shifted by the tap offset -- out-of-image coordinates are zero-filled by the
+//   TMA unit, which IS the convolution's zero padding.  Cin of the decoder is 32/160/320/640: multiples of 32, not of 64, so
+//   the K blocks are 32 channels wide and the tiles use SWIZZLE_64B (64-byte rows, 8-row groups of 512 bytes).
+//   A CTA pair owns 256 consecutive pixels x BN output channels (tcgen05.mma.cta_group::2, M=256): each CTA loads its own
+//   128 pixels and HALF of the weight tile per K block, accumulators (2 x BN fp32 columns) live in tensor memory so the
+//   epilogue of tile i overlaps the main loop of tile i+1.  Cout of the decoder is 160/320/640 = 1/2/4 tiles of BN = 160.
+//   Epilogue (8 warps per CTA): tcgen05.ld -> + bias -> + skip connection (bf16) -> bf16 channels-last, or, for conv_out,
+//   clamp -> fp32 NCHW image.  Same barrier protocol as gemm2_tcgen05.cu.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace sdvar {
+namespace conv {
+
+constexpr int BM = 128;                 // pixels per CTA (256 per cluster tile)
+constexpr int KC = 32, UMMA_K = 16;     // channels per K block
+constexpr int kAccStages = 2;
+constexpr int A_BYTES = BM * KC * 2;    // 8 KiB
+constexpr int kThreads = 384;           // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kBarBytes = 512;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+
+template <int BN>
+struct Cfg {
+  static constexpr int b_bytes = (BN / 2) * KC * 2;
+  static constexpr int b_stride = (b_bytes + 1023) & ~1023;
+  static constexpr int stage_bytes = A_BYTES + b_stride;
+  static constexpr int stages = (200 * 1024 / stage_bytes) > 16 ? 16 : (200 * 1024 / stage_bytes);
+  static constexpr int tmem_cols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static constexpr size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + kBarBytes;
+};
+
+struct Params {
+  int Nimg, H, W, Cin, Cout, taps;      // taps: 9 (3x3, padding 1) or 1
+  int BW, BH;                           // pixel box of one CTA: BW x BH x (128 / (BW*BH)) images
+  long long M;                          // Nimg * H * W
+  const float* bias;                    // nullable
+  const __nv_bfloat16* res;             // nullable, (M, Cout)
+  __nv_bfloat16* out_bf16;              // (M, Cout) channels-last, or
+  float* out_f32_nchw;                  // (Nimg, Cout, H, W) with clamp
+  float lo, hi;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_leader(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(ptx::smem_u32(bar) & kPeerMask), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ptx::smem_u32(bar) & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   ptx::smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// K-major operand tile written by TMA with SWIZZLE_64B: rows of 64 bytes (32 bf16), 8-row groups 512 bytes apart;
+// descriptor version 1, layout type SWIZZLE_64B = 4 (cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+  using C = Cfg<BN>;
+  constexpr int kStages = C::stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * C::stage_bytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* tfull = empty + kStages;
+  uint64_t* tempty = tfull + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
+  static_assert((2 * 16 + 2 * kAccStages) * 8 + 4 <= kBarBytes, "barrier region");
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_n = (p.Cout + BN - 1) / BN;
+  const long long num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const long long num_tiles = num_m * num_n;
+  const int chunks = p.Cin / KC;
+  const int kblocks = p.taps * chunks;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int HW = p.H * p.W;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&full[i], 2); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kAccStages; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 2 * kEpiWarps); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(tmem_slot, C::tmem_cols);
+  ptx::tc_fence_before();
+  cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = cluster_id; t < num_tiles; t += num_clusters) {
+        const long long mb = t / num_n;
+        const int nb = (int)(t - mb * num_n);
+        const long long p0 = (mb * 2 + rank) * BM;             // this CTA's 128 pixels
+        const int n0 = (int)(p0 / HW), rem = (int)(p0 - (long long)n0 * HW);
+        const int y0 = rem / p.W, x0 = rem - y0 * p.W;
+        const int col0 = nb * BN + (int)rank * (BN / 2);       // this CTA's half of the weight tile
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          for (int cc = 0; cc < chunks; ++cc) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * C::stage_bytes;
+            mbar_expect_tx_leader(&full[stage], A_BYTES + C::b_bytes);
+            tma_load_4d_pair(sa, &tmA, &full[stage], cc * KC, x0 + dx, y0 + dy, n0);
+            tma_load_3d_pair(sa + A_BYTES, &tmB, &full[stage], cc * KC, col0, tap);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (long long t = cluster_id; t < num_tiles; t += num_clusters) {
+        ptx::mbar_wait(&tempty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + (size_t)stage * C::stage_bytes);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < KC / UMMA_K; ++k)
+            umma2_f16(d, umma_desc_k_sw64(a_addr + k * UMMA_K * 2), umma_desc_k_sw64(b_addr + k * UMMA_K * 2), idesc,
+                      (uint32_t)((kb | k) != 0));
+          umma2_commit_mc(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma2_commit_mc(&tfull[as]);
+        if (++as == kAccStages) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp & 3;                    // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;           // column half of the tile
+    constexpr int nch = BN / 16, nch0 = (nch + 1) / 2;
+    const int cbeg = half == 0 ? 0 : nch0, cend = half == 0 ? nch0 : nch;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long long t = cluster_id; t < num_tiles; t += num_clusters) {
+      const long long mb = t / num_n;
+      const int nb = (int)(t - mb * num_n);
+      const long long row = (mb * 2 + rank) * BM + ew * 32 + lane;
+      const bool rv = row < p.M;
+      ptx::mbar_wait(&tfull[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+      for (int c = cbeg; c < cend; ++c) {
+        const int col = nb * BN + c * 16;
+        uint32_t r[16];
+        tmem_ld_32x16(taddr + c * 16, r);
+        uint4 rs[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        const bool cv0 = rv && col < p.Cout, cv1 = rv && col + 8 < p.Cout;
+        if (p.res != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + row * p.Cout + col);
+          if (cv0) rs[0] = __ldg(rp);
+          if (cv1) rs[1] = __ldg(rp + 1);
+        }
+        ptx::tmem_ld_wait();
+        if (cv0) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col + j < p.Cout) v[j] += __ldg(p.bias + col + j);
+          }
+          if (p.out_bf16 != nullptr) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rs);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[2 * j] += __uint_as_float(rw[j] << 16);
+              v[2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.Cout + col);
+            op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            if (cv1)
+              op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          } else {
+            const long long n = row / HW;
+            const long long pix = row - n * HW;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col + j < p.Cout) p.out_f32_nchw[(n * p.Cout + col + j) * HW + pix] = fminf(fmaxf(v[j], p.lo), p.hi);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty[as]);
+      if (++as == kAccStages) { as = 0; aphase ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  cluster_sync_all();   // the peer may still be reading this CTA's shared memory / signalling its barriers
+  if (warp == 2) tmem_dealloc2(tmem_base, C::tmem_cols);
+}
+
+template <int BN>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t st) {
+  SDVAR_SET_SMEM_ONCE(conv_kernel<BN>, Cfg<BN>::smem_bytes);
+  const int sms = sm_count();
+  const long long tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.Cout + BN - 1) / BN);
+  const int clusters = tiles < sms / 2 ? (int)tiles : sms / 2;
+  conv_kernel<BN><<<2 * clusters, kThreads, Cfg<BN>::smem_bytes, st>>>(tmA, tmB, p);
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
+}
+
+}  // namespace conv
+}  // namespace sdvar
+
+using namespace sdvar;
+
+extern "C" int sdvar_conv_nhwc(const sdvar_bf16* x, int N, int H, int W, int Cin, const sdvar_bf16* w_packed, int taps, int Cout,
+                               const float* bias, const sdvar_bf16* res, sdvar_bf16* y, float* y_f32_nchw, float lo, float hi,
+                               void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(x && w_packed && ((y != nullptr) != (y_f32_nchw != nullptr)), "NULL argument, or not exactly one output");
+  SDVAR_REQUIRE(taps == 9 || taps == 1, "taps=%d (3x3 with padding 1, or 1x1)", taps);
+  SDVAR_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cin % conv::KC == 0 && Cout > 0, "bad geometry N=%d H=%d W=%d Cin=%d Cout=%d", N, H, W,
+                Cin, Cout);
+  SDVAR_REQUIRE(y == nullptr || Cout % 8 == 0, "channels-last bf16 output needs Cout %% 8 == 0 (Cout=%d)", Cout);
+  SDVAR_REQUIRE(y_f32_nchw == nullptr || res == nullptr, "the NCHW fp32 output takes no skip connection");
+  SDVAR_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)res & 15) == 0,
+                "16-byte alignment");
+  // pixel box of one CTA: 128 consecutive pixels in (n, y, x) order must be a box BW x BH x BI
+  const int BW = W < conv::BM ? W : conv::BM;
+  SDVAR_REQUIRE(W % BW == 0 && conv::BM % BW == 0, "W=%d must divide or be a multiple of %d", W, conv::BM);
+  const int BH = H < conv::BM / BW ? H : conv::BM / BW;
+  SDVAR_REQUIRE(H % BH == 0 && (conv::BM / BW) % BH == 0, "H=%d does not tile into %d-pixel boxes of width %d", H, conv::BM, BW);
+  const int BI = conv::BM / (BW * BH);
+  cudaStream_t st = (cudaStream_t)stream;
+  conv::Params p;
+  p.Nimg = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.BW = BW; p.BH = BH;
+  p.M = (long long)N * H * W;
+  p.bias = bias;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res);
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(y);
+  p.out_f32_nchw = y_f32_nchw;
+  p.lo = lo; p.hi = hi;
+  const int BN = Cout % 160 == 0 ? 160 : Cout >= 128 ? 128 : Cout > 16 ? 32 : 16;
+  CUtensorMap tmA, tmB;
+  const uint64_t dimsA[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  const uint64_t strA[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  const uint32_t boxA[4] = {(uint32_t)conv::KC, (uint32_t)BW, (uint32_t)BH, (uint32_t)BI};
+  if (int rc = make_tmap_bf16_sw64(&tmA, x, 4, dimsA, strA, boxA)) return rc;
+  const uint64_t dimsB[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)taps};
+  const uint64_t strB[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+  const uint32_t boxB[3] = {(uint32_t)conv::KC, (uint32_t)(BN / 2), 1u};
+  if (int rc = make_tmap_bf16_sw64(&tmB, w_packed, 3, dimsB, strB, boxB)) return rc;
+  ProfileScope prof(st, FAM_CONV, 2.0 * (double)p.M * Cout * Cin * taps);
+  switch (BN) {
+    case 160: return conv::launch<160>(tmA, tmB, p, st);
+    case 128: return conv::launch<128>(tmA, tmB, p, st);
+    case 32: return conv::launch<32>(tmA, tmB, p, st);
+    default: return conv::launch<16>(tmA, tmB, p, st);
+  }
+}

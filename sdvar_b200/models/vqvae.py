@@ -1,9 +1,11 @@
 """VQVAE, inference side: quantizer (K5 kernels) + decoder.
 
 The decoder (``fhat_to_img``, reference models/vqvae.py:62-63 + models/basic_vae.py:163-226) is NOT one of the
-four north-star kernel families; it is the boundary right after the path and runs here through
-cuDNN convolutions (library code, bias-free) in bf16 channels-last; GroupNorm+SiLU, bias+skip adds and the 2x upsampling are
-libsdvar kernels.  Parameter names follow the reference checkpoint
+four north-star kernel families; it is the boundary right after the path.  It runs in bf16 channels-last:
+every 3x3 / 1x1 convolution is the libsdvar tcgen05 implicit-GEMM kernel (``sdvar_conv_nhwc``: bias, skip connection and, for
+``conv_out``, the clamp + fp32 NCHW image fused into its epilogue); GroupNorm+SiLU and the 2x upsampling are libsdvar kernels
+too.  Shapes the kernel does not tile (input channels not a multiple of 32, widths that do not divide 128) and the encoder
+fall back to cuDNN (library code).  Parameter names follow the reference checkpoint
 (``decoder.*``, ``post_quant_conv.*``, ``quantize.*``); the encode side (``encoder.*``, ``quant_conv.*``) is
 created when asked for or when a state dict that carries it (a real ``vae_ch160v4096z32.pth``) is loaded.
 """
@@ -37,13 +39,59 @@ def _bias32(conv: nn.Conv2d) -> torch.Tensor:
     return conv._b32
 
 
+def _packed_w(conv: nn.Conv2d) -> torch.Tensor:
+    """(taps, Cout, Cin) bf16: the K-major B operand of the implicit GEMM, one (Cout, Cin) matrix per filter tap"""
+    w = conv.weight
+    if getattr(conv, "_wp", None) is None or conv._wp.device != w.device or conv._wp_ver != w._version:
+        co, ci, kh, kw = w.shape
+        conv._wp = w.detach().permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16).contiguous()
+        conv._wp_ver = w._version
+    return conv._wp
+
+
+def _tc_ok(conv: nn.Conv2d, x: torch.Tensor, nchw_f32: bool = False) -> bool:
+    """shapes sdvar_conv_nhwc tiles (include/sdvar_b200.h): 3x3 padding 1 or 1x1, stride 1, Cin % 32 == 0, and 128 consecutive
+    pixels form a box of the image"""
+    if not _fast(x) or conv.stride != (1, 1) or conv.groups != 1 or conv.dilation != (1, 1):
+        return False
+    if not ((conv.kernel_size == (3, 3) and conv.padding == (1, 1)) or (conv.kernel_size == (1, 1) and conv.padding == (0, 0))):
+        return False
+    _, ci, H, W = x.shape
+    if ci % 32 or (conv.out_channels % 8 and not nchw_f32):
+        return False
+    bw = min(W, 128)
+    if W % bw or 128 % bw:
+        return False
+    bh = min(H, 128 // bw)
+    return H % bh == 0 and (128 // bw) % bh == 0
+
+
+def _conv_tc(conv: nn.Conv2d, x: torch.Tensor, bias: bool, res=None, image_out: bool = False) -> torch.Tensor:
+    from .. import _cabi
+    N, ci, H, W = x.shape
+    co = conv.out_channels
+    taps = conv.kernel_size[0] * conv.kernel_size[1]
+    b = _bias32(conv) if bias and conv.bias is not None else None
+    if image_out:
+        y = torch.empty((N, co, H, W), device=x.device, dtype=torch.float32)
+        _cabi.conv_nhwc(x, N, H, W, ci, _packed_w(conv), taps, co, b, None, y_f32_nchw=y, lo=-1.0, hi=1.0)
+    else:
+        y = torch.empty((N, co, H, W), device=x.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+        _cabi.conv_nhwc(x, N, H, W, ci, _packed_w(conv), taps, co, b, res, y=y)
+    return y
+
+
 def _conv_nobias(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    if _tc_ok(conv, x):
+        return _conv_tc(conv, x, bias=False)
     return F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
 
 
 def _conv_bias_res(conv: nn.Conv2d, x: torch.Tensor, res=None) -> torch.Tensor:
-    """conv(x) + bias (+ res).  Device path: bias-free cuDNN convolution, then ONE libsdvar pass adds bias and skip connection in
-    place (cuDNN's own bias is a separate un-vectorised broadcast kernel, and the skip add a third pass)."""
+    """conv(x) + bias (+ res).  Device path: the tcgen05 convolution with bias and skip connection in its epilogue.  Shapes it does
+    not tile: bias-free cuDNN convolution, then ONE libsdvar pass adds bias and skip connection in place."""
+    if _tc_ok(conv, x) and (res is None or (_fast(res) and res.shape[1] == conv.out_channels and res.shape[2:] == x.shape[2:])):
+        return _conv_tc(conv, x, bias=True, res=res)
     if _fast(x) and conv.out_channels % 8 == 0:
         h = _conv_nobias(conv, x)
         if _fast(h) and (res is None or (_fast(res) and res.shape == h.shape)):
@@ -92,7 +140,7 @@ class _Res(nn.Module):
             b = _gn_act(self.norm2, _conv_nobias(self.conv1, a), True, pre_bias=_bias32(self.conv1))
         else:
             b = _gn_act(self.norm2, self.conv1(a), True)
-        return _conv_bias_res(self.conv2, b, self.nin_shortcut(x) if hasattr(self, "nin_shortcut") else x)
+        return _conv_bias_res(self.conv2, b, _conv_bias_res(self.nin_shortcut, x) if hasattr(self, "nin_shortcut") else x)
 
 
 class _SpatialAttn(nn.Module):
@@ -102,7 +150,14 @@ class _SpatialAttn(nn.Module):
 
     def forward(self, x):
         B, C, H, W = x.shape
-        q, k, v = self.qkv(_gn_act(self.norm, x, False)).reshape(B, 3, C, H * W).unbind(1)
+        a = _gn_act(self.norm, x, False)
+        if _tc_ok(self.qkv, a) and _tc_ok(self.proj_out, a):
+            # channels-last all the way: qkv (B, HW, 3C) is read in place as three strided (B, HW, C) views
+            t = _conv_bias_res(self.qkv, a).permute(0, 2, 3, 1).reshape(B, H * W, 3, C)
+            o = F.scaled_dot_product_attention(t[:, None, :, 0], t[:, None, :, 1], t[:, None, :, 2], scale=C ** -0.5)
+            o = o.reshape(B, H, W, C).permute(0, 3, 1, 2)          # a channels-last (B, C, H, W) view of the contiguous result
+            return _conv_bias_res(self.proj_out, o, res=x)
+        q, k, v = self.qkv(a).reshape(B, 3, C, H * W).unbind(1)
         o = F.scaled_dot_product_attention(q.transpose(1, 2).unsqueeze(1), k.transpose(1, 2).unsqueeze(1),
                                            v.transpose(1, 2).unsqueeze(1), scale=C ** -0.5)   # softmax(q k^T / sqrt(C)) v
         return x + self.proj_out(o.squeeze(1).transpose(1, 2).reshape(B, C, H, W))
@@ -168,7 +223,10 @@ class Decoder(nn.Module):
         h = self.mid(_conv_bias_res(self.conv_in, z))
         for lv in reversed(range(len(self.up))):
             h = self.up[lv](h)
-        return self.conv_out(_gn_act(self.norm_out, h, True))
+        a = _gn_act(self.norm_out, h, True)
+        if _tc_ok(self.conv_out, a, nchw_f32=True):
+            return _conv_tc(self.conv_out, a, bias=True, image_out=True)      # fp32 NCHW, already clamped to [-1, 1]
+        return self.conv_out(a)
 
 
 class _Down(nn.Module):
@@ -271,7 +329,9 @@ class VQVAE(nn.Module):
             return self.decoder(self.post_quant_conv(f_hat.float())).clamp_(-1, 1)
         mods = self._decoder_exec()
         x = f_hat.to(self.decoder_dtype).contiguous(memory_format=torch.channels_last)
-        return mods(x).float().clamp_(-1, 1)
+        y = _conv_bias_res(mods[0], x) if _tc_ok(mods[0], x) else mods[0](x)
+        img = mods[1](y)
+        return img if img.dtype == torch.float32 else img.float().clamp_(-1, 1)   # conv_out's epilogue already clamped
 
     def idxBl_to_img(self, ms_idx_Bl: List[torch.Tensor], same_shape: bool = True, last_one: bool = False):
         """models/vqvae.py:69-76: decode token pyramids (same_shape=True only)."""

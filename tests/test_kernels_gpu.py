@@ -386,6 +386,66 @@ def test_bias_residual_and_upsample_nhwc(cuda_lib, N, C, H, W, with_res):
     assert torch.equal(y, torch.nn.functional.interpolate(h, scale_factor=2.0, mode="nearest"))
 
 
+@pytest.mark.parametrize("N,Cin,Cout,H,W,taps,with_res,with_bias", [
+    (2, 160, 160, 64, 64, 9, True, True),      # BN=160, W < 128: two rows per CTA
+    (1, 160, 160, 8, 256, 9, False, True),     # W > 128: two CTA boxes per row
+    (3, 640, 640, 16, 16, 9, True, False),     # four N tiles, one cluster tile per image
+    (2, 320, 160, 32, 32, 9, False, True),
+    (2, 640, 320, 32, 32, 1, False, True),     # nin_shortcut (1x1)
+    (2, 32, 640, 16, 16, 9, False, True),      # conv_in: one 32-channel chunk per tap
+    (2, 32, 32, 16, 16, 9, False, True),       # post_quant_conv, BN=32
+    (5, 64, 128, 4, 4, 9, True, True),         # toy decoder: 8 images per CTA box, ragged last tile, BN=128
+    (2, 128, 64, 8, 8, 9, True, True),         # BN=32, two N tiles
+    (1, 640, 1920, 16, 16, 1, False, True),    # decoder attention qkv (1x1)
+])
+def test_conv_nhwc_tcgen05_vs_torch(cuda_lib, N, Cin, Cout, H, W, taps, with_res, with_bias):
+    """decoder convolution (tcgen05 implicit GEMM, TMA zero-fill as padding) vs torch fp32 conv2d on the same bf16 operands
+    (reference nn.Conv2d at models/basic_vae.py:22-27,44-52,171-196): bf16 output = one rounding of the fp32 result"""
+    k = 3 if taps == 9 else 1
+    x = hashed("cv.x", Cin + H, (N, Cin, H, W), 1.0).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = hashed("cv.w", Cout, (Cout, Cin, k, k), 1.0 / math.sqrt(Cin * taps)).to(DEV).bfloat16()
+    b = hashed("cv.b", 2, (Cout,), 0.5).to(DEV) if with_bias else None
+    r = hashed("cv.r", 3, (N, Cout, H, W), 1.0).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last) if with_res else None
+    wp = w.permute(2, 3, 0, 1).reshape(taps, Cout, Cin).contiguous()
+    y = torch.full((N, Cout, H, W), float("nan"), device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    cuda_lib.conv_nhwc(x, N, H, W, Cin, wp, taps, Cout, b, r, y=y)
+    torch.cuda.synchronize()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        ref = torch.nn.functional.conv2d(x.float(), w.float(), b, padding=k // 2)
+    if with_res:
+        ref = ref + r.float()
+    err = (y.float() - ref).abs()
+    assert bool(torch.isfinite(y.float()).all())
+    assert float(err.max()) < 2 ** -7 * float(ref.abs().max()) + 1e-3, (float(err.max()), float(ref.abs().max()))
+    assert float(err.mean()) < 2e-3 * float(ref.abs().mean()) + 1e-5
+
+
+@pytest.mark.parametrize("N,Cin,H,W", [(2, 160, 32, 128), (3, 32, 16, 16)])
+def test_conv_nhwc_image_epilogue(cuda_lib, N, Cin, H, W):
+    """conv_out: 3 output channels, fp32 NCHW image clamped to [-1, 1] straight from the epilogue (models/vqvae.py:63)"""
+    x = hashed("cvo.x", Cin, (N, Cin, H, W), 1.0).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = hashed("cvo.w", 1, (3, Cin, 3, 3), 3.0 / math.sqrt(Cin * 9)).to(DEV).bfloat16()
+    b = hashed("cvo.b", 2, (3,), 0.5).to(DEV)
+    y = torch.full((N, 3, H, W), float("nan"), device=DEV)
+    cuda_lib.conv_nhwc(x, N, H, W, Cin, w.permute(2, 3, 0, 1).reshape(9, 3, Cin).contiguous(), 9, 3, b, None, y_f32_nchw=y, lo=-1.0, hi=1.0)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        ref = torch.nn.functional.conv2d(x.float(), w.float(), b, padding=1).clamp_(-1, 1)
+    assert float(ref.abs().max()) == 1.0          # the clamp is exercised
+    assert torch.allclose(y, ref, rtol=0, atol=2e-5), float((y - ref).abs().max())
+
+
+def test_conv_nhwc_rejects_untiled_shapes(cuda_lib):
+    from sdvar_b200._cabi import SdvarError
+    x = torch.zeros(1, 24, 16, 16, device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.zeros(1, 32, 16, 16, device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with pytest.raises(SdvarError):
+        cuda_lib.conv_nhwc(x, 1, 16, 16, 24, torch.zeros(9, 32, 24, device=DEV, dtype=torch.bfloat16), 9, 32, None, None, y=y)
+    x = torch.zeros(1, 32, 12, 12, device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.zeros(1, 32, 12, 12, device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with pytest.raises(SdvarError):
+        cuda_lib.conv_nhwc(x, 1, 12, 12, 32, torch.zeros(9, 32, 32, device=DEV, dtype=torch.bfloat16), 9, 32, None, None, y=y)
+
+
 # ---- encode side (SURVEY.md 8f #3) ------------------------------------------------------------------------------------
 def test_vq_nearest_code_bit_exact_vs_c_spec(cuda_lib):
     """sdvar_vq_nearest_code vs oracle/spec_c:sdvar_spec_nearest_code: identical indices on random rows (ragged N), on rows
