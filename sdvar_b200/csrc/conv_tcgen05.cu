@@ -12,6 +12,8 @@
 //   epilogue of tile i overlaps the main loop of tile i+1.  Cout of the decoder is 160/320/640 = 1/2/4 tiles of BN = 160.
 //   Epilogue (8 warps per CTA): tcgen05.ld -> + bias -> + skip connection (bf16) -> bf16 channels-last, or, for conv_out,
 //   clamp -> fp32 NCHW image.  Same barrier protocol as gemm2_tcgen05.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -113,6 +115,19 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;
   return d;
 }
+// rows of ROWB = 64 (SWIZZLE_64B) or 128 bytes (SWIZZLE_128B), 8-row groups 8*ROWB apart.  The start address may be ANY row of a
+// TMA-written tile (base_offset stays 0): the tensor core swizzles on the absolute shared-memory address bits, exactly like the
+// TMA unit that wrote the tile (checked on a B200 with tools/ubench/umma_shift.cu for every row shift 0..9, both swizzles).
+template <int ROWB>
+__device__ __forceinline__ uint64_t umma_desc_k_rows(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * ROWB) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;
+  return d;
+}
 // 32 lanes x 16 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -122,6 +137,73 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+
+// Epilogue of both kernels (8 warps per CTA: TMEM lane quarter x column half): tcgen05.ld -> + bias -> + skip connection ->
+// bf16 channels-last, or clamp -> fp32 NCHW.  A thread owns one output pixel; its 16-column chunks are 32-byte stores.
+template <int BN>
+__device__ __forceinline__ void epilogue_loop(const Params& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty, int warp, int lane,
+                                              uint32_t rank, int cluster_id, int num_clusters, long long num_tiles, int num_n, int HW) {
+  const int ew = warp & 3;                    // TMEM lane quarter this warp may read
+  const int half = (warp - 4) >> 2;           // column half of the tile
+  constexpr int nch = BN / 16, nch0 = (nch + 1) / 2;
+  const int cbeg = half == 0 ? 0 : nch0, cend = half == 0 ? nch0 : nch;
+  int as = 0;
+  uint32_t aphase = 0;
+  for (long long t = cluster_id; t < num_tiles; t += num_clusters) {
+    const long long mb = t / num_n;
+    const int nb = (int)(t - mb * num_n);
+    const long long row = (mb * 2 + rank) * BM + ew * 32 + lane;
+    const bool rv = row < p.M;
+    ptx::mbar_wait(&tfull[as], aphase);
+    ptx::tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+    for (int c = cbeg; c < cend; ++c) {
+      const int col = nb * BN + c * 16;
+      uint32_t r[16];
+      tmem_ld_32x16(taddr + c * 16, r);
+      uint4 rs[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      const bool cv0 = rv && col < p.Cout, cv1 = rv && col + 8 < p.Cout;
+      if (p.res != nullptr) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + row * p.Cout + col);
+        if (cv0) rs[0] = __ldg(rp);
+        if (cv1) rs[1] = __ldg(rp + 1);
+      }
+      ptx::tmem_ld_wait();
+      if (cv0) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col + j < p.Cout) v[j] += __ldg(p.bias + col + j);
+        }
+        if (p.out_bf16 != nullptr) {
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rs);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[2 * j] += __uint_as_float(rw[j] << 16);
+            v[2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.Cout + col);
+          op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          if (cv1)
+            op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        } else {
+          const long long n = row / HW;
+          const long long pix = row - n * HW;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col + j < p.Cout) p.out_f32_nchw[(n * p.Cout + col + j) * HW + pix] = fminf(fmaxf(v[j], p.lo), p.hi);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_leader(&tempty[as]);
+    if (++as == kAccStages) { as = 0; aphase ^= 1; }
+  }
 }
 
 template <int BN>
@@ -215,70 +297,174 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp & 3;                    // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;           // column half of the tile
-    constexpr int nch = BN / 16, nch0 = (nch + 1) / 2;
-    const int cbeg = half == 0 ? 0 : nch0, cend = half == 0 ? nch0 : nch;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (long long t = cluster_id; t < num_tiles; t += num_clusters) {
-      const long long mb = t / num_n;
-      const int nb = (int)(t - mb * num_n);
-      const long long row = (mb * 2 + rank) * BM + ew * 32 + lane;
-      const bool rv = row < p.M;
-      ptx::mbar_wait(&tfull[as], aphase);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
-      for (int c = cbeg; c < cend; ++c) {
-        const int col = nb * BN + c * 16;
-        uint32_t r[16];
-        tmem_ld_32x16(taddr + c * 16, r);
-        uint4 rs[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        const bool cv0 = rv && col < p.Cout, cv1 = rv && col + 8 < p.Cout;
-        if (p.res != nullptr) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + row * p.Cout + col);
-          if (cv0) rs[0] = __ldg(rp);
-          if (cv1) rs[1] = __ldg(rp + 1);
-        }
-        ptx::tmem_ld_wait();
-        if (cv0) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col + j < p.Cout) v[j] += __ldg(p.bias + col + j);
-          }
-          if (p.out_bf16 != nullptr) {
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rs);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[2 * j] += __uint_as_float(rw[j] << 16);
-              v[2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
-            }
-            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.Cout + col);
-            op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-            if (cv1)
-              op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-          } else {
-            const long long n = row / HW;
-            const long long pix = row - n * HW;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col + j < p.Cout) p.out_f32_nchw[(n * p.Cout + col + j) * HW + pix] = fminf(fmaxf(v[j], p.lo), p.hi);
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tempty[as]);
-      if (++as == kAccStages) { as = 0; aphase ^= 1; }
-    }
+    epilogue_loop<BN>(p, tmem_base, tfull, tempty, warp, lane, rank, cluster_id, num_clusters, num_tiles, num_n, HW);
   }
   ptx::tc_fence_before();
   cluster_sync_all();   // the peer may still be reading this CTA's shared memory / signalling its barriers
   if (warp == 2) tmem_dealloc2(tmem_base, C::tmem_cols);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Halo-strip kernel for 3x3 convolutions on images at least 128 pixels wide (76 % of the decoder's convolution FLOPs).
+// The generic kernel above re-loads the activation for each of the nine taps: 13 KiB of operands per 160 tensor-core cycles
+// per SM, 9.6 TB/s of L2->SM traffic chip-wide -- it runs at the L2 bandwidth limit with the tensor pipe half idle (ncu:
+// l1tex__m_xbar2l1tex_read_bytes 19.7 GB for a 160->160 layer at 256x256, lts throughput 61 %).  Here a CTA's 128 output pixels lie
+// on ONE image row, and per channel chunk ONE 4-D TMA box brings the three input rows y-1..y+1 with a one-pixel halo on either
+// side (3 x 130 pixels) into shared memory; the nine taps are nine VIEWS of that strip: the UMMA descriptor of tap (dy, dx)
+// simply starts (dy+1)*130 + (dx+1) rows into it.  Activation traffic drops 3x; only the weight tiles stream per tap.
+template <int BN, int KCH>
+struct HaloCfg {
+  static constexpr int rowb = KCH * 2;                              // 64 -> SWIZZLE_64B, 128 -> SWIZZLE_128B
+  static constexpr int strip_px = BM + 2;
+  static constexpr int a_bytes = 3 * strip_px * rowb;
+  static constexpr int a_stride = (a_bytes + 1023) & ~1023;
+  static constexpr int b_bytes = 3 * (BN / 2) * rowb;               // one kernel row: the three dx taps of one dy
+  static constexpr int b_tap = (BN / 2) * rowb;
+  static constexpr int b_stride = (b_bytes + 1023) & ~1023;
+  static constexpr int a_stages = KCH == 32 ? 4 : 2;
+  static constexpr int b_stages = (216 * 1024 - a_stages * a_stride) / b_stride > 16 ? 16 : (216 * 1024 - a_stages * a_stride) / b_stride;
+  static constexpr int tmem_cols = 2 * BN <= 32 ? 32 : 2 * BN <= 256 ? 256 : 512;
+  static constexpr size_t smem_bytes = 1024 + (size_t)a_stages * a_stride + (size_t)b_stages * b_stride + kBarBytes;
+};
+
+template <int BN, int KCH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+  using C = HaloCfg<BN, KCH>;
+  constexpr int kAS = C::a_stages, kBS = C::b_stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)kAS * C::a_stride;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + (size_t)kBS * C::b_stride);
+  uint64_t* a_empty = a_full + kAS;
+  uint64_t* b_full = a_empty + kAS;
+  uint64_t* b_empty = b_full + kBS;
+  uint64_t* tfull = b_empty + kBS;
+  uint64_t* tempty = tfull + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
+  static_assert((2 * 4 + 2 * 16 + 2 * kAccStages) * 8 + 4 <= kBarBytes, "barrier region");
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_n = (p.Cout + BN - 1) / BN;
+  const long long num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const long long num_tiles = num_m * num_n;
+  const int chunks = (p.Cin + KCH - 1) / KCH;     // a ragged last chunk (Cin = 160 with 64-channel chunks) is zero-filled by the TMA unit
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int HW = p.H * p.W;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kAS; ++i) { ptx::mbar_init(&a_full[i], 2); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kBS; ++i) { ptx::mbar_init(&b_full[i], 2); ptx::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < kAccStages; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 2 * kEpiWarps); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(tmem_slot, C::tmem_cols);
+  ptx::tc_fence_before();
+  cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (long long t = cluster_id; t < num_tiles; t += num_clusters) {
+        const long long mb = t / num_n;
+        const int nb = (int)(t - mb * num_n);
+        const long long p0 = (mb * 2 + rank) * BM;             // this CTA's 128 pixels: one image row segment
+        const int n0 = (int)(p0 / HW), rem = (int)(p0 - (long long)n0 * HW);
+        const int y0 = rem / p.W, x0 = rem - y0 * p.W;
+        const int col0 = nb * BN + (int)rank * (BN / 2);
+        for (int cc = 0; cc < chunks; ++cc) {
+          ptx::mbar_wait(&a_empty[as], aph ^ 1);
+          mbar_expect_tx_leader(&a_full[as], C::a_bytes);
+          tma_load_4d_pair(sA + (size_t)as * C::a_stride, &tmA, &a_full[as], cc * KCH, x0 - 1, y0 - 1, n0);
+          if (++as == kAS) { as = 0; aph ^= 1; }
+          for (int ky = 0; ky < 3; ++ky) {                     // weights of one kernel row: (KCH, BN/2, 3 taps) in one box
+            ptx::mbar_wait(&b_empty[bs], bph ^ 1);
+            mbar_expect_tx_leader(&b_full[bs], C::b_bytes);
+            tma_load_3d_pair(sB + (size_t)bs * C::b_stride, &tmB, &b_full[bs], cc * KCH, col0, 3 * ky);
+            if (++bs == kBS) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN);
+      int as = 0, bs = 0, acs = 0;
+      uint32_t aph = 0, bph = 0, acph = 0;
+      for (long long t = cluster_id; t < num_tiles; t += num_clusters) {
+        ptx::mbar_wait(&tempty[acs], acph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acs * BN);
+        for (int cc = 0; cc < chunks; ++cc) {
+          ptx::mbar_wait(&a_full[as], aph);
+          const uint32_t strip = ptx::smem_u32(sA + (size_t)as * C::a_stride);
+          for (int ky = 0; ky < 3; ++ky) {
+            ptx::mbar_wait(&b_full[bs], bph);
+            ptx::tc_fence_after();
+            const uint32_t a_row = strip + (uint32_t)(ky * C::strip_px * C::rowb);
+            const uint32_t b_row = ptx::smem_u32(sB + (size_t)bs * C::b_stride);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+              for (int k = 0; k < KCH / UMMA_K; ++k)
+                umma2_f16(d, umma_desc_k_rows<C::rowb>(a_row + kx * C::rowb + k * UMMA_K * 2),
+                          umma_desc_k_rows<C::rowb>(b_row + kx * C::b_tap + k * UMMA_K * 2), idesc, (uint32_t)((cc | ky | kx | k) != 0));
+            }
+            umma2_commit_mc(&b_empty[bs]);
+            if (++bs == kBS) { bs = 0; bph ^= 1; }
+          }
+          umma2_commit_mc(&a_empty[as]);
+          if (++as == kAS) { as = 0; aph ^= 1; }
+        }
+        umma2_commit_mc(&tfull[acs]);
+        if (++acs == kAccStages) { acs = 0; acph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    epilogue_loop<BN>(p, tmem_base, tfull, tempty, warp, lane, rank, cluster_id, num_clusters, num_tiles, num_n, HW);
+  }
+  ptx::tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc2(tmem_base, C::tmem_cols);
+}
+
+template <int BN, int KCH>
+static int launch_halo(const void* x, const void* w_packed, const Params& p, cudaStream_t st) {
+  using C = HaloCfg<BN, KCH>;
+  CUtensorMap tmA, tmB;
+  const uint64_t dimsA[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Nimg};
+  const uint64_t strA[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.W * p.Cin * 2, (uint64_t)p.H * p.W * p.Cin * 2};
+  const uint32_t boxA[4] = {(uint32_t)KCH, (uint32_t)C::strip_px, 3u, 1u};
+  const uint64_t dimsB[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, 9u};
+  const uint64_t strB[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.Cout * p.Cin * 2};
+  const uint32_t boxB[3] = {(uint32_t)KCH, (uint32_t)(BN / 2), 3u};
+  if (KCH == 32) {
+    if (int rc = make_tmap_bf16_sw64(&tmA, x, 4, dimsA, strA, boxA)) return rc;
+    if (int rc = make_tmap_bf16_sw64(&tmB, w_packed, 3, dimsB, strB, boxB)) return rc;
+  } else {
+    if (int rc = make_tmap_bf16_nd(&tmA, x, 4, dimsA, strA, boxA)) return rc;
+    if (int rc = make_tmap_bf16_nd(&tmB, w_packed, 3, dimsB, strB, boxB)) return rc;
+  }
+  auto kern = conv_halo_kernel<BN, KCH>;
+  SDVAR_SET_SMEM_ONCE(kern, C::smem_bytes);
+  const int sms = sm_count();
+  const long long tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.Cout + BN - 1) / BN);
+  const int clusters = tiles < sms / 2 ? (int)tiles : sms / 2;
+  kern<<<2 * clusters, kThreads, C::smem_bytes, st>>>(tmA, tmB, p);
+  SDVAR_LAUNCH_CHECK();
+  return SDVAR_OK;
 }
 
 template <int BN>
@@ -325,6 +511,14 @@ extern "C" int sdvar_conv_nhwc(const sdvar_bf16* x, int N, int H, int W, int Cin
   p.out_f32_nchw = y_f32_nchw;
   p.lo = lo; p.hi = hi;
   const int BN = Cout % 160 == 0 ? 160 : Cout >= 128 ? 128 : Cout > 16 ? 32 : 16;
+  ProfileScope prof(st, FAM_CONV, 2.0 * (double)p.M * Cout * Cin * taps);
+  static const bool no_halo = getenv("SDVAR_CONV_NO_HALO") != nullptr;   // A/B switch for profiling
+  if (taps == 9 && W % conv::BM == 0 && (BN == 160 || BN == 128 || BN == 16) && !no_halo) {
+    // rows of at least 128 pixels: halo-strip kernel (BN = 16: conv_out, bound by the activation stream alone)
+    if (BN == 160) return conv::launch_halo<160, 32>(x, w_packed, p, st);
+    if (BN == 16) return conv::launch_halo<16, 32>(x, w_packed, p, st);
+    return conv::launch_halo<128, 32>(x, w_packed, p, st);
+  }
   CUtensorMap tmA, tmB;
   const uint64_t dimsA[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
   const uint64_t strA[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
@@ -334,7 +528,6 @@ extern "C" int sdvar_conv_nhwc(const sdvar_bf16* x, int N, int H, int W, int Cin
   const uint64_t strB[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
   const uint32_t boxB[3] = {(uint32_t)conv::KC, (uint32_t)(BN / 2), 1u};
   if (int rc = make_tmap_bf16_sw64(&tmB, w_packed, 3, dimsB, strB, boxB)) return rc;
-  ProfileScope prof(st, FAM_CONV, 2.0 * (double)p.M * Cout * Cin * taps);
   switch (BN) {
     case 160: return conv::launch<160>(tmA, tmB, p, st);
     case 128: return conv::launch<128>(tmA, tmB, p, st);

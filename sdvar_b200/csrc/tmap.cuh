@@ -12,6 +12,9 @@ namespace sdvar {
 // strides_bytes[i] is the byte stride of dims[i+1].  box[0] must be 64 elements (=128 bytes).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// same as make_tmap_bf16 for up to 4 dims
+int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box);
 // bf16 tensor, up to 4 dims, 64-byte swizzle: box[0] must be 32 elements (the convolution's channel chunks: 160/320/640 input
 // channels are multiples of 32, not of 64)
 int make_tmap_bf16_sw64(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -388,7 +388,12 @@ def test_bias_residual_and_upsample_nhwc(cuda_lib, N, C, H, W, with_res):
 
 @pytest.mark.parametrize("N,Cin,Cout,H,W,taps,with_res,with_bias", [
     (2, 160, 160, 64, 64, 9, True, True),      # BN=160, W < 128: two rows per CTA
-    (1, 160, 160, 8, 256, 9, False, True),     # W > 128: two CTA boxes per row
+    (1, 160, 160, 8, 256, 9, False, True),     # W > 128: halo-strip kernel, two CTA strips per row
+    (2, 160, 160, 128, 128, 9, True, True),    # halo-strip kernel, one strip per row, all four image borders
+    (1, 320, 160, 16, 128, 9, False, True),    # halo-strip kernel, ten channel chunks
+    (1, 320, 320, 4, 256, 9, True, False),     # halo-strip kernel, two N tiles
+    (3, 64, 128, 2, 128, 9, True, True),       # halo-strip kernel, BN=128, ragged last cluster tile
+    (1, 32, 160, 1, 128, 9, False, True),      # halo-strip kernel, single image row: both dy halos out of bounds
     (3, 640, 640, 16, 16, 9, True, False),     # four N tiles, one cluster tile per image
     (2, 320, 160, 32, 32, 9, False, True),
     (2, 640, 320, 32, 32, 1, False, True),     # nin_shortcut (1x1)
@@ -420,7 +425,7 @@ def test_conv_nhwc_tcgen05_vs_torch(cuda_lib, N, Cin, Cout, H, W, taps, with_res
     assert float(err.mean()) < 2e-3 * float(ref.abs().mean()) + 1e-5
 
 
-@pytest.mark.parametrize("N,Cin,H,W", [(2, 160, 32, 128), (3, 32, 16, 16)])
+@pytest.mark.parametrize("N,Cin,H,W", [(2, 160, 32, 128), (1, 160, 6, 256), (3, 32, 16, 16)])
 def test_conv_nhwc_image_epilogue(cuda_lib, N, Cin, H, W):
     """conv_out: 3 output channels, fp32 NCHW image clamped to [-1, 1] straight from the epilogue (models/vqvae.py:63)"""
     x = hashed("cvo.x", Cin, (N, Cin, H, W), 1.0).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)

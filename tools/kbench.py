@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel microbenchmarks on one B200 (CUDA events, >=3 warm-ups, inputs larger than L2 or rotated buffers).
 
-    python tools/kbench.py [gemm] [attn] [verify] [sample] [ln] [--json out.json]
+    python tools/kbench.py [gemm] [attn] [verify] [sample] [ln] [conv] [--json out.json]
 
 `verify` is BASELINE.json configs[4]: synthetic draft+target logits B x 680 tokens x V=4096, batch sweep, segment table =
 the 256 px pyramid.  Numbers are ALGORITHMIC bytes (or FLOPs) / event time, against MEASURED_PEAKS.json."""
@@ -167,10 +167,34 @@ def bench_ln(out):
     out["ln_modulate"] = rows
 
 
+def bench_conv(out):
+    """decoder layer shapes at B=64 (ch=160, 256 px): tcgen05 implicit GEMM vs cuDNN on the same channels-last bf16 tensors"""
+    pk = peaks()
+    rows = []
+    B = 64
+    for (cin, cout, hw, taps) in ((160, 160, 256, 9), (160, 160, 128, 9), (320, 160, 128, 9), (320, 320, 128, 9), (320, 320, 64, 9),
+                                  (640, 320, 32, 9), (320, 320, 32, 9), (640, 640, 32, 9), (640, 640, 16, 9), (32, 640, 16, 9),
+                                  (640, 1920, 16, 1), (640, 320, 32, 1), (320, 160, 128, 1)):
+        k = 3 if taps == 9 else 1
+        x = torch.randn(B, cin, hw, hw, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(cout, cin, k, k, device=DEV) / math.sqrt(cin * taps)).bfloat16().contiguous(memory_format=torch.channels_last)
+        wp = w.permute(2, 3, 0, 1).reshape(taps, cout, cin).contiguous()
+        bias = torch.zeros(cout, device=DEV)
+        y = torch.empty(B, cout, hw, hw, device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        ms = timeit(lambda: _cabi.conv_nhwc(x, B, hw, hw, cin, wp, taps, cout, bias, None, y=y), iters=5)
+        ms_lib = timeit(lambda: torch.nn.functional.conv2d(x, w, None, padding=k // 2), iters=5)
+        fl = 2.0 * B * hw * hw * cin * cout * taps
+        rows.append(dict(cin=cin, cout=cout, hw=hw, taps=taps, ms=ms, tflops=fl / ms / 1e9, cudnn_ms=ms_lib, cudnn_tflops=fl / ms_lib / 1e9))
+        print(f"conv {cin:4d}->{cout:4d} {hw:3d}x{hw:<3d} taps={taps}  {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TF/s ({fl / ms / 1e9 / pk['bf16_tflops'] * 100:5.1f}% of burst)"
+              f"  cuDNN {ms_lib:8.3f} ms {fl / ms_lib / 1e9:7.1f}")
+        del x, y
+    out["conv"] = rows
+
+
 if __name__ == "__main__":
     which = [a for a in sys.argv[1:] if not a.startswith("--") and not a.endswith(".json")] or ["gemm", "attn", "verify", "sample", "ln"]
     out = {"gpu": torch.cuda.get_device_name(0), "peaks": peaks()}
     for w in which:
-        {"gemm": bench_gemm, "attn": bench_attn, "verify": bench_verify, "sample": bench_sample, "ln": bench_ln}[w](out)
+        {"gemm": bench_gemm, "attn": bench_attn, "verify": bench_verify, "sample": bench_sample, "ln": bench_ln, "conv": bench_conv}[w](out)
     if "--json" in sys.argv:
         json.dump(out, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
