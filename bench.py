@@ -14,7 +14,10 @@ Data-parallel replicas; NCCL only to gather the (uint8) images and to sum the ac
   kernels    the same figure for every kernel family (GB/s for the HBM-bound ones), incl. the verify kernel of the metric
   bounds     the acceptance-schedule bounds SURVEY.md 8(d) asks for, measured in the same run on the same models:
              accept_all / reject_all (every window committed whole / one stage per round), target_only and draft_only
-             (``VAR.autoregressive_infer_cfg``), and the reference's gamma controller (``gamma_policy='reference'``)
+             (``VAR.autoregressive_infer_cfg``), the reference's gamma controller (``gamma_policy='reference'``), and the
+             same measured schedule with the target verifying by one window pass (``window_verify``) / stage by stage with
+             early exit (``lazy_verify``); the default ``--verify-mode auto`` picks between them per window by shape, results
+             are bit-identical in all three (tests/test_engine_gpu.py::test_lazy_verify_equals_window_verify)
   cpu_baseline  the REFERENCE's own functions (oracle/_ref archive of its unmodified modules; ``kind: "reference"``) timed on
              this box's host cores on a bounded sample, with the oracle port's loop beside it; ``kind: "port"`` only when
              the archive is absent
@@ -59,6 +62,9 @@ def parse():
     ap.add_argument("--accept-rule", default="speculative", choices=["speculative", "reference"])
     ap.add_argument("--schedule", default="lockstep", choices=["lockstep", "ragged"])
     ap.add_argument("--gamma-policy", default="fixed", choices=["fixed", "reference"])
+    ap.add_argument("--verify-mode", default="auto", choices=["auto", "window", "lazy"],
+                    help="how the target verifies a drafted window (identical results): one window pass, stage by stage with early "
+                         "exit, or auto = lazy from the stage whose pass alone is compute-bound (SDVAR.LAZY_MIN_ROWS)")
     ap.add_argument("--px", type=int, default=256, choices=[256, 512], help="256: patch_nums 1..16 (L=680); 512: 1..32 (L=2240)")
     ap.add_argument("--shared-aln-target", action="store_true", help="target uses shared adaLN (the d36 layout, README.md:142-144)")
     ap.add_argument("--cpu-sample-images", type=int, default=1)
@@ -227,7 +233,7 @@ def main():
     batch_txt = f"global batch {args.global_batch} split over {world} GPU(s)" if strong else f"batch {args.batch}/GPU"
     workload = (f"SDVAR VAR-d{args.depth_draft} draft + VAR-d{args.depth_target} target, random-init, {args.px}px, patch_nums 1..{P256[-1]}, "
                 f"{batch_txt}, cfg={args.cfg}, top_k={args.top_k}, top_p={args.top_p}, gamma={args.gamma}, accept_rule={args.accept_rule}, "
-                f"schedule={args.schedule}, gamma_policy={args.gamma_policy}")
+                f"schedule={args.schedule}, gamma_policy={args.gamma_policy}, verify_mode={args.verify_mode}")
 
     if args.impl == "reference":
         if rank != 0:
@@ -273,7 +279,7 @@ def main():
     img_host = torch.empty(B, 3, px, px, dtype=torch.float32).pin_memory()
     gather_buf = parallel.GatherBuffer(world, B, (3, px, px), dev) if world > 1 else None
     sd_kw = dict(cfg=args.cfg, gamma=args.gamma, top_k=args.top_k, top_p=args.top_p, accept_rule=args.accept_rule,
-                 schedule=args.schedule, gamma_policy=args.gamma_policy)
+                 schedule=args.schedule, gamma_policy=args.gamma_policy, verify_mode=args.verify_mode)
 
     def generate(lab, seed, **over):
         kw = dict(sd_kw); kw.update(over)
@@ -346,12 +352,14 @@ def main():
            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": B * 8,
                    "d2h_bytes_per_step": B * 3 * px * px * 4},
            "gpu_launches": launches, "clocks": clocks,
-           "accept_stats": {k: last_stats[k] for k in ("rounds", "target_passes", "draft_stages", "accepted_tokens", "rejected_tokens", "advance")}}
+           "accept_stats": {k: last_stats[k] for k in ("rounds", "target_passes", "draft_stages", "accepted_tokens", "rejected_tokens", "advance",
+                                                       "verify_mode", "target_stages_skipped")}}
 
     if not args.no_bounds:
-        # acceptance-schedule bounds on the same models, labels and batch: 1 warm-up + 2 timed calls each
+        # acceptance-schedule bounds on the same models, labels and batch: 2 warm-ups (eager pass, graph capture)
+        # + 2 timed calls each
         def ips(fn):
-            ms = timed(fn, 2, 1)[0]
+            ms = timed(fn, 2, 2)[0]
             return gb * 2 / (ms * 1e-3)
 
         def only(model):
@@ -359,7 +367,9 @@ def main():
                 for c0, c1 in chunks:
                     model.autoregressive_infer_cfg(c1 - c0, lab_dev[c0:c1], g_seed=1000 * rank + i, cfg=args.cfg, top_k=args.top_k, top_p=args.top_p)
             return f
-        bounds = {"unit": "images/s", "how": "same run, same models / labels / batch; 1 warm-up + 2 timed calls each, device-timed",
+        bounds = {"unit": "images/s", "how": "same run, same models / labels / batch; 2 warm-ups + 2 timed calls each, device-timed",
+                  "window_verify": ips(lambda i: generate(lab_dev, i, verify_mode="window")),
+                  "lazy_verify": ips(lambda i: generate(lab_dev, i, verify_mode="lazy")),
                   "accept_all": ips(lambda i: generate(lab_dev, i, _bound="accept_all")),
                   "reject_all": ips(lambda i: generate(lab_dev, i, _bound="reject_all")),
                   "gamma_policy_reference": ips(lambda i: generate(lab_dev, i, gamma_policy="reference")),

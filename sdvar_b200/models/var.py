@@ -303,6 +303,7 @@ class SDVARInferenceState:
         self.accept_count = self.reject_count = self.target_calls = self.draft_stage_calls = self.rounds = 0
         self.top_k, self.top_p, self.more_smooth = 0, 0.0, False
         self.schedule, self.gamma_policy, self.record = "lockstep", "fixed", None
+        self.verify_mode, self.lazy, self.lazy_skipped = "window", False, 0
         self.f_hat = None             # committed f_hat (B,Cvae,HW,HW)
         self.final: List[torch.Tensor] = []     # committed tokens per stage, (B, l_s) int64
         self.stage = [0] * B          # per image: next stage to produce
@@ -334,7 +335,8 @@ class SDVARInferenceState:
         return dict(rounds=self.rounds, target_passes=self.target_calls, draft_stages=self.draft_stage_calls,
                     accepted_tokens=acc, rejected_tokens=sum(self.stage_tokens) - acc, advance=list(self.advance),
                     stage_accept_tokens=list(self.stage_accept_tokens), stage_tokens=list(self.stage_tokens),
-                    schedule=self.schedule, gamma_policy=self.gamma_policy)
+                    schedule=self.schedule, gamma_policy=self.gamma_policy, verify_mode=self.verify_mode,
+                    target_stages_skipped=self.lazy_skipped)
 
 
 def _draw(noise, kind: str, stream: str, out: torch.Tensor):
@@ -349,6 +351,8 @@ def _draw(noise, kind: str, stream: str, out: torch.Tensor):
 
 
 class SDVAR(nn.Module):
+    LAZY_MIN_ROWS = 1024      # verify_mode='auto': rows (CFG included) from which a single-stage target pass is compute-bound on a B200
+
     def __init__(self, draft_model: VAR, target_model: VAR, similarity_thresh: float = 0.8):
         super().__init__()
         self.draft_model, self.target_model, self.similarity_thresh = draft_model, target_model, similarity_thresh
@@ -444,8 +448,12 @@ class SDVAR(nn.Module):
         if not stages:
             return draft_tokens
         smap = None if state.group is None else e.slot_map(state.group)
-        state.win_xd = torch.empty(n, Lw, V, dtype=torch.float32, device=dev)
-        state.win_d = torch.empty(n, Lw, dtype=torch.int64, device=dev)
+        if state.lazy:     # stage-by-stage verification reads each stage on its own: per-stage dense buffers
+            state.st_xd = [torch.empty(n, D.ls[si], V, dtype=torch.float32, device=dev) for si in stages]
+            state.st_d = [torch.empty(n, D.ls[si], dtype=torch.int64, device=dev) for si in stages]
+        else:
+            state.win_xd = torch.empty(n, Lw, V, dtype=torch.float32, device=dev)
+            state.win_d = torch.empty(n, Lw, dtype=torch.int64, device=dev)
         fh = self._group_f_hat(state)
         nm = None
         if stages[0] > 0:      # stage input rebuilt from the committed f_hat (same kernel as the K5 step => same bits)
@@ -460,9 +468,13 @@ class SDVAR(nn.Module):
             logits = e.forward([si], slot_map=smap)
             nz = state.noise.exponential("draft", n * l, V)
             t1, t2 = D._cfg_scalars(state.cfg, [si])
-            _cabi.sample_cfg_topk_topp(logits, n, l, V, [0, l], t1, t2, state.top_k, thr, nz, state.win_d, state.win_xd, None,
-                                       out_ld=Lw, out_off=offs[j])
-            idx = state.win_d[:, offs[j]:offs[j + 1]].contiguous()
+            if state.lazy:
+                _cabi.sample_cfg_topk_topp(logits, n, l, V, [0, l], t1, t2, state.top_k, thr, nz, state.st_d[j], state.st_xd[j], None)
+                idx = state.st_d[j]
+            else:
+                _cabi.sample_cfg_topk_topp(logits, n, l, V, [0, l], t1, t2, state.top_k, thr, nz, state.win_d, state.win_xd, None,
+                                           out_ld=Lw, out_off=offs[j])
+                idx = state.win_d[:, offs[j]:offs[j + 1]].contiguous()
             fh, nm = vq.next_input_from_idx(si, fh, idx)
             draft_tokens.append(idx); state.snaps.append(fh.clone())
             state.maps.append(nm if si != state.total_stages - 1 else None)
@@ -489,6 +501,53 @@ class SDVAR(nn.Module):
         state.win_xt = torch.empty(n, Lw, T.V, dtype=torch.float32, device=T.device)
         _cabi.sample_cfg_topk_topp(logits, n, Lw, T.V, offs, t1, t2, state.top_k, thr, None, None, state.win_xt, None)
         return [state.win_xt[:, offs[j]:offs[j + 1]] for j in range(g)], g
+
+    def lazy_verify_batch(self, draft_tokens: List[torch.Tensor], state: SDVARInferenceState, B: int) -> int:
+        """``verify_mode='lazy'``: the drafted window is verified STAGE BY STAGE with early exit -- one single-stage target pass,
+        K3 filter and K4 launch per stage, and the next drafted stage is only run through the target if every token of this one
+        was accepted.  A window pass equals the incremental passes bit for bit (tests/test_engine_gpu.py::
+        test_window_pass_equals_incremental), every noise draw of the window is still made in the loop spec's order, and a stage
+        behind the first rejected one is never committed anyway: tokens, accept flags, advances and images are IDENTICAL to the
+        one-pass window verification; only target work that the window pass would have thrown away is not done.  When target
+        passes are compute-bound (large batch) a rejected window then costs one stage, not g.  Lock-step schedule only."""
+        T = self.target_model
+        e = T._engine
+        stages, offs, Lw = self._window(state)
+        g, n, V, dev = len(stages), state.n, T.V, T.device
+        assert state.group is None and state.schedule == "lockstep"
+        u = torch.empty(n * Lw, dtype=torch.float32, device=dev)
+        nr = torch.empty(n * Lw, V, dtype=torch.float32, device=dev)
+        for j in range(g):       # all draws of the window, in the loop spec's order, whether or not the stage gets verified
+            _draw(state.noise, "uni", "u", u[n * offs[j]:n * offs[j + 1]])
+            _draw(state.noise, "exp", "resample", nr[n * offs[j]:n * offs[j + 1]])
+        thr = float(np.float32(1.0 - state.top_p)) if state.top_p > 0 else -1.0
+        out = torch.empty(n, Lw, dtype=torch.int64, device=dev)
+        na_all = torch.zeros(n, g, dtype=torch.int32)
+        n_ok = 0
+        for j, si in enumerate(stages):
+            l = T.ls[si]
+            e.put_first_map(l) if si == 0 else e.put_embed_map(si, state.maps[j], l)
+            logits = e.forward([si])
+            state.target_calls += 1
+            t1, t2 = T._cfg_scalars(state.cfg, [si])
+            xt = torch.empty(n, l, V, dtype=torch.float32, device=dev)
+            _cabi.sample_cfg_topk_topp(logits, n, l, V, [0, l], t1, t2, state.top_k, thr, None, None, xt, None)
+            o = torch.empty(n, l, dtype=torch.int64, device=dev)
+            acc = torch.empty(n, l, dtype=torch.uint8, device=dev)
+            fr = torch.empty(n, 1, dtype=torch.int32, device=dev); na = torch.empty(n, 1, dtype=torch.int32, device=dev)
+            st = torch.empty(n, dtype=torch.int32, device=dev); summ = torch.empty(4, dtype=torch.int32, device=dev)
+            _cabi.verify_accept_resample(xt, state.st_xd[j], state.st_d[j], u[n * offs[j]:n * offs[j + 1]], nr[n * offs[j]:n * offs[j + 1]],
+                                         n, l, V, [0, l], o, acc, None, None, fr, na, st, summ, state.ws)
+            out[:, offs[j]:offs[j + 1]] = o
+            h = torch.cat((summ, na.flatten())).cpu()         # one host sync per verified stage
+            na_all[:, j] = h[4:]
+            if int(h[0]) < 1:                                 # some image rejected a token of this stage: it is repaired, the rest is moot
+                break
+            n_ok += 1
+        state.lazy_skipped += g - min(n_ok + 1, g)
+        state.out_idx = out
+        state.last_n_ok = torch.full((n,), n_ok, dtype=torch.int32)
+        return self._advance_from_counts(state, stages, state.last_n_ok, na_all, n_ok)
 
     def _advance_from_counts(self, state, stages, n_ok_per_image, na_host, lockstep_n_ok):
         """statistics + advance lengths from the per-(image, stage) accept counts of the round"""
@@ -626,7 +685,8 @@ class SDVAR(nn.Module):
                                                    gamma: int = 2, top_k: int = 0, top_p: float = 0.0, more_smooth: bool = False,
                                                    accept_rule: str = "speculative", schedule: str = "lockstep",
                                                    gamma_policy: str = "fixed", noise=None, return_tokens: bool = False,
-                                                   record: Optional[dict] = None, _bound: Optional[str] = None):
+                                                   record: Optional[dict] = None, _bound: Optional[str] = None,
+                                                   verify_mode: str = "window"):
         """while stage < K: draft g stages -> one target pass -> verify -> commit a prefix (models/var.py:1285-1383).
         Returns the image (B,3,H,W) in [0,1]; acceptance statistics are left in ``self.last_stats``.
 
@@ -638,12 +698,21 @@ class SDVAR(nn.Module):
                       no drafted stage survived intact the window shrinks by one (never below 1, never grows back).
         more_smooth   accepted and stored like the reference does (var.py:1315); the drafting / verification path never reads
                       it there either.
+        verify_mode   how the target verifies a drafted window -- the RESULT is the same bit for bit, only the work differs:
+                      'window' (default) one block-causal target pass over all g stages; 'lazy' stage by stage with early exit
+                      (``lazy_verify_batch``); 'auto' lazy when the first stage alone already fills the GPU (2n*l_s >=
+                      ``LAZY_MIN_ROWS`` rows: its pass is compute-bound, so a second stage costs its full FLOPs and is pure loss
+                      when the first one gets repaired) and one window pass otherwise (small stages are weight-bandwidth /
+                      latency-bound: the second stage rides along almost for free).  Lock-step + speculative rule only;
+                      anything else verifies by window.
         record        optional dict: receives every round's verify inputs and outputs (loop-replay tests).
         _bound        measurement only (bench.py 'bounds'): 'accept_all' commits every drafted window whole, 'reject_all' commits
                       one stage per round, whatever the verify kernel said -- the two ends of the acceptance schedule."""
         assert accept_rule in ("speculative", "reference") and schedule in ("lockstep", "ragged") and gamma_policy in ("fixed", "reference")
-        assert gamma >= 1 and _bound in (None, "accept_all", "reject_all")
+        assert gamma >= 1 and _bound in (None, "accept_all", "reject_all") and verify_mode in ("window", "lazy", "auto")
         state = self._initialize_inference_state(B, label_B, g_seed, cfg, gamma, noise)
+        can_lazy = verify_mode != "window" and schedule == "lockstep" and accept_rule == "speculative" and record is None and _bound is None
+        state.verify_mode = verify_mode if can_lazy else "window"
         state.top_k, state.top_p, state.more_smooth = top_k, top_p, more_smooth
         state.schedule, state.gamma_policy, state.record = schedule, gamma_policy, record
         match = self.speculative_token_matching if accept_rule == "speculative" else self.basic_token_matching
@@ -660,9 +729,14 @@ class SDVAR(nn.Module):
                 state.group = None if members is None or len(members) == B else torch.tensor(members, device=dev, dtype=torch.int64)
                 state.n = B if state.group is None else len(members)
                 ids = list(range(B)) if state.group is None else members
+                state.lazy = can_lazy and min(gm, K - s) > 1 and (
+                    verify_mode == "lazy" or 2 * state.n * self.target_model.ls[s] >= self.LAZY_MIN_ROWS)
                 draft_tokens = self.draft_generate_batch(state, state.n)
-                target_logits, _ = self.target_verify_batch(draft_tokens, state, state.n)
-                accept_length = match(draft_tokens, target_logits, state, state.n)
+                if state.lazy:
+                    accept_length = self.lazy_verify_batch(draft_tokens, state, state.n)
+                else:
+                    target_logits, _ = self.target_verify_batch(draft_tokens, state, state.n)
+                    accept_length = match(draft_tokens, target_logits, state, state.n)
                 if _bound == "accept_all":
                     accept_length, state.out_idx = len(draft_tokens), state.win_d
                 elif _bound == "reject_all":

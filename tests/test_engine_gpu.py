@@ -168,6 +168,50 @@ def test_sd_loop_draft_equals_target_accepts_everything(cuda_lib, gamma):
     assert all(torch.equal(a, b) for a, b in zip(idx_sd, idx_b)) and torch.equal(f_sd, f_b)
 
 
+@pytest.mark.parametrize("pair,gamma", [("equal", 3), ("close", 2), ("close", 3), ("far", 2), ("far", 4)])
+def test_lazy_verify_equals_window_verify(cuda_lib, pair, gamma):
+    """verify_mode='lazy' / 'auto' (stage-by-stage target verification with early exit) must be a pure scheduling change:
+    tokens, f_hat, image, advances and acceptance counters identical to the one-pass window verification on the same noise,
+    for a draft that equals the target (every stage accepted: lazy runs all g stages), one that is close to it (mixed rounds)
+    and one that is far (every round repairs its first stage: lazy skips the rest of each window)."""
+    from oracle.ref_model import ReplayNoise
+    from sdvar_b200.models import SDVAR
+    vae, d, t, sd, _ = _build(P256, 3, 3, gamma_bias=0.5, init_head=1.0)
+    if pair != "far":
+        sdict = {k: v.clone() for k, v in d.state_dict().items()}
+        if pair == "close":
+            sdict["head.bias"] = sdict["head.bias"] + 0.05 * hashed("lazy.hb", 0, tuple(sdict["head.bias"].shape), 1.0).to(DEV)
+        t.load_state_dict(sdict)
+    sd = SDVAR(d, t)
+    B, lab = 3, torch.tensor([5, 6, 7], device=DEV)
+    kw = dict(gamma=gamma, cfg=1.5, top_k=900, top_p=0.96, return_tokens=True)
+    res = {}
+    for mode in ("window", "lazy", "auto"):
+        sd.LAZY_MIN_ROWS = 2 * B * 16                    # 'auto': stages of 16+ tokens verify lazily, smaller ones by window
+        img, idxs, f_hat = sd.sdvar_autoregressive_infer_cfg_parallel_v1(B, lab, noise=ReplayNoise(21, DEV), verify_mode=mode, **kw)
+        res[mode] = (img.clone(), [i.clone() for i in idxs], f_hat.clone(), dict(sd.last_stats))
+    w = res["window"]
+    K = len(P256)
+    for mode in ("lazy", "auto"):
+        r = res[mode]
+        assert all(torch.equal(a, b) for a, b in zip(r[1], w[1])), mode
+        assert torch.equal(r[2], w[2]) and torch.equal(r[0], w[0]), mode
+        for k in ("advance", "accepted_tokens", "rejected_tokens", "rounds", "stage_accept_tokens", "stage_tokens", "draft_stages"):
+            assert r[3][k] == w[3][k], (mode, k, r[3][k], w[3][k])
+        assert r[3]["verify_mode"] == mode and sum(r[3]["advance"]) == K
+    lz, wn = res["lazy"][3], w[3]
+    windows = [min(gamma, K - s) for s in np.cumsum([0] + wn["advance"][:-1])]
+    assert wn["target_passes"] == wn["rounds"] and wn["target_stages_skipped"] == 0
+    # lazy: one single-stage pass per verified stage = the committed stages, except that a window accepted whole needs no repair pass
+    assert lz["target_passes"] + lz["target_stages_skipped"] == sum(windows)
+    if pair == "equal":
+        assert lz["target_stages_skipped"] == 0 and lz["rejected_tokens"] == 0
+    if pair == "far":
+        assert lz["target_passes"] == K and lz["target_stages_skipped"] == sum(windows) - K and lz["rejected_tokens"] > 0
+    if pair == "close":
+        assert 0 < lz["rejected_tokens"] and max(lz["advance"]) > 1, "the close pair should mix accepted and repaired stages"
+
+
 @pytest.mark.parametrize("rule,gamma", [("speculative", 2), ("speculative", 3), ("reference", 2)])
 def test_sd_loop_invariants_after_rejections(cuda_lib, rule, gamma):
     """draft != target: rejections, repairs and KV rollback happen.  Invariants that pin the state handling:
