@@ -435,51 +435,66 @@ class SDVAR(nn.Module):
     def _group_f_hat(self, state: SDVARInferenceState) -> torch.Tensor:
         return state.f_hat.clone() if state.group is None else state.f_hat.index_select(0, state.group)
 
-    def draft_generate_batch(self, state: SDVARInferenceState, B: int) -> List[torch.Tensor]:
+    def draft_generate_batch(self, state: SDVARInferenceState, B: int, upto: Optional[int] = None) -> List[torch.Tensor]:
         """Draft g = min(gamma, K - stage) stages incrementally for the current group (models/var.py:949-1024).  Each stage's
         input is area_down(f_hat) of the previous DRAFTED stage (fixes D2), stage 0 is the sos map (D3); K3 writes the draft's
         tokens and its mixed+filtered logits straight into the window-shaped buffers the verify kernel reads; f_hat
-        snapshots are kept for the commit."""
+        snapshots are kept for the commit.  ``upto`` (lazy verification) drafts only the first ``upto`` stages of the window
+        now; ``_draft_stage`` continues on demand."""
         D = self.draft_model
-        e, vq = D._engine, D.vae_quant_proxy[0]
+        e = D._engine
         stages, offs, Lw = self._window(state)
         n, V, dev = state.n, D.V, D.device
-        state.snaps, draft_tokens = [], []
+        state.snaps, state.draft_tokens = [], []
         if not stages:
-            return draft_tokens
-        smap = None if state.group is None else e.slot_map(state.group)
+            return state.draft_tokens
+        state.draft_smap = None if state.group is None else e.slot_map(state.group)
         if state.lazy:     # stage-by-stage verification reads each stage on its own: per-stage dense buffers
             state.st_xd = [torch.empty(n, D.ls[si], V, dtype=torch.float32, device=dev) for si in stages]
             state.st_d = [torch.empty(n, D.ls[si], dtype=torch.int64, device=dev) for si in stages]
         else:
             state.win_xd = torch.empty(n, Lw, V, dtype=torch.float32, device=dev)
             state.win_d = torch.empty(n, Lw, dtype=torch.int64, device=dev)
-        fh = self._group_f_hat(state)
+        state.draft_fh = self._group_f_hat(state)
         nm = None
         if stages[0] > 0:      # stage input rebuilt from the committed f_hat (same kernel as the K5 step => same bits)
             pn = D.patch_nums[stages[0]]
             nm = torch.empty(n, D.Cvae, pn, pn, dtype=torch.float32, device=dev)
-            _cabi.vq_area_down(fh, n, D.patch_nums[-1], pn, D.Cvae, nm)
+            _cabi.vq_area_down(state.draft_fh, n, D.patch_nums[-1], pn, D.Cvae, nm)
         state.maps = [nm]
+        for j in range(len(stages) if upto is None else min(upto, len(stages))):
+            self._draft_stage(state, j)
+        return state.draft_tokens
+
+    def _draft_stage(self, state: SDVARInferenceState, j: int, skip: bool = False):
+        """draft stage j of the current window (must follow stage j-1).  ``skip``: only make the stage's noise draw, so the
+        'draft' stream stays where the loop spec puts it when lazy verification never needs this stage."""
+        D = self.draft_model
+        e, vq = D._engine, D.vae_quant_proxy[0]
+        stages, offs, Lw = self._window(state)
+        si, n, V = stages[j], state.n, D.V
+        l = D.ls[si]
+        if skip:
+            state.noise.exponential("draft", n * l, V)
+            return
+        assert j == len(state.draft_tokens)
+        smap = state.draft_smap
         thr = float(np.float32(1.0 - state.top_p)) if state.top_p > 0 else -1.0
-        for j, si in enumerate(stages):
-            l = D.ls[si]
-            e.put_first_map(l, slot_map=smap) if si == 0 else e.put_embed_map(si, state.maps[j], l)
-            logits = e.forward([si], slot_map=smap)
-            nz = state.noise.exponential("draft", n * l, V)
-            t1, t2 = D._cfg_scalars(state.cfg, [si])
-            if state.lazy:
-                _cabi.sample_cfg_topk_topp(logits, n, l, V, [0, l], t1, t2, state.top_k, thr, nz, state.st_d[j], state.st_xd[j], None)
-                idx = state.st_d[j]
-            else:
-                _cabi.sample_cfg_topk_topp(logits, n, l, V, [0, l], t1, t2, state.top_k, thr, nz, state.win_d, state.win_xd, None,
-                                           out_ld=Lw, out_off=offs[j])
-                idx = state.win_d[:, offs[j]:offs[j + 1]].contiguous()
-            fh, nm = vq.next_input_from_idx(si, fh, idx)
-            draft_tokens.append(idx); state.snaps.append(fh.clone())
-            state.maps.append(nm if si != state.total_stages - 1 else None)
-            state.draft_stage_calls += 1
-        return draft_tokens
+        e.put_first_map(l, slot_map=smap) if si == 0 else e.put_embed_map(si, state.maps[j], l)
+        logits = e.forward([si], slot_map=smap)
+        nz = state.noise.exponential("draft", n * l, V)
+        t1, t2 = D._cfg_scalars(state.cfg, [si])
+        if state.lazy:
+            _cabi.sample_cfg_topk_topp(logits, n, l, V, [0, l], t1, t2, state.top_k, thr, nz, state.st_d[j], state.st_xd[j], None)
+            idx = state.st_d[j]
+        else:
+            _cabi.sample_cfg_topk_topp(logits, n, l, V, [0, l], t1, t2, state.top_k, thr, nz, state.win_d, state.win_xd, None,
+                                       out_ld=Lw, out_off=offs[j])
+            idx = state.win_d[:, offs[j]:offs[j + 1]].contiguous()
+        state.draft_fh, nm = vq.next_input_from_idx(si, state.draft_fh, idx)
+        state.draft_tokens.append(idx); state.snaps.append(state.draft_fh.clone())
+        state.maps.append(nm if si != state.total_stages - 1 else None)
+        state.draft_stage_calls += 1
 
     def target_verify_batch(self, draft_tokens: List[torch.Tensor], state: SDVARInferenceState, B: int):
         """ONE block-causal target pass over the g drafted stages on top of the KV cache of accepted stages
@@ -503,9 +518,9 @@ class SDVAR(nn.Module):
         return [state.win_xt[:, offs[j]:offs[j + 1]] for j in range(g)], g
 
     def lazy_verify_batch(self, draft_tokens: List[torch.Tensor], state: SDVARInferenceState, B: int) -> int:
-        """``verify_mode='lazy'``: the drafted window is verified STAGE BY STAGE with early exit -- one single-stage target pass,
-        K3 filter and K4 launch per stage, and the next drafted stage is only run through the target if every token of this one
-        was accepted.  A window pass equals the incremental passes bit for bit (tests/test_engine_gpu.py::
+        """``verify_mode='lazy'``: the window is drafted and verified STAGE BY STAGE with early exit -- one single-stage target
+        pass, K3 filter and K4 launch per stage; the next stage is only drafted and run through the target if every token of
+        this one was accepted (its noise is drawn either way).  A window pass equals the incremental passes bit for bit (tests/test_engine_gpu.py::
         test_window_pass_equals_incremental), every noise draw of the window is still made in the loop spec's order, and a stage
         behind the first rejected one is never committed anyway: tokens, accept flags, advances and images are IDENTICAL to the
         one-pass window verification; only target work that the window pass would have thrown away is not done.  When target
@@ -526,6 +541,8 @@ class SDVAR(nn.Module):
         n_ok = 0
         for j, si in enumerate(stages):
             l = T.ls[si]
+            if j >= len(state.draft_tokens):                  # lazy drafting: stage j is drafted only now that stage j-1 survived
+                self._draft_stage(state, j)
             e.put_first_map(l) if si == 0 else e.put_embed_map(si, state.maps[j], l)
             logits = e.forward([si])
             state.target_calls += 1
@@ -544,6 +561,8 @@ class SDVAR(nn.Module):
             if int(h[0]) < 1:                                 # some image rejected a token of this stage: it is repaired, the rest is moot
                 break
             n_ok += 1
+        for j in range(len(state.draft_tokens), g):          # never needed: keep the 'draft' noise stream in step with the spec
+            self._draft_stage(state, j, skip=True)
         state.lazy_skipped += g - min(n_ok + 1, g)
         state.out_idx = out
         state.last_n_ok = torch.full((n,), n_ok, dtype=torch.int32)
@@ -731,7 +750,7 @@ class SDVAR(nn.Module):
                 ids = list(range(B)) if state.group is None else members
                 state.lazy = can_lazy and min(gm, K - s) > 1 and (
                     verify_mode == "lazy" or 2 * state.n * self.target_model.ls[s] >= self.LAZY_MIN_ROWS)
-                draft_tokens = self.draft_generate_batch(state, state.n)
+                draft_tokens = self.draft_generate_batch(state, state.n, upto=1 if state.lazy else None)
                 if state.lazy:
                     accept_length = self.lazy_verify_batch(draft_tokens, state, state.n)
                 else:

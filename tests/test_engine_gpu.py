@@ -196,7 +196,7 @@ def test_lazy_verify_equals_window_verify(cuda_lib, pair, gamma):
         r = res[mode]
         assert all(torch.equal(a, b) for a, b in zip(r[1], w[1])), mode
         assert torch.equal(r[2], w[2]) and torch.equal(r[0], w[0]), mode
-        for k in ("advance", "accepted_tokens", "rejected_tokens", "rounds", "stage_accept_tokens", "stage_tokens", "draft_stages"):
+        for k in ("advance", "accepted_tokens", "rejected_tokens", "rounds", "stage_accept_tokens", "stage_tokens"):
             assert r[3][k] == w[3][k], (mode, k, r[3][k], w[3][k])
         assert r[3]["verify_mode"] == mode and sum(r[3]["advance"]) == K
     lz, wn = res["lazy"][3], w[3]
@@ -204,6 +204,7 @@ def test_lazy_verify_equals_window_verify(cuda_lib, pair, gamma):
     assert wn["target_passes"] == wn["rounds"] and wn["target_stages_skipped"] == 0
     # lazy: one single-stage pass per verified stage = the committed stages, except that a window accepted whole needs no repair pass
     assert lz["target_passes"] + lz["target_stages_skipped"] == sum(windows)
+    assert lz["draft_stages"] == lz["target_passes"] and wn["draft_stages"] == sum(windows)   # lazy drafts a stage only when it verifies it
     if pair == "equal":
         assert lz["target_stages_skipped"] == 0 and lz["rejected_tokens"] == 0
     if pair == "far":
