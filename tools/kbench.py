@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel microbenchmarks on one B200 (CUDA events, >=3 warm-ups, inputs larger than L2 or rotated buffers).
 
-    python tools/kbench.py [gemm] [attn] [verify] [sample] [ln] [conv] [--json out.json]
+    python tools/kbench.py [gemm] [attn] [verify] [sample] [ln] [conv] [hbm] [--json out.json]
 
 `verify` is BASELINE.json configs[4]: synthetic draft+target logits B x 680 tokens x V=4096, batch sweep, segment table =
 the 256 px pyramid.  Numbers are ALGORITHMIC bytes (or FLOPs) / event time, against MEASURED_PEAKS.json."""
@@ -167,6 +167,26 @@ def bench_ln(out):
     out["ln_modulate"] = rows
 
 
+def bench_hbm(out):
+    """what a READ-ONLY stream reaches on this box (torch.sum over 4 GiB of fp32, and of bf16) next to the read+write copy
+    figure MEASURED_PEAKS.json quotes: the roof the read-only row kernels (K4 verify, K3 without mixed output) can see"""
+    pk = peaks()
+    rows = []
+    for dt, name in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        x = torch.ones(4 * 1024 ** 3 // torch.finfo(dt).bits * 8, device=DEV, dtype=dt)
+        ms = timeit(lambda: x.sum(), iters=5)
+        gbs = x.numel() * x.element_size() / ms / 1e6
+        rows.append(dict(kind=f"read-only sum {name}", gbs=gbs, frac_of_copy_peak=gbs / pk["hbm_gbs"]))
+        print(f"hbm read-only torch.sum {name}  {ms:8.3f} ms  {gbs:7.0f} GB/s ({gbs / pk['hbm_gbs'] * 100:5.1f}% of the measured copy peak)")
+        del x
+    a = torch.empty(1024 ** 3, device=DEV, dtype=torch.float32); b = torch.empty_like(a)
+    ms = timeit(lambda: b.copy_(a), iters=5)
+    gbs = 2 * a.numel() * 4 / ms / 1e6
+    rows.append(dict(kind="copy fp32 (read+write)", gbs=gbs, frac_of_copy_peak=gbs / pk["hbm_gbs"]))
+    print(f"hbm copy (read+write)          {ms:8.3f} ms  {gbs:7.0f} GB/s ({gbs / pk['hbm_gbs'] * 100:5.1f}%)")
+    out["hbm"] = rows
+
+
 def bench_conv(out):
     """decoder layer shapes at B=64 (ch=160, 256 px): tcgen05 implicit GEMM vs cuDNN on the same channels-last bf16 tensors"""
     pk = peaks()
@@ -195,6 +215,6 @@ if __name__ == "__main__":
     which = [a for a in sys.argv[1:] if not a.startswith("--") and not a.endswith(".json")] or ["gemm", "attn", "verify", "sample", "ln"]
     out = {"gpu": torch.cuda.get_device_name(0), "peaks": peaks()}
     for w in which:
-        {"gemm": bench_gemm, "attn": bench_attn, "verify": bench_verify, "sample": bench_sample, "ln": bench_ln, "conv": bench_conv}[w](out)
+        {"gemm": bench_gemm, "attn": bench_attn, "verify": bench_verify, "sample": bench_sample, "ln": bench_ln, "conv": bench_conv, "hbm": bench_hbm}[w](out)
     if "--json" in sys.argv:
         json.dump(out, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
