@@ -396,7 +396,7 @@ def main():
             # DRAM bytes per launch of the GEMM family: STATIC, from the committed ncu launch list of this same default workload
             # (profiles/traffic_r02.json if present, else r01); null for any other workload -- ncu cannot run inside a timed bench
             traffic, tsrc = None, None
-            default_workload = (B, args.depth_draft, args.depth_target, args.gamma, args.px, args.top_k, args.scaling) == (64, 16, 30, 2, 256, 900, "weak")
+            default_workload = (B, args.depth_draft, args.depth_target, args.gamma, args.px, args.top_k, args.scaling, args.verify_mode) == (64, 16, 30, 2, 256, 900, "weak", "auto")
             for name in ("traffic_r02.json", "traffic_r01.json"):
                 tpath = os.path.join(ROOT, "profiles", name)
                 if default_workload and os.path.exists(tpath):

@@ -14,7 +14,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FAMILY = [("gemm", r"gemm2?::gemm2?_kernel"), ("attention", r"attention"), ("ln_modulate", r"ln_modulate"), ("sample", r"k3_"),
           ("verify", r"k4_|top1_match"), ("vq", r"vq_"), ("embed", r"embed_next_map|first_map"),
-          ("decoder_glue", r"gn_stats|gn_apply|bias_residual|upsample2x|image_to_u8"), ("library_conv", r"cutlass|cudnn|implicit_gemm|conv")]
+          ("decoder_glue", r"gn_stats|gn_apply|bias_residual|upsample2x|image_to_u8"), ("conv", r"conv::conv_"),
+          ("library", r"cutlass|cudnn|implicit_gemm|fmha|conv")]
 
 
 def short(name):
