@@ -304,6 +304,7 @@ class SDVARInferenceState:
         self.top_k, self.top_p, self.more_smooth = 0, 0.0, False
         self.schedule, self.gamma_policy, self.record = "lockstep", "fixed", None
         self.verify_mode, self.lazy, self.lazy_skipped = "window", False, 0
+        self.p_full = 0.0             # running estimate of P(a drafted stage is accepted whole), drives verify_mode='auto'
         self.f_hat = None             # committed f_hat (B,Cvae,HW,HW)
         self.final: List[torch.Tensor] = []     # committed tokens per stage, (B, l_s) int64
         self.stage = [0] * B          # per image: next stage to produce
@@ -721,9 +722,11 @@ class SDVAR(nn.Module):
                       'window' (default) one block-causal target pass over all g stages; 'lazy' stage by stage with early exit
                       (``lazy_verify_batch``); 'auto' lazy when the first stage alone already fills the GPU (2n*l_s >=
                       ``LAZY_MIN_ROWS`` rows: its pass is compute-bound, so a second stage costs its full FLOPs and is pure loss
-                      when the first one gets repaired) and one window pass otherwise (small stages are weight-bandwidth /
-                      latency-bound: the second stage rides along almost for free).  Lock-step + speculative rule only;
-                      anything else verifies by window.
+                      when the first one gets repaired), or when fewer than half of the recently verified stages were accepted
+                      whole (running estimate ``p_full``: in the latency-bound regime a window round costs three passes -- two
+                      draft, one target -- and commits 1+p stages, a lazy round two passes per committed stage, so the window
+                      pays only for p > 1/2); one window pass otherwise.  Lock-step + speculative rule only; anything else
+                      verifies by window.
         record        optional dict: receives every round's verify inputs and outputs (loop-replay tests).
         _bound        measurement only (bench.py 'bounds'): 'accept_all' commits every drafted window whole, 'reject_all' commits
                       one stage per round, whatever the verify kernel said -- the two ends of the acceptance schedule."""
@@ -749,7 +752,7 @@ class SDVAR(nn.Module):
                 state.n = B if state.group is None else len(members)
                 ids = list(range(B)) if state.group is None else members
                 state.lazy = can_lazy and min(gm, K - s) > 1 and (
-                    verify_mode == "lazy" or 2 * state.n * self.target_model.ls[s] >= self.LAZY_MIN_ROWS)
+                    verify_mode == "lazy" or 2 * state.n * self.target_model.ls[s] >= self.LAZY_MIN_ROWS or state.p_full <= 0.5)
                 draft_tokens = self.draft_generate_batch(state, state.n, upto=1 if state.lazy else None)
                 if state.lazy:
                     accept_length = self.lazy_verify_batch(draft_tokens, state, state.n)
@@ -761,6 +764,10 @@ class SDVAR(nn.Module):
                 elif _bound == "reject_all":
                     accept_length = 1
                 self.update_state_with_accepted_tokens(draft_tokens, accept_length, state, state.n)
+                if can_lazy and _bound is None:     # every verified stage is one observation: the n_ok leading ones held, the next one did not
+                    n_ok = int(min(state.last_n_ok.tolist()))
+                    for smp in [1.0] * n_ok + ([0.0] if n_ok < min(gm, K - s) else []):
+                        state.p_full = 0.5 * state.p_full + 0.5 * smp
                 per_img = [accept_length] * state.n if isinstance(accept_length, int) else accept_length
                 round_adv += per_img
                 if gamma_policy == "reference":      # var.py:1352-1358: shrink the window after a round with no intact stage
