@@ -561,7 +561,7 @@ class ReplayNoise:
 
 @torch.no_grad()
 def sd_generate(draft: RefVAR, target: RefVAR, vq: RefVQ, B: int, label_B: torch.Tensor, noise, cfg=1.5, gamma=2,
-                top_k=0, top_p=0.0, accept_rule: str = "speculative", match_threshold: float = 0.5):
+                top_k=0, top_p=0.0, accept_rule: str = "speculative", match_threshold: float = 0.5, verify_mode: str = "window"):
     """Spec of ``sdvar_autoregressive_infer_cfg_parallel_v1`` with defects D1-D11 resolved:
 
     round at stage s, window g=min(gamma,K-s):
@@ -574,9 +574,16 @@ def sd_generate(draft: RefVAR, target: RefVAR, vq: RefVQ, B: int, label_B: torch
          s..s+a-2 keep the draft tokens, stage s+a-1 keeps accepted tokens and the target's repairs (D8);
       5. both KV caches are truncated to ends[s+a-1] (D4), f_hat is rebuilt from the snapshot after stage
          s+a-2 plus the final tokens of stage s+a-1 (D7).
+    ``verify_mode='lazy'`` restates the engine's stage-by-stage schedule: stage s+j is drafted and run through
+    the target (one single-stage pass on top of the cache) only if every stage before it in the window was accepted whole;
+    the noise of the stages never reached is drawn and dropped so the three streams stay where the window schedule leaves
+    them.  Same tokens, accept flags and advances as 'window'; ``target_passes`` / ``draft_stages`` count the work actually done.
     Returns (f_hat, final idx per stage, stats dict)."""
     K = len(draft.patch_nums)
     V = draft.V
+    if verify_mode == "lazy":
+        assert accept_rule == "speculative"
+        return _sd_generate_lazy(draft, target, vq, B, label_B, noise, cfg, gamma, top_k, top_p)
     cond_d, cond_t = draft.cond(label_B), target.cond(label_B)
     f_hat = cond_d.new_zeros(B, draft.Cvae, draft.patch_nums[-1], draft.patch_nums[-1])
     draft.kv_caching(True); target.kv_caching(True)
@@ -627,6 +634,62 @@ def sd_generate(draft: RefVAR, target: RefVAR, vq: RefVQ, B: int, label_B: torch
         n_ok = 0
         while n_ok < g and stage_ok[n_ok]:
             n_ok += 1
+        a = min(n_ok + 1, g)
+        for j in range(a - 1):
+            final_idx.append(idx_d[j])
+        final_idx.append(out_idx[a - 1])
+        base = snaps[a - 2] if a >= 2 else f_hat
+        f_hat, next_map = vq.next_input(s + a - 1, base.clone(), out_idx[a - 1])
+        draft.kv_truncate(draft.ends[s + a - 1]); target.kv_truncate(target.ends[s + a - 1])
+        stats["rounds"] += 1; stats["advance"].append(a)
+        s += a
+    draft.kv_caching(False); target.kv_caching(False)
+    stats["accepted_tokens"] = sum(stats["stage_accept_tokens"])
+    stats["rejected_tokens"] = sum(stats["stage_tokens"]) - stats["accepted_tokens"]
+    return f_hat, final_idx, stats
+
+
+@torch.no_grad()
+def _sd_generate_lazy(draft: RefVAR, target: RefVAR, vq: RefVQ, B, label_B, noise, cfg, gamma, top_k, top_p):
+    K, V = len(draft.patch_nums), draft.V
+    cond_d, cond_t = draft.cond(label_B), target.cond(label_B)
+    f_hat = cond_d.new_zeros(B, draft.Cvae, draft.patch_nums[-1], draft.patch_nums[-1])
+    draft.kv_caching(True); target.kv_caching(True)
+    s, next_map = 0, None
+    final_idx: List[torch.Tensor] = []
+    stats = dict(rounds=0, target_passes=0, draft_stages=0, accepted_tokens=0, rejected_tokens=0,
+                 advance=[], stage_accept_tokens=[0] * K, stage_tokens=[0] * K)
+    while s < K:
+        g = min(gamma, K - s)
+        fh = f_hat.clone()
+        maps, snaps, idx_d, out_idx = [next_map], [], [], []
+        u_all = [None] * g
+        n_ok = 0
+        # the u / resample draws of the whole window come first in their streams, exactly as in the window schedule
+        for j in range(g):
+            l = draft.ls[s + j]
+            u_all[j] = (noise.uniform("u", B * l), noise.exponential("resample", B * l, V))
+        for j in range(g):
+            si = s + j
+            l = draft.ls[si]
+            x = draft.first_map(cond_d) if si == 0 else draft.embed_map(si, maps[j])
+            mixed_d = cfg_mix(draft.get_logits(draft.blocks(x, cond_d, None), cond_d), B, cfg * si / (K - 1))
+            idx = sample_with_noise_(mixed_d, noise.exponential("draft", B * l, V), top_k, top_p)
+            fh, nm = vq.next_input(si, fh, idx)
+            idx_d.append(idx); snaps.append(fh.clone()); maps.append(nm)
+            stats["draft_stages"] += 1
+            xt = target.first_map(cond_t) if si == 0 else target.embed_map(si, maps[j])
+            logits_t = target.forward_window(si, [xt], cond_t)[0]
+            stats["target_passes"] += 1
+            mixed_t = filter_top_k_top_p_(cfg_mix(logits_t, B, cfg * si / (K - 1)), top_k, top_p)
+            o, acc, _, _ = verify_tokens(mixed_t.view(-1, V), mixed_d.view(-1, V), idx.view(-1), u_all[j][0], u_all[j][1])
+            out_idx.append(o.view(B, l))
+            stats["stage_accept_tokens"][si] += int(acc.sum()); stats["stage_tokens"][si] += B * l
+            if not bool(acc.all()):
+                break
+            n_ok += 1
+        for j in range(len(idx_d), g):           # never drafted: keep the 'draft' stream in step
+            noise.exponential("draft", B * draft.ls[s + j], V)
         a = min(n_ok + 1, g)
         for j in range(a - 1):
             final_idx.append(idx_d[j])

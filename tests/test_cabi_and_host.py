@@ -92,3 +92,48 @@ def test_stage_tables_and_phi_index():
     from sdvar_b200.models.quant import _PhiBank
     bank = _PhiBank(4, 32, 0.5, "partial")
     assert [bank.index(si / 9) for si in range(10)] == [0, 0, 1, 1, 1, 2, 2, 3, 3, 3]
+
+
+def test_conv_weight_packing_and_tap_order_cpu():
+    """host side of sdvar_conv_nhwc: weights are packed (taps, Cout, Cin) with tap = ky*3 + kx and the kernel reads the input at
+    (y + ky - 1, x + kx - 1) with zero fill outside the image.  Restated on the CPU with plain tensor ops and compared with
+    F.conv2d, so the convention the kernel implements is pinned without a GPU."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from sdvar_b200.models.vqvae import _packed_w
+    torch.manual_seed(0)
+    for k in (3, 1):
+        conv = nn.Conv2d(32, 24, k, padding=k // 2)
+        wp = _packed_w(conv).float()                                  # (taps, Cout, Cin), bf16-rounded
+        assert wp.shape == (k * k, 24, 32)
+        x = torch.randn(2, 32, 6, 5)
+        xp = F.pad(x, (k // 2,) * 4)
+        out = torch.zeros(2, 24, 6, 5)
+        for tap in range(k * k):
+            ky, kx = (tap // 3, tap % 3) if k == 3 else (0, 0)
+            out += torch.einsum("nchw,oc->nohw", xp[:, :, ky:ky + 6, kx:kx + 5], wp[tap])
+        ref = F.conv2d(x, conv.weight.detach().bfloat16().float(), None, padding=k // 2)
+        assert torch.allclose(out, ref, atol=1e-4), float((out - ref).abs().max())
+
+
+def test_conv_tiling_predicate_matches_the_c_abi_rule():
+    """_tc_ok (python) mirrors the geometry rule documented in include/sdvar_b200.h: Cin % 32 == 0 and 128 consecutive pixels
+    form a box of the image; everything else falls back to the library convolution"""
+    import torch.nn as nn
+    from sdvar_b200.models import vqvae
+
+    class FakeX:
+        def __init__(self, shape): self.shape = shape
+    real_fast = vqvae._fast
+    vqvae._fast = lambda x: True
+    try:
+        c3 = nn.Conv2d(160, 160, 3, padding=1)
+        ok = lambda c, shp, **kw: vqvae._tc_ok(c, FakeX(shp), **kw)
+        assert ok(c3, (1, 160, 256, 256)) and ok(c3, (1, 160, 16, 16)) and ok(c3, (3, 160, 4, 4)) and ok(c3, (1, 160, 1, 128))
+        assert not ok(c3, (1, 160, 12, 12)) and not ok(c3, (1, 160, 16, 48)) and not ok(c3, (1, 160, 3, 16))
+        assert not ok(nn.Conv2d(24, 32, 3, padding=1), (1, 24, 16, 16))                    # Cin % 32
+        assert not ok(nn.Conv2d(32, 32, 3, stride=2), (1, 32, 16, 16))                     # encoder downsample
+        assert not ok(nn.Conv2d(160, 3, 3, padding=1), (1, 160, 16, 16)) and ok(nn.Conv2d(160, 3, 3, padding=1), (1, 160, 16, 16), nchw_f32=True)
+        assert ok(nn.Conv2d(640, 1920, 1), (1, 640, 16, 16))
+    finally:
+        vqvae._fast = real_fast

@@ -2,6 +2,8 @@
 data-parallel plumbing (gloo, world_size 2)."""
 import os
 
+import numpy as np
+
 import pytest
 import torch
 import torch.distributed as dist
@@ -164,3 +166,29 @@ def test_uint8_gather_and_async_stats_gloo_world2():
     for rank, out, st in res:
         assert out.dtype == torch.uint8 and torch.equal(out, want)
         assert st == dict(rounds=3, target_passes=4, draft_stages=6, accepted_tokens=30, rejected_tokens=2)
+
+
+@pytest.mark.parametrize("pair,gamma", [("equal", 2), ("equal", 4), ("far", 2), ("far", 3)])
+def test_lazy_schedule_equals_window_schedule(pair, gamma):
+    """spec level (CPU, fp32): verify_mode='lazy' -- draft and verify stage by stage with early exit, the unreached stages' noise
+    drawn and dropped -- commits the same tokens and advances as the one-pass window schedule.  (The oracle's window pass and
+    its incremental passes agree to fp32 re-association, 1e-7, which moves a decision only on an exact near-tie -- not with
+    these seeds; on the device the two passes are bit-identical and the same identity is asserted exactly in
+    tests/test_engine_gpu.py::test_lazy_verify_equals_window_verify.)"""
+    vq, d, t = _models()
+    if pair == "equal":
+        t = RefVAR(var_state_dict(2, patch_nums=P4, seed=1, tag="draft", **KW), P4)
+    B, lab = 2, torch.tensor([4, 5])
+    kw = dict(cfg=1.5, gamma=gamma, top_k=900, top_p=0.96)
+    fw, iw, sw = sd_generate(d, t, vq, B, lab, ReplayNoise(5), verify_mode="window", **kw)
+    fl, il, sl = sd_generate(d, t, vq, B, lab, ReplayNoise(5), verify_mode="lazy", **kw)
+    assert all(torch.equal(a, b) for a, b in zip(iw, il)) and torch.allclose(fw, fl, atol=1e-6)
+    for k in ("advance", "rounds", "accepted_tokens", "rejected_tokens", "stage_tokens", "stage_accept_tokens"):
+        assert sw[k] == sl[k], k
+    K = len(P4)
+    windows = [min(gamma, K - s) for s in np.cumsum([0] + sw["advance"][:-1])]
+    assert sw["draft_stages"] == sum(windows) and sw["target_passes"] == sw["rounds"]
+    # lazy: one draft stage + one target pass per VERIFIED stage; every committed stage is verified, wasted ones are not
+    assert sl["draft_stages"] == sl["target_passes"] and sl["target_passes"] <= sum(windows) and sl["target_passes"] >= K
+    if pair == "far":
+        assert sl["rejected_tokens"] > 0 and sl["target_passes"] < sum(windows)
