@@ -219,6 +219,12 @@ int sdvar_bias_residual_nhwc(const sdvar_bf16* h, const float* bias, const sdvar
  * or is a multiple of it, H likewise for the rows left.  Zero padding comes from the TMA unit's out-of-bounds fill. */
 int sdvar_conv_nhwc(const sdvar_bf16* x, int N, int H, int W, int Cin, const sdvar_bf16* w_packed, int taps, int Cout,
                     const float* bias, const sdvar_bf16* res, sdvar_bf16* y, float* y_f32_nchw, float lo, float hi, void* stream);
+/* Upsample2x of the decoder in one step (models/basic_vae.py:28-33: F.interpolate(scale_factor=2, mode='nearest') then a 3x3
+ * convolution): y (N,2H,2W,Cout) = conv3x3(nearest2x(x)) + bias, computed as four 2x2 convolutions on the low-resolution x
+ * (N,H,W,Cin), one per output parity (a,b).  w_par (16, Cout, Cin) bf16: matrix (a*2+b)*4 + (u*2+v) is the sum of the 3x3 taps
+ * that fall on input pixel (Y+a-1+u, X+b-1+v) of output pixel (2Y+a, 2X+b).  Same geometry rules as sdvar_conv_nhwc. */
+int sdvar_conv_up2x_nhwc(const sdvar_bf16* x, int N, int H, int W, int Cin, const sdvar_bf16* w_par, int Cout, const float* bias,
+                         sdvar_bf16* y, void* stream);
 /* nearest-neighbour 2x upsampling (models/basic_vae.py:31), channels-last bf16: x (N,H,W,C) -> y (N,2H,2W,C). */
 int sdvar_upsample2x_nhwc(const sdvar_bf16* x, int N, int H, int W, int C, sdvar_bf16* y, void* stream);
 

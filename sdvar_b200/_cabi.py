@@ -24,7 +24,7 @@ EXPORTS = [
     "sdvar_sample_cfg_topk_topp", "sdvar_verify_accept_resample", "sdvar_verify_workspace_bytes", "sdvar_verify_top1", "sdvar_vq_next_input", "sdvar_vq_area_down",
     "sdvar_embed_next_map", "sdvar_first_map", "sdvar_ln_modulate", "sdvar_silu_bf16", "sdvar_f32_to_bf16", "sdvar_image_to_u8",
     "sdvar_gemm_bf16", "sdvar_attention", "sdvar_var_forward", "sdvar_profile_begin", "sdvar_profile_end",
-    "sdvar_groupnorm_silu_nhwc", "sdvar_conv_nhwc", "sdvar_bias_residual_nhwc", "sdvar_upsample2x_nhwc", "sdvar_vq_nearest_code",
+    "sdvar_groupnorm_silu_nhwc", "sdvar_conv_nhwc", "sdvar_conv_up2x_nhwc", "sdvar_bias_residual_nhwc", "sdvar_upsample2x_nhwc", "sdvar_vq_nearest_code",
     "sdvar_debug_spec_expf",
 ]
 PROFILE_FAMILIES = ("gemm", "attention", "ln_modulate", "sample", "verify", "vq", "embed", "misc", "conv")
@@ -246,6 +246,12 @@ def conv_nhwc(x, N, H, W, Cin, w_packed, taps, Cout, bias, res, y=None, y_f32_nc
     vp = lambda t: C.c_void_p(t.data_ptr() if t is not None else 0)
     _check(lib().sdvar_conv_nhwc(vp(x), N, H, W, Cin, vp(w_packed), taps, Cout, ptr(bias), vp(res), vp(y), ptr(y_f32_nchw),
                                  C.c_float(lo), C.c_float(hi), stream_ptr()), "sdvar_conv_nhwc")
+
+
+def conv_up2x_nhwc(x, N, H, W, Cin, w_par, Cout, bias, y):
+    """conv3x3(nearest2x(x)) + bias as four 2x2 parity convolutions on the low-resolution input; see include/sdvar_b200.h"""
+    _check(lib().sdvar_conv_up2x_nhwc(C.c_void_p(x.data_ptr()), N, H, W, Cin, C.c_void_p(w_par.data_ptr()), Cout, ptr(bias),
+                                      C.c_void_p(y.data_ptr()), stream_ptr()), "sdvar_conv_up2x_nhwc")
 
 
 def upsample2x_nhwc(x, N, H, W, Cc, y):

@@ -41,7 +41,10 @@ struct Cfg {
 };
 
 struct Params {
-  int Nimg, H, W, Cin, Cout, taps;      // taps: 9 (3x3, padding 1) or 1
+  int Nimg, H, W, Cin, Cout, taps;      // taps: 9 (3x3, padding 1), 1, or 4 (one parity class of upsample2x + 3x3, see below)
+  int tw, dy0, dx0, wtap0;              // tap t reads the input at (y + dy0 + t / tw, x + dx0 + t % tw) with weight matrix wtap0 + t
+  int wtaps;                            // weight matrices in w_packed (9, 1, or 16 for the four parity classes)
+  int up, pa, pb;                       // up: the output pixel of input-grid pixel (n, Y, X) is (n, 2Y + pa, 2X + pb) of a (2H, 2W) image
   int BW, BH;                           // pixel box of one CTA: BW x BH x (128 / (BW*BH)) images
   long long M;                          // Nimg * H * W
   const float* bias;                    // nullable
@@ -155,6 +158,12 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, uint32_t tmem_bas
     const int nb = (int)(t - mb * num_n);
     const long long row = (mb * 2 + rank) * BM + ew * 32 + lane;
     const bool rv = row < p.M;
+    long long orow = row;               // output pixel (channels-last row) this thread writes
+    if (p.up && rv) {
+      const long long n = row / HW;
+      const int rem = (int)(row - n * HW), Y = rem / p.W, X = rem - Y * p.W;
+      orow = (n * (2 * p.H) + 2 * Y + p.pa) * (2 * p.W) + 2 * X + p.pb;
+    }
     ptx::mbar_wait(&tfull[as], aphase);
     ptx::tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
@@ -175,9 +184,18 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, uint32_t tmem_bas
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         if (p.bias != nullptr) {
+          if (col + 16 <= p.Cout && (p.Cout & 3) == 0) {      // whole chunk in range: four 16-byte loads (warp-uniform, L1-resident)
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (col + j < p.Cout) v[j] += __ldg(p.bias + col + j);
+            for (int q = 0; q < 4; ++q) {
+              const float4 bb = __ldg(b4 + q);
+              v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col + j < p.Cout) v[j] += __ldg(p.bias + col + j);
+          }
         }
         if (p.out_bf16 != nullptr) {
           const uint32_t* rw = reinterpret_cast<const uint32_t*>(rs);
@@ -186,7 +204,7 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, uint32_t tmem_bas
             v[2 * j] += __uint_as_float(rw[j] << 16);
             v[2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
           }
-          uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row * p.Cout + col);
+          uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + orow * p.Cout + col);
           op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           if (cv1)
             op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
@@ -259,13 +277,13 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int y0 = rem / p.W, x0 = rem - y0 * p.W;
         const int col0 = nb * BN + (int)rank * (BN / 2);       // this CTA's half of the weight tile
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          const int dy = p.dy0 + tap / p.tw, dx = p.dx0 + tap % p.tw;
           for (int cc = 0; cc < chunks; ++cc) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * C::stage_bytes;
             mbar_expect_tx_leader(&full[stage], A_BYTES + C::b_bytes);
             tma_load_4d_pair(sa, &tmA, &full[stage], cc * KC, x0 + dx, y0 + dy, n0);
-            tma_load_3d_pair(sa + A_BYTES, &tmB, &full[stage], cc * KC, col0, tap);
+            tma_load_3d_pair(sa + A_BYTES, &tmB, &full[stage], cc * KC, col0, p.wtap0 + tap);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -389,10 +407,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_expect_tx_leader(&a_full[as], C::a_bytes);
           tma_load_4d_pair(sA + (size_t)as * C::a_stride, &tmA, &a_full[as], cc * KCH, x0 - 1, y0 - 1, n0);
           if (++as == kAS) { as = 0; aph ^= 1; }
-          for (int ky = 0; ky < 3; ++ky) {                     // weights of one kernel row: (KCH, BN/2, 3 taps) in one box
+          for (int ky = 0; ky < p.tw; ++ky) {                  // weights of one kernel row: (KCH, BN/2, tw taps) in one box
             ptx::mbar_wait(&b_empty[bs], bph ^ 1);
-            mbar_expect_tx_leader(&b_full[bs], C::b_bytes);
-            tma_load_3d_pair(sB + (size_t)bs * C::b_stride, &tmB, &b_full[bs], cc * KCH, col0, 3 * ky);
+            mbar_expect_tx_leader(&b_full[bs], (uint32_t)(p.tw * C::b_tap));
+            tma_load_3d_pair(sB + (size_t)bs * C::b_stride, &tmB, &b_full[bs], cc * KCH, col0, p.wtap0 + p.tw * ky);
             if (++bs == kBS) { bs = 0; bph ^= 1; }
           }
         }
@@ -410,13 +428,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int cc = 0; cc < chunks; ++cc) {
           ptx::mbar_wait(&a_full[as], aph);
           const uint32_t strip = ptx::smem_u32(sA + (size_t)as * C::a_stride);
-          for (int ky = 0; ky < 3; ++ky) {
+          for (int ky = 0; ky < p.tw; ++ky) {
             ptx::mbar_wait(&b_full[bs], bph);
             ptx::tc_fence_after();
-            const uint32_t a_row = strip + (uint32_t)(ky * C::strip_px * C::rowb);
+            // strip row 0 is image row y - 1, strip pixel 0 is x - 1: tap (ky, kx) reads row y + dy0 + ky, pixel x + dx0 + kx
+            const uint32_t a_row = strip + (uint32_t)(((p.dy0 + 1 + ky) * C::strip_px + p.dx0 + 1) * C::rowb);
             const uint32_t b_row = ptx::smem_u32(sB + (size_t)bs * C::b_stride);
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
+              if (kx >= p.tw) break;
 #pragma unroll
               for (int k = 0; k < KCH / UMMA_K; ++k)
                 umma2_f16(d, umma_desc_k_rows<C::rowb>(a_row + kx * C::rowb + k * UMMA_K * 2),
@@ -447,9 +467,9 @@ static int launch_halo(const void* x, const void* w_packed, const Params& p, cud
   const uint64_t dimsA[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Nimg};
   const uint64_t strA[3] = {(uint64_t)p.Cin * 2, (uint64_t)p.W * p.Cin * 2, (uint64_t)p.H * p.W * p.Cin * 2};
   const uint32_t boxA[4] = {(uint32_t)KCH, (uint32_t)C::strip_px, 3u, 1u};
-  const uint64_t dimsB[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, 9u};
+  const uint64_t dimsB[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)p.wtaps};
   const uint64_t strB[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.Cout * p.Cin * 2};
-  const uint32_t boxB[3] = {(uint32_t)KCH, (uint32_t)(BN / 2), 3u};
+  const uint32_t boxB[3] = {(uint32_t)KCH, (uint32_t)(BN / 2), (uint32_t)p.tw};
   if (KCH == 32) {
     if (int rc = make_tmap_bf16_sw64(&tmA, x, 4, dimsA, strA, boxA)) return rc;
     if (int rc = make_tmap_bf16_sw64(&tmB, w_packed, 3, dimsB, strB, boxB)) return rc;
@@ -483,6 +503,53 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& 
 
 using namespace sdvar;
 
+// one launch: `taps` = tw*tw taps at offsets (dy0 + t / tw, dx0 + t % tw) using weight matrices wtap0 + t of the `wtaps` packed ones;
+// up = 1 writes input-grid pixel (n, Y, X) to pixel (n, 2Y + pa, 2X + pb) of a (2H, 2W) output
+static int conv_dispatch(const sdvar_bf16* x, int N, int H, int W, int Cin, const sdvar_bf16* w_packed, int wtaps, int tw, int dy0, int dx0,
+                         int wtap0, int up, int pa, int pb, int Cout, const float* bias, const sdvar_bf16* res, sdvar_bf16* y,
+                         float* y_f32_nchw, float lo, float hi, cudaStream_t st) {
+  // pixel box of one CTA: 128 consecutive pixels in (n, y, x) order must be a box BW x BH x BI
+  const int BW = W < conv::BM ? W : conv::BM;
+  SDVAR_REQUIRE(W % BW == 0 && conv::BM % BW == 0, "W=%d must divide or be a multiple of %d", W, conv::BM);
+  const int BH = H < conv::BM / BW ? H : conv::BM / BW;
+  SDVAR_REQUIRE(H % BH == 0 && (conv::BM / BW) % BH == 0, "H=%d does not tile into %d-pixel boxes of width %d", H, conv::BM, BW);
+  const int BI = conv::BM / (BW * BH);
+  const int taps = tw * tw;
+  conv::Params p;
+  p.Nimg = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.BW = BW; p.BH = BH;
+  p.tw = tw; p.dy0 = dy0; p.dx0 = dx0; p.wtap0 = wtap0; p.wtaps = wtaps; p.up = up; p.pa = pa; p.pb = pb;
+  p.M = (long long)N * H * W;
+  p.bias = bias;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res);
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(y);
+  p.out_f32_nchw = y_f32_nchw;
+  p.lo = lo; p.hi = hi;
+  const int BN = Cout % 160 == 0 ? 160 : Cout >= 128 ? 128 : Cout > 16 ? 32 : 16;
+  ProfileScope prof(st, FAM_CONV, 2.0 * (double)p.M * Cout * Cin * taps);
+  static const bool no_halo = getenv("SDVAR_CONV_NO_HALO") != nullptr;   // A/B switch for profiling
+  if (tw >= 2 && W % conv::BM == 0 && (BN == 160 || BN == 128 || BN == 16) && !no_halo) {
+    // rows of at least 128 pixels: halo-strip kernel (BN = 16: conv_out, bound by the activation stream alone)
+    if (BN == 160) return conv::launch_halo<160, 32>(x, w_packed, p, st);
+    if (BN == 16) return conv::launch_halo<16, 32>(x, w_packed, p, st);
+    return conv::launch_halo<128, 32>(x, w_packed, p, st);
+  }
+  CUtensorMap tmA, tmB;
+  const uint64_t dimsA[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  const uint64_t strA[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  const uint32_t boxA[4] = {(uint32_t)conv::KC, (uint32_t)BW, (uint32_t)BH, (uint32_t)BI};
+  if (int rc = make_tmap_bf16_sw64(&tmA, x, 4, dimsA, strA, boxA)) return rc;
+  const uint64_t dimsB[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)wtaps};
+  const uint64_t strB[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+  const uint32_t boxB[3] = {(uint32_t)conv::KC, (uint32_t)(BN / 2), 1u};
+  if (int rc = make_tmap_bf16_sw64(&tmB, w_packed, 3, dimsB, strB, boxB)) return rc;
+  switch (BN) {
+    case 160: return conv::launch<160>(tmA, tmB, p, st);
+    case 128: return conv::launch<128>(tmA, tmB, p, st);
+    case 32: return conv::launch<32>(tmA, tmB, p, st);
+    default: return conv::launch<16>(tmA, tmB, p, st);
+  }
+}
+
 extern "C" int sdvar_conv_nhwc(const sdvar_bf16* x, int N, int H, int W, int Cin, const sdvar_bf16* w_packed, int taps, int Cout,
                                const float* bias, const sdvar_bf16* res, sdvar_bf16* y, float* y_f32_nchw, float lo, float hi,
                                void* stream) {
@@ -495,43 +562,27 @@ extern "C" int sdvar_conv_nhwc(const sdvar_bf16* x, int N, int H, int W, int Cin
   SDVAR_REQUIRE(y_f32_nchw == nullptr || res == nullptr, "the NCHW fp32 output takes no skip connection");
   SDVAR_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)res & 15) == 0,
                 "16-byte alignment");
-  // pixel box of one CTA: 128 consecutive pixels in (n, y, x) order must be a box BW x BH x BI
-  const int BW = W < conv::BM ? W : conv::BM;
-  SDVAR_REQUIRE(W % BW == 0 && conv::BM % BW == 0, "W=%d must divide or be a multiple of %d", W, conv::BM);
-  const int BH = H < conv::BM / BW ? H : conv::BM / BW;
-  SDVAR_REQUIRE(H % BH == 0 && (conv::BM / BW) % BH == 0, "H=%d does not tile into %d-pixel boxes of width %d", H, conv::BM, BW);
-  const int BI = conv::BM / (BW * BH);
-  cudaStream_t st = (cudaStream_t)stream;
-  conv::Params p;
-  p.Nimg = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.BW = BW; p.BH = BH;
-  p.M = (long long)N * H * W;
-  p.bias = bias;
-  p.res = reinterpret_cast<const __nv_bfloat16*>(res);
-  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(y);
-  p.out_f32_nchw = y_f32_nchw;
-  p.lo = lo; p.hi = hi;
-  const int BN = Cout % 160 == 0 ? 160 : Cout >= 128 ? 128 : Cout > 16 ? 32 : 16;
-  ProfileScope prof(st, FAM_CONV, 2.0 * (double)p.M * Cout * Cin * taps);
-  static const bool no_halo = getenv("SDVAR_CONV_NO_HALO") != nullptr;   // A/B switch for profiling
-  if (taps == 9 && W % conv::BM == 0 && (BN == 160 || BN == 128 || BN == 16) && !no_halo) {
-    // rows of at least 128 pixels: halo-strip kernel (BN = 16: conv_out, bound by the activation stream alone)
-    if (BN == 160) return conv::launch_halo<160, 32>(x, w_packed, p, st);
-    if (BN == 16) return conv::launch_halo<16, 32>(x, w_packed, p, st);
-    return conv::launch_halo<128, 32>(x, w_packed, p, st);
-  }
-  CUtensorMap tmA, tmB;
-  const uint64_t dimsA[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-  const uint64_t strA[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-  const uint32_t boxA[4] = {(uint32_t)conv::KC, (uint32_t)BW, (uint32_t)BH, (uint32_t)BI};
-  if (int rc = make_tmap_bf16_sw64(&tmA, x, 4, dimsA, strA, boxA)) return rc;
-  const uint64_t dimsB[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)taps};
-  const uint64_t strB[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
-  const uint32_t boxB[3] = {(uint32_t)conv::KC, (uint32_t)(BN / 2), 1u};
-  if (int rc = make_tmap_bf16_sw64(&tmB, w_packed, 3, dimsB, strB, boxB)) return rc;
-  switch (BN) {
-    case 160: return conv::launch<160>(tmA, tmB, p, st);
-    case 128: return conv::launch<128>(tmA, tmB, p, st);
-    case 32: return conv::launch<32>(tmA, tmB, p, st);
-    default: return conv::launch<16>(tmA, tmB, p, st);
-  }
+  const int tw = taps == 9 ? 3 : 1;
+  return conv_dispatch(x, N, H, W, Cin, w_packed, taps, tw, taps == 9 ? -1 : 0, taps == 9 ? -1 : 0, 0, 0, 0, 0, Cout, bias, res, y, y_f32_nchw,
+                       lo, hi, (cudaStream_t)stream);
+}
+
+// conv3x3(padding 1) of the nearest-2x upsampled x WITHOUT materialising the upsampled tensor (reference Upsample2x,
+// models/basic_vae.py:31-33).  Output pixel (2Y+a, 2X+b) sees only the 2x2 input pixels (Y+a-1.., X+b-1..): the nine taps
+// collapse onto four whose weights are sums of the original ones, so each of the four parity classes (a, b) is a 2x2 convolution
+// on the LOW-resolution input -- 16 multiply-adds per output channel pair instead of 36, and no 4x larger intermediate.
+// w_par: (16, Cout, Cin) bf16, matrix (a*2 + b)*4 + (u*2 + v) = sum of the 3x3 weights that land on input pixel (Y+a-1+u, X+b-1+v).
+extern "C" int sdvar_conv_up2x_nhwc(const sdvar_bf16* x, int N, int H, int W, int Cin, const sdvar_bf16* w_par, int Cout,
+                                    const float* bias, sdvar_bf16* y, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SDVAR_REQUIRE(x && w_par && y, "NULL argument");
+  SDVAR_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cin % conv::KC == 0 && Cout > 0 && Cout % 8 == 0, "bad geometry N=%d H=%d W=%d Cin=%d Cout=%d",
+                N, H, W, Cin, Cout);
+  SDVAR_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_par & 15) == 0 && ((uintptr_t)y & 15) == 0, "16-byte alignment");
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b)
+      if (int rc = conv_dispatch(x, N, H, W, Cin, w_par, 16, 2, a - 1, b - 1, (a * 2 + b) * 4, 1, a, b, Cout, bias, nullptr, y, nullptr, 0.f,
+                                 0.f, (cudaStream_t)stream))
+        return rc;
+  return SDVAR_OK;
 }

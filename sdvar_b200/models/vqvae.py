@@ -49,6 +49,25 @@ def _packed_w(conv: nn.Conv2d) -> torch.Tensor:
     return conv._wp
 
 
+def _packed_w_up(conv: nn.Conv2d) -> torch.Tensor:
+    """(16, Cout, Cin) bf16 for conv3x3(nearest2x(x)): output pixel (2Y+a, 2X+b) reads the 2x2 input pixels (Y+a-1+u, X+b-1+v);
+    matrix (a*2+b)*4 + u*2+v is the sum (in fp32, rounded once) of the 3x3 taps that land there: rows ky in R[a][u], columns kx
+    in R[b][v] with R[0] = ({0}, {1,2}) and R[1] = ({0,1}, {2})"""
+    w = conv.weight
+    if getattr(conv, "_wpu", None) is None or conv._wpu.device != w.device or conv._wpu_ver != w._version:
+        R = (((0,), (1, 2)), ((0, 1), (2,)))
+        wf = w.detach().float()
+        mats = []
+        for a in range(2):
+            for b in range(2):
+                for u in range(2):
+                    for v in range(2):
+                        mats.append(sum(wf[:, :, ky, kx] for ky in R[a][u] for kx in R[b][v]))
+        conv._wpu = torch.stack(mats).to(torch.bfloat16).contiguous()
+        conv._wpu_ver = w._version
+    return conv._wpu
+
+
 def _tc_ok(conv: nn.Conv2d, x: torch.Tensor, nchw_f32: bool = False) -> bool:
     """shapes sdvar_conv_nhwc tiles (include/sdvar_b200.h): 3x3 padding 1 or 1x1, stride 1, Cin % 32 == 0, and 128 consecutive
     pixels form a box of the image"""
@@ -169,6 +188,14 @@ class _Up(nn.Module):
         self.conv = nn.Conv2d(c, c, 3, padding=1)
 
     def forward(self, x):
+        if _tc_ok(self.conv, x) and self.conv.kernel_size == (3, 3):
+            # upsample + convolution in one step: four 2x2 parity convolutions on the low-resolution input (sdvar_conv_up2x_nhwc)
+            from .. import _cabi
+            N, C, H, W = x.shape
+            co = self.conv.out_channels
+            y = torch.empty((N, co, 2 * H, 2 * W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+            _cabi.conv_up2x_nhwc(x, N, H, W, C, _packed_w_up(self.conv), co, _bias32(self.conv), y)
+            return y
         if _fast(x):
             from .. import _cabi
             N, C, H, W = x.shape

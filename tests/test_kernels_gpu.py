@@ -439,6 +439,42 @@ def test_conv_nhwc_image_epilogue(cuda_lib, N, Cin, H, W):
     assert torch.allclose(y, ref, rtol=0, atol=2e-5), float((y - ref).abs().max())
 
 
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(2, 160, 160, 8, 128), (1, 160, 160, 3, 256), (2, 320, 320, 16, 16), (2, 640, 640, 16, 16),
+                                           (3, 64, 128, 4, 4), (1, 320, 320, 64, 64)])
+def test_conv_up2x_nhwc_vs_torch(cuda_lib, N, Cin, Cout, H, W):
+    """Upsample2x of the decoder (models/basic_vae.py:28-33) in one step: four 2x2 parity convolutions on the low-resolution
+    input.  (1) against the same parity-summed bf16 weights applied in fp32 by torch: one bf16 rounding of the result;
+    (2) against the real thing, conv3x3(nearest2x(x)) with the unsummed bf16 weights: the weight sums are rounded once more, so
+    the tolerance is that of one extra bf16 rounding of the weights."""
+    from sdvar_b200.models.vqvae import _packed_w_up
+    x = hashed("cu.x", Cin + H, (N, Cin, H, W), 1.0).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    conv = torch.nn.Conv2d(Cin, Cout, 3, padding=1).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(hashed("cu.w", Cout, (Cout, Cin, 3, 3), 1.0 / math.sqrt(Cin * 9)).to(DEV).bfloat16().float())
+        conv.bias.copy_(hashed("cu.b", 1, (Cout,), 0.5).to(DEV))
+    wp = _packed_w_up(conv)
+    assert wp.shape == (16, Cout, Cin) and wp.dtype == torch.bfloat16
+    y = torch.full((N, Cout, 2 * H, 2 * W), float("nan"), device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    cuda_lib.conv_up2x_nhwc(x, N, H, W, Cin, wp, Cout, conv.bias.detach().float().contiguous(), y)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(y.float()).all())
+    xf = x.float()
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        ref1 = torch.empty(N, Cout, 2 * H, 2 * W, device=DEV)
+        for a in range(2):
+            for b in range(2):
+                k = wp[(a * 2 + b) * 4:(a * 2 + b) * 4 + 4].float().view(2, 2, Cout, Cin).permute(2, 3, 0, 1).contiguous()   # (Cout, Cin, u, v)
+                # output (2Y+a, 2X+b) reads input rows Y+a-1.., columns X+b-1..: pad one row/column on the side the parity reaches over
+                xp = torch.nn.functional.pad(xf, (1 - b, b, 1 - a, a))
+                ref1[:, :, a::2, b::2] = torch.nn.functional.conv2d(xp, k, conv.bias)
+        ref2 = conv(torch.nn.functional.interpolate(xf, scale_factor=2.0, mode="nearest"))
+    scale = float(ref2.abs().max())
+    e1 = (y.float() - ref1).abs()
+    assert float(e1.max()) < 2 ** -7 * scale + 1e-3, (float(e1.max()), scale)
+    e2 = (y.float() - ref2).abs()
+    assert float(e2.max()) < 2e-2 * scale and float(e2.mean()) < 3e-3 * float(ref2.abs().mean()) + 1e-5, (float(e2.max()), float(e2.mean()), scale)
+
+
 def test_conv_nhwc_rejects_untiled_shapes(cuda_lib):
     from sdvar_b200._cabi import SdvarError
     x = torch.zeros(1, 24, 16, 16, device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
