@@ -67,7 +67,8 @@ def parse():
                          "exit, or auto = lazy from the stage whose pass alone is compute-bound (SDVAR.LAZY_MIN_ROWS)")
     ap.add_argument("--px", type=int, default=256, choices=[256, 512], help="256: patch_nums 1..16 (L=680); 512: 1..32 (L=2240)")
     ap.add_argument("--shared-aln-target", action="store_true", help="target uses shared adaLN (the d36 layout, README.md:142-144)")
-    ap.add_argument("--cpu-sample-images", type=int, default=1)
+    ap.add_argument("--cpu-sample-images", type=int, default=4,
+                    help="images per step of the CPU reference arm / cpu_baseline leg (4 = the batch of BASELINE.json configs[0])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-bounds", action="store_true")
