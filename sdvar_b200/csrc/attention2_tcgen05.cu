@@ -36,10 +36,11 @@ constexpr int kKS = 6, kVS = 5;  // K / V^T ring depths: TMA latency x tile rate
 constexpr int kNS = 3;           // S accumulators in TMEM
 constexpr int Q_BYTES = BQ * D * 2, K_BYTES = BKV * D * 2, V_BYTES = D * BKV * 2;
 constexpr int kTmemCols = 512;   // S0..S2 at [0,384), O0/O1 at [384,512)
-constexpr size_t kSmemBytes = 1024 + 2 * Q_BYTES + kKS * K_BYTES + kVS * V_BYTES + 2048 /*row sums*/ + 512;
+constexpr size_t kSmemBytes = 1024 + 2 * Q_BYTES + kKS * K_BYTES + kVS * V_BYTES + 2048 /*row sums*/ + 512 /*barriers*/ + 256 /*per-head softmax offsets*/;
 
 struct Params {
   int H, Lq, kv_off, C, nqt, n_items;
+  uint32_t inv_nqt, inv_H;   // ceil(2^32 / d): it / d == __umulhi(it, inv) for it * (inv * d - 2^32) < 2^32 (items < 2^32 / d), checked by the launcher
   float log2e_scale;
   const float* scale_mul;  // [H] raw log-scale parameter
   const int* slot_map;     // pass-image -> KV-cache slot (nullptr: identity)
@@ -55,17 +56,20 @@ __device__ __forceinline__ float ex2(float x) {
 
 struct Item {
   int qt, bh, h, img, q0, nk, kvbh;   // kvbh: (cache slot, head) coordinate of the K / V tensor maps
+  int kv_lim;                         // keys visible to the item's last row = keys any of its rows can see
 };
 __device__ __forceinline__ Item decode(const Params& p, int it) {
   Item w;
-  w.qt = it % p.nqt;
-  w.bh = it / p.nqt;
-  w.img = w.bh / p.H;
+  // every role decodes every item: multiply-high instead of three integer divisions (~120 dependent instructions per item)
+  w.bh = p.nqt == 1 ? it : (int)__umulhi((uint32_t)it, p.inv_nqt);
+  w.qt = it - w.bh * p.nqt;
+  w.img = (int)__umulhi((uint32_t)w.bh, p.inv_H);
   w.h = w.bh - w.img * p.H;
   w.q0 = w.qt * BQ;
   w.kvbh = (p.slot_map != nullptr ? __ldg(p.slot_map + w.img) : w.img) * p.H + w.h;
   const int t_last = min(w.q0 + BQ, p.Lq) - 1;
-  w.nk = (p.kv_off + p.seg.begin[seg_of(p.seg, t_last) + 1] + BKV - 1) / BKV;
+  w.kv_lim = p.kv_off + p.seg.begin[seg_of(p.seg, t_last) + 1];
+  w.nk = (w.kv_lim + BKV - 1) / BKV;
   return w;
 }
 
@@ -93,6 +97,8 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint64_t* v_full = k_empty + kKS;  // [kVS]
   uint64_t* v_empty = v_full + kVS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + kVS);
+  float* sMC = reinterpret_cast<float*>(bars + 64);   // [H <= 64] exp(min(scale_mul_h, ln 100)) * log2e * scale: the softmax reference point of head h
+  if (threadIdx.x < p.H) sMC[threadIdx.x] = __expf(fminf(__ldg(p.scale_mul + threadIdx.x), 4.605170185988092f)) * p.log2e_scale;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -157,12 +163,12 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const int nk = decode(p, it).nk;
         const uint32_t qb = qn & 1;
         const uint64_t q_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ + qb * Q_BYTES));
-        ptx::mbar_spin(&q_full[qb], (qn >> 1) & 1);
         for (int j = 0; j < nk; ++j, ++tn) {
           const uint32_t sb = tn % kNS, spar = (tn / kNS) & 1, kb = tn % kKS, kpar = (tn / kKS) & 1;
           const uint64_t k_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(sK + kb * K_BYTES));
-          ptx::mbar_spin(&k_full[kb], kpar);
-          ptx::mbar_spin(&s_empty[sb], spar ^ 1);
+          // all the barriers of a tile probed together (one test_wait latency instead of two or three)
+          if (j == 0) ptx::mbar_spin3(&q_full[qb], (qn >> 1) & 1, &k_full[kb], kpar, &s_empty[sb], spar ^ 1);
+          else ptx::mbar_spin2(&k_full[kb], kpar, &s_empty[sb], spar ^ 1);
           ptx::tc_fence_after();
 #pragma unroll
           for (int k = 0; k < D / 16; ++k)
@@ -179,22 +185,28 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, D);
       uint32_t qn = 0, tn = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x, ++qn) {
-        const int nk = decode(p, it).nk;
+        const Item w = decode(p, it);
+        const int nk = w.nk;
         const uint32_t ob = qn & 1;
-        ptx::mbar_spin(&o_empty[ob], ((qn >> 1) & 1) ^ 1);   // O buffer drained by the epilogue
         for (int j = 0; j < nk; ++j, ++tn) {
           const uint32_t sb = tn % kNS, spar = (tn / kNS) & 1, vb = tn % kVS, vpar = (tn / kVS) & 1;
           const uint64_t v_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(sV + vb * V_BYTES));
           const uint32_t p_tmem = tmem_base + sb * 128;
-          ptx::mbar_spin(&v_full[vb], vpar);
-          ptx::mbar_spin(&p_full[sb], spar);
+          // o_empty: the O buffer was drained by the epilogue (first tile of the item only)
+          if (j == 0) ptx::mbar_spin3(&o_empty[ob], ((qn >> 1) & 1) ^ 1, &v_full[vb], vpar, &p_full[sb], spar);
+          else ptx::mbar_spin2(&v_full[vb], vpar, &p_full[sb], spar);
           ptx::tc_fence_after();
+          // only the 16-key steps that hold keys some row of the item can see: the P columns past them are exactly 0 (the softmax
+          // warps do not even write them), so the skipped steps would add 0 * V -- the short stages (30 keys at stage 3) and the
+          // tail tile of every stage otherwise pay 8 steps per tile
+          const int ksteps = (min(BKV, w.kv_lim - j * BKV) + 15) >> 4;
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // A = P from TMEM: 16 keys = 8 columns per K step
-              ptx::umma_f16_ts(tmem_O + ob * D, p_tmem + (kb * 4 + k) * 8, ptx::umma_desc_advance(v_desc, kb * (D * 128) + k * 32), idesc_o,
-                               (uint32_t)((j | kb | k) != 0));
+              if (kb * 4 + k < ksteps)
+                ptx::umma_f16_ts(tmem_O + ob * D, p_tmem + (kb * 4 + k) * 8, ptx::umma_desc_advance(v_desc, kb * (D * 128) + k * 32), idesc_o,
+                                 (uint32_t)((j | kb | k) != 0));
           ptx::umma_commit(&v_empty[vb]);
           ptx::umma_commit(&s_empty[sb]);   // the S/P accumulator is free again once this PV has read it
           if (j == nk - 1) ptx::umma_commit(&o_full[ob]);
@@ -214,7 +226,7 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const int t = w.q0 + r;
       const bool warp_active = (w.q0 + quarter * 32) < p.Lq;     // warp-uniform: any real query row in this warp
       const int limit = p.kv_off + p.seg.begin[seg_of(p.seg, min(t, p.Lq - 1)) + 1];   // padding rows mirror the last real row
-      const float mc = __expf(fminf(__ldg(p.scale_mul + w.h), 4.605170185988092f)) * c;
+      const float mc = sMC[w.h];
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
       for (int j = 0; j < w.nk; ++j, ++tn) {
         if ((tn & 1) != (uint32_t)g) continue;
@@ -222,6 +234,7 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint32_t tmem_S = tmem_base + sbuf * 128 + lane_addr;
         ptx::mbar_wait(&s_full[sbuf], spar);
         ptx::tc_fence_after();
+        const int chunks = (min(BKV, w.kv_lim - j * BKV) + 31) >> 5;   // 32-key chunks of this tile that hold visible keys
         if (warp_active) {
           // software-pipelined over the four 32-column chunks: chunk c+1 is in flight from TMEM while chunk c is
           // exponentiated, rounded to bf16 and stored over columns [16c, 16c+16) of the same accumulator (always behind the
@@ -235,8 +248,9 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
               uint32_t(&cur)[32] = half == 0 ? sa : sb;
               uint32_t(&nxt)[32] = half == 0 ? sb : sa;
               const int cc = q4 + half;
+              if (cc >= chunks) continue;          // warp-uniform: nothing visible from here on, the PV issuer skips these columns too
               ptx::tmem_ld_wait();
-              if (cc < 3) ptx::tmem_ld_32x32(tmem_S + (cc + 1) * 32, nxt);
+              if (cc + 1 < chunks) ptx::tmem_ld_32x32(tmem_S + (cc + 1) * 32, nxt);
               const int nvalid = limit - (j * BKV + cc * 32);   // keys of this chunk visible to this row
               uint32_t pk[16];
               if (__all_sync(0xffffffffu, nvalid >= 32)) {
@@ -251,10 +265,15 @@ attention_onepass_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
                 for (int i = 0; i < 16; ++i) pk[i] = 0u;
               } else {
+                // chunk that holds a row's last visible key: exponentials of all 32 columns, invisible ones masked by an AND.
+                // (Written as `(i < nvalid) ? ex2(..) : 0` the compiler emitted one divergent branch per element: clock64
+                // traces showed ~1 800 cycles for this one chunk -- every item of every stage has one -- against ~400 for a
+                // full chunk.)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                  const float e0 = (i < nvalid) ? ex2(fmaf(__uint_as_float(cur[i]), c, -mc)) : 0.0f;
-                  const float e1 = (i + 1 < nvalid) ? ex2(fmaf(__uint_as_float(cur[i + 1]), c, -mc)) : 0.0f;
+                  const uint32_t m0 = (uint32_t)-(int)(i < nvalid), m1 = (uint32_t)-(int)(i + 1 < nvalid);
+                  const float e0 = __uint_as_float(__float_as_uint(ex2(fmaf(__uint_as_float(cur[i]), c, -mc))) & m0);
+                  const float e1 = __uint_as_float(__float_as_uint(ex2(fmaf(__uint_as_float(cur[i + 1]), c, -mc))) & m1);
                   l4[(i >> 1) & 3] += e0 + e1;
                   pk[i >> 1] = pack_bf16x2(e0, e1);
                 }
@@ -349,6 +368,9 @@ int launch_onepass(const void* q, const void* k_cache, const void* vT_cache, int
   p.H = H; p.Lq = Lq; p.kv_off = kv_off; p.C = H * D;
   p.nqt = (Lq + BQ - 1) / BQ;
   p.n_items = p.nqt * H * imgs;
+  SDVAR_REQUIRE(H <= 64 && (long long)p.n_items * (p.nqt > H ? p.nqt : H) < (1ll << 31), "attention: H=%d / item count %d out of range", H, p.n_items);
+  p.inv_nqt = (uint32_t)(((1ull << 32) + p.nqt - 1) / p.nqt);
+  p.inv_H = (uint32_t)(((1ull << 32) + H - 1) / H);
   p.log2e_scale = scale * 1.4426950408889634f;
   p.scale_mul = scale_mul;
   p.slot_map = slot_map;

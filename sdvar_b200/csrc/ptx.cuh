@@ -56,6 +56,45 @@ __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
   while (!mbar_test(bar, parity)) {}
 }
 
+// two barriers at once: both probes are in flight together, so a pair of already-complete barriers costs one test_wait latency
+// (~150 cycles) instead of two -- the single-lane MMA issuers of the attention kernel wait on two or three barriers per tile
+__device__ __forceinline__ void mbar_spin2(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb) {
+  const uint32_t aa = smem_u32(a), ab = smem_u32(b);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 q, [%3], %4;\n"
+        "and.pred p, p, q;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(aa), "r"(pa), "r"(ab), "r"(pb)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_spin3(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb, uint64_t* c, uint32_t pc) {
+  const uint32_t aa = smem_u32(a), ab = smem_u32(b), ac = smem_u32(c);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q, r;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 q, [%3], %4;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 r, [%5], %6;\n"
+        "and.pred p, p, q;\n"
+        "and.pred p, p, r;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(aa), "r"(pa), "r"(ab), "r"(pb), "r"(ac), "r"(pc)
+        : "memory");
+  } while (!ok);
+}
+
 // ---- TMA ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
