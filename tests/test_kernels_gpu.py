@@ -394,6 +394,8 @@ def test_bias_residual_and_upsample_nhwc(cuda_lib, N, C, H, W, with_res):
     (1, 320, 320, 4, 256, 9, True, False),     # halo-strip kernel, two N tiles
     (3, 64, 128, 2, 128, 9, True, True),       # halo-strip kernel, BN=128, ragged last cluster tile
     (1, 32, 160, 1, 128, 9, False, True),      # halo-strip kernel, single image row: both dy halos out of bounds
+    (1, 32, 160, 3, 128, 9, True, True),       # halo-strip kernel, odd number of strips: the last cluster tile is half empty
+    (2, 64, 160, 2, 384, 9, False, True),      # halo-strip kernel, three strips per row: a CTA pair straddles two image rows
     (3, 640, 640, 16, 16, 9, True, False),     # four N tiles, one cluster tile per image
     (2, 320, 160, 32, 32, 9, False, True),
     (2, 640, 320, 32, 32, 1, False, True),     # nin_shortcut (1x1)
