@@ -380,9 +380,15 @@ def main():
         out["bounds"] = bounds
 
     if not args.no_profile:   # roofline leg: one extra step with per-family CUDA-event timing on the launch stream
+        # The per-family CUDA events sit on each kernel's own launch stream.  The timed region above overlaps the draft's work
+        # with the target's on a second stream (SDVAR.OVERLAP_MAX_ROWS); co-running kernels stretch each other, so THIS leg runs
+        # the two streams back to back: the figures are the kernels' own durations, not their share of a shared GPU.
+        ov_saved = sd.OVERLAP_MAX_ROWS
+        sd.OVERLAP_MAX_ROWS = 0
         _cabi.profile_begin()
         st = step(10_000, False)
         prof = _cabi.profile_end()
+        sd.OVERLAP_MAX_ROWS = ov_saved
         kern = {}
         for fam, (ms, work, n) in prof.items():
             if n == 0:
@@ -408,6 +414,7 @@ def main():
                                "traffic_source": tsrc,
                                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the family's launches)",
                                "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
+                               "timing_note": "per-launch CUDA events in one extra step with the draft/target stream overlap switched off (kernels timed alone, not co-running)",
                                "share_of_step_ms": g["ms"], "launches": g["launches"]}
         for k, v in kern.items():
             v["frac"] = v["achieved"] / (pk["tf_sustained"] if v["bound"] == "tensor" else pk["hbm"])
