@@ -102,15 +102,32 @@ static int find_seg(const int* seg_begin, int S, int pos) {
 /* Two arithmetic regimes, chosen by the (launch-uniform) filter setting:
  *   no filter  : softmax sum in the canonical 256-lane float order over the whole row (canon_sum);
  *   top-k/top-p: every sum is an INTEGER sum of fixed-point terms, hence independent of the summation order -- the kernel
- *                may compact the survivors of the top-k cut and histogram them in any order and still agree bit for bit:
+ *                may histogram the row in any order (shared-memory atomics) and still agree bit for bit:
  *                  E_v    = (uint64) rint(e_v * 2^40)             e_v = sdvar_spec_expf(x_v - max) in [0,1]
- *                  Z      = (float)(sum_v E_v) * 2^-40            (u64 -> f32 round-to-nearest, exact scaling)
- *                  mass_v = (uint32) rint((e_v / Z) * 2^30)       top-p mass of v, exact integer cumulation
- *                  removed by top-p  <=>  sum{mass_w : w alive, x_w <= x_v} <= floor(thr * 2^30)  and x_v is not the row maximum
- *                (the reference accumulates float probabilities in ascending order, helpers.py:12-16; tie groups are kept whole).
+ *                  Zi     = sum_v E_v  over the survivors of the top-k cut
+ *                  thrE   = floor(Zi * floor(thr * 2^30) / 2^30)  the removable mass, in units of 2^-40 (exact integer arithmetic)
+ *                  removed by top-p  <=>  sum{E_w : w alive, x_w <= x_v} <= thrE  and x_v is not the row maximum
+ *                  Z2     = (float)(sum of the remaining E_v) * 2^-40
+ *                (the reference accumulates float probabilities in ascending order, helpers.py:12-16; tie groups are kept whole.
+ *                 Comparing fixed-point numerators with thrE is the same test as comparing probabilities with thr, without a
+ *                 division per entry.)
+ *                The exponential race argmax p_v / noise_v (helpers.py:19 via torch.multinomial) is run on the numerators,
+ *                argmax e_v * R(noise_v), with R a division-free reciprocal (magic-constant seed + 4 Newton steps in fma; relative
+ *                error < 2^-22): the common factor 1/Z2 cannot change the winner beyond rounding.  prob_out = e_win / Z2.
  * Ordering is by VALUE: -0 and +0 are the same logit (keys are taken of x + 0). */
 #define FIX_E 1099511627776.0f /* 2^40 */
 #define FIX_M 1073741824.0f    /* 2^30 */
+
+/* reciprocal of the race: y0 = bits(0x7EF311C7 - bits(n)), then y <- y + y * (1 - n y), SDVAR_RCP_STEPS times, every step two fmaf */
+#define SDVAR_RCP_STEPS 4
+float sdvar_spec_rcp(float n) {
+  float y = u2f(0x7EF311C7u - f2u(n));
+  for (int i = 0; i < SDVAR_RCP_STEPS; ++i) {
+    const float t = fmaf(-n, y, 1.0f);
+    y = fmaf(y, t, y);
+  }
+  return y;
+}
 
 static int cmp_u32(const void* a, const void* b) {
   const uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
@@ -152,44 +169,42 @@ static long long sample_row(const float* xc, const float* xu, float t1, float t2
     if (prob_out) *prob_out = bp;
     return bi;
   }
+  static __thread uint64_t Ei[65536];
   uint64_t Zi = 0;
-  for (int v = 0; v < V; ++v) Zi += (uint64_t)llrintf(e[v] * FIX_E);
+  for (int v = 0; v < V; ++v) { Ei[v] = (uint64_t)llrintf(e[v] * FIX_E); Zi += Ei[v]; }
   if (thr >= 0.0f) {
-    const float Z = (float)Zi * (1.0f / FIX_E);
-    const uint32_t thr_i = (uint32_t)(thr * FIX_M); /* floor */
-    static __thread uint32_t mass[65536], srt[65536];
+    const uint32_t thr_fix = (uint32_t)(thr * FIX_M); /* floor */
+    const uint64_t thrE = (uint64_t)(((unsigned __int128)Zi * thr_fix) >> 30);
+    static __thread uint32_t srt[65536];
     int n = 0;
-    for (int v = 0; v < V; ++v) {
-      mass[v] = (e[v] > 0.0f) ? (uint32_t)llrintf((e[v] / Z) * FIX_M) : 0u;
+    for (int v = 0; v < V; ++v)
       if (x[v] > -INFINITY) srt[n++] = keys[v];
-    }
     qsort(srt, (size_t)n, sizeof(uint32_t), cmp_u32);
-    /* T = largest alive key with mass{key <= T} <= thr_i (0 = nothing removable) */
+    /* T = largest alive key with E{alive, key <= T} <= thrE (0 = nothing removable) */
     uint32_t T = 0;
     for (int i = 0; i < n; ++i) {
       if (i + 1 < n && srt[i + 1] == srt[i]) continue; /* evaluate a tie group at its last member */
       uint64_t acc = 0;
       for (int v = 0; v < V; ++v)
-        if (x[v] > -INFINITY && keys[v] <= srt[i]) acc += mass[v];
-      if (acc <= thr_i) T = srt[i]; else break;
+        if (x[v] > -INFINITY && keys[v] <= srt[i]) acc += Ei[v];
+      if (acc <= thrE) T = srt[i]; else break;
     }
     for (int v = 0; v < V; ++v)
-      if (x[v] > -INFINITY && keys[v] <= T && keys[v] != kmax) { x[v] = -INFINITY; e[v] = 0.0f; }
+      if (x[v] > -INFINITY && keys[v] <= T && keys[v] != kmax) { x[v] = -INFINITY; e[v] = 0.0f; Ei[v] = 0; }
   }
   if (noise == NULL) return -1;
   uint64_t Z2i = 0;
-  for (int v = 0; v < V; ++v) Z2i += (uint64_t)llrintf(e[v] * FIX_E);
+  for (int v = 0; v < V; ++v) Z2i += Ei[v];
   const float Z2 = (float)Z2i * (1.0f / FIX_E);
   float best = -1.0f;
   long long bi = 0;
   float bp = 0.0f;
   for (int v = 0; v < V; ++v) {
-    if (e[v] == 0.0f) continue; /* masked or underflowed: cannot win the race (0 / noise = 0 > -1 only when nothing else is alive) */
-    const float p = e[v] / Z2;
-    const float r = p / noise[v];
-    if (r > best) { best = r; bi = v; bp = p; }
+    if (!(x[v] > -INFINITY)) continue; /* masked: not in the race (an underflowed survivor runs with r = 0) */
+    const float r = e[v] * sdvar_spec_rcp(noise[v]);
+    if (r > best) { best = r; bi = v; bp = e[v]; }
   }
-  if (prob_out) *prob_out = bp;
+  if (prob_out) *prob_out = best >= 0.0f ? bp / Z2 : 0.0f;
   return bi;
 }
 

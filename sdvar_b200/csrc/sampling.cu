@@ -174,6 +174,26 @@ __device__ __forceinline__ void block_max_u32x2(uint32_t& a, uint32_t& b, RedSme
   for (int k = 0; k < kWarps; ++k) { a = max(a, s.u[slot][0][k]); b = max(b, s.u[slot][1][k]); }
   slot ^= 1;
 }
+// two u32 maxima and two float sums behind ONE barrier (the sums feed a heuristic: their order is fixed but not part of any spec)
+__device__ __forceinline__ void block_stats(uint32_t& a, uint32_t& b, float& f0, float& f1, RedSmem& s, int& slot) {
+  a = __reduce_max_sync(0xffffffffu, a);
+  b = __reduce_max_sync(0xffffffffu, b);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    f0 += __shfl_xor_sync(0xffffffffu, f0, off);
+    f1 += __shfl_xor_sync(0xffffffffu, f1, off);
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s.u[slot][0][w] = a; s.u[slot][1][w] = b; s.f[slot][0][w] = f0; s.f[slot][1][w] = f1; }
+  __syncthreads();
+  f0 = 0.0f; f1 = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kWarps; ++k) {
+    a = max(a, s.u[slot][0][k]); b = max(b, s.u[slot][1][k]);
+    f0 += s.f[slot][0][k]; f1 += s.f[slot][1][k];
+  }
+  slot ^= 1;
+}
 __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, RedSmem& s, int& slot) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -210,21 +230,31 @@ __global__ void spec_expf_kernel(const float* __restrict__ x, long long n, float
 // ================================================================================================
 // Two kernels, selected by the launch-uniform filter setting (the spec has the same two regimes):
 //   k3_plain_kernel     no top-k / top-p: CFG mix, softmax in the canonical 256-lane float order, exponential race.
-//   k3_filtered_kernel  top-k and/or top-p.  Round 1 searched the k-th largest key and the top-p threshold by bisection,
-//                       ~26 block-wide barrier rounds of 16 compares per thread each, and ran every exponential and division
-//                       on all V entries although only ~k survive (0.15-0.23 of HBM).  Now:
-//     1. the exact k-th largest value comes from ONE shared-memory histogram pass (512 value-space bins, integer atomics),
-//        a suffix scan over the bins, and an exact rank among the handful of candidates in the crossing bin;
-//     2. the survivors (~top_k of V) are compacted into shared memory together with their noise and vocabulary index, so
-//        exponentials, probabilities, divisions and the race touch ~k/256 entries per thread instead of V/256;
-//     3. every sum of the filtered regime is an integer sum of fixed-point terms (spec: E = rint(e 2^40), mass =
-//        rint(p 2^30)), so it does not depend on the order in which the atomics / the compaction happen to run: the kernel
-//        is free to reorder and still bit-exact to oracle/spec_c; the top-p cut is a second histogram (of masses) + scan +
-//        exact resolution inside the crossing bin.
-//     Degenerate rows (more than 256 candidates in a crossing bin, non-finite value range) take bisection fall-backs.
-constexpr int kBins = 512;
+//   k3_filtered_kernel  top-k and/or top-p.  Round 1 searched both cuts by bisection (~26 block-wide barrier rounds, 0.15-0.23
+//                       of HBM); round 2 (first half) compacted the survivors of a histogram cut into shared memory and worked
+//                       on the list (16 barriers, ~2060 instructions per thread-row, 0.28-0.38).  v3, this one:
+//     1. the row never leaves the registers.  ONE pass computes every exponential (packed fp32x2) and adds each entry to three
+//        shared-memory histograms over 1024 value bins: count, and the two 20-bit limbs of E = rint(e * 2^40).  Bin index and
+//        limbs come from magic-addend roundings on the packed pipe -- no float<->int conversion, no division;
+//     2. one block scan over the bins (from the top) gives, for every bin, the entries and the mass above it, hence the bin
+//        the top-k cut falls into AND the few bins the top-p cut can fall into (the spec states the top-p test on the
+//        fixed-point numerators: E{x_w > x_v} >= Zi - floor(Zi * thr), no per-entry probability);
+//     3. the entries of those bins (~20-40 of the row) are the only ones looked at individually: all-pairs ranks and sums
+//        among them, 256 / P threads per candidate, settle both cuts exactly (tie groups whole) and yield Zi and the final
+//        sum Z2i without another pass;
+//     4. the race runs on the numerators, argmax e * R(noise), R the spec's division-free reciprocal (packed Newton steps).
+//     Every sum that decides something is an integer sum of fixed-point terms, so the atomics may run in any order and the
+//     kernel is bit-exact to oracle/spec_c.  9 barriers per row.  Rows the histograms cannot take (non-finite or zero value
+//     range, > 256 candidates, top_p == 0) go through k3_row_slow (bit-serial searches, any input).
+constexpr int kBins = 1024;
+constexpr int kCandMax = 256;
+constexpr int kRcpSteps = 4;                // SDVAR_RCP_STEPS of the spec
 constexpr float kFixE = 1099511627776.0f;   // 2^40
 constexpr float kFixM = 1073741824.0f;      // 2^30
+constexpr float kMagic = 12582912.0f;       // 1.5 * 2^23: x + kMagic rounds x to an integer that sits in the low mantissa bits
+constexpr uint32_t kMagicBits = 0x4B400000u;
+constexpr float kMagic4 = 3145728.0f;        // 1.5 * 2^21: one ulp is 1/4 there
+constexpr uint32_t kMagic4Bits = 0x4A400000u;
 
 template <int NV>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -302,46 +332,26 @@ k3_plain_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int i
   }
 }
 
+// ---- K3 filtered, v3: the row stays in registers; ONE pass builds three shared-memory histograms ----
 struct K3Smem {
-  uint32_t hist[kBins];
-  float cand[256];
-  uint32_t candm[256];
-  uint32_t wtot[kWarps];
-  __align__(16) unsigned long long zpart[2][kWarps];   // per-warp fixed-point partial sums (two buffers: consecutive sums may have no barrier in between)
-  int bstar;
-  uint32_t above;
-  int ncand, n_list;
-  float xK;
+  __align__(16) uint32_t hcnt[kBins];          // entries per value bin
+  __align__(16) uint32_t hhi[kBins];           // sum of the raw high limbs (each carries the magic exponent bits, removed in the scan)
+  __align__(16) uint32_t hlo[kBins];           // sum of the raw low limbs
+  unsigned long long pdex[kBins + 1];          // pdex[b + 1] = E of all bins above b; pdex[0] = E of the whole row
+  uint32_t pcab[kBins];                        // entries in the bins above b
+  unsigned long long cE[kCandMax];             // candidates: fixed-point exponential,
+  float cx[kCandMax];                          //   logit,
+  unsigned char cg[kCandMax];                  //   group (0: the top-k crossing bin on its own, 1: the top-p bin range)
+  unsigned long long wE[kWarps];
+  uint32_t wc[kWarps];
+  __align__(16) unsigned long long zpart[2][kWarps];
+  unsigned long long Zi, Z2i;
   uint32_t tkey, minkey;
+  int bK, bPlo, bPhi, nc, slow;
+  float xK;
   RedSmem red;
 };
 
-// inclusive warp scan of a u32
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const uint32_t o = __shfl_up_sync(0xffffffffu, v, off);
-    if (lane >= off) v += o;
-  }
-  return v;
-}
-// block-wide inclusive scan over the 256 threads (thread order); `tot` receives the grand total.  One barrier.
-__device__ __forceinline__ uint32_t block_incl_scan(uint32_t v, K3Smem& s, uint32_t& tot) {
-  const int w = threadIdx.x >> 5;
-  uint32_t inc = warp_incl_scan(v);
-  if ((threadIdx.x & 31) == 31) s.wtot[w] = inc;
-  __syncthreads();
-  uint32_t base = 0, t = 0;
-#pragma unroll
-  for (int k = 0; k < kWarps; ++k) {
-    const uint32_t x = s.wtot[k];
-    base += (k < w) ? x : 0u;
-    t += x;
-  }
-  tot = t;
-  return inc + base;
-}
 // fixed-point exponential E = rint(e * 2^40) as two 20-bit limbs (hi * 2^20 + lo); e in [0, 1]
 __device__ __forceinline__ void fix_e(float e, uint32_t& hi, uint32_t& lo) {
   const float a = __fmul_rn(e, 1048576.0f);                 // e * 2^20, exact
@@ -350,7 +360,7 @@ __device__ __forceinline__ void fix_e(float e, uint32_t& hi, uint32_t& lo) {
   lo = __float2uint_rn(__fmul_rn(__fsub_rn(a, fh), 1048576.0f));   // both operations exact; one rounding in the conversion
 }
 // block sum of per-thread limb sums -> u64 total: two warp reductions, one 64-bit partial per warp, one barrier, then every
-// thread adds the 8 partials (4 LDS.128).  Integer sums: any order gives the same total.  (per-thread sums < 2^25, warp < 2^30)
+// thread adds the 8 partials (4 LDS.128).  Integer sums: any order gives the same total.  (per-thread sums < 2^26, warp < 2^31)
 __device__ __forceinline__ unsigned long long block_sum_fix(uint32_t hi, uint32_t lo, K3Smem& s, int buf) {
   hi = __reduce_add_sync(0xffffffffu, hi);
   lo = __reduce_add_sync(0xffffffffu, lo);
@@ -362,241 +372,138 @@ __device__ __forceinline__ unsigned long long block_sum_fix(uint32_t hi, uint32_
   for (int k = 0; k < kWarps / 2; ++k) { const ulonglong2 v = z2[k]; t += v.x + v.y; }
   return t;
 }
-
-// value-space bin of x: floor(x * scale + off) with off = 0.5 - lo * scale; for lo <= x <= hi the fused multiply-add stays
-// inside (0, 512) as long as |lo| * scale < 2^18 (checked by the caller), so no clamp is needed.  Monotone in x.
-__device__ __forceinline__ int vbin(float x, float scale, float off) { return __float2int_rd(__fmaf_rn(x, scale, off)); }
-
-// ---- the part of the filtered path that works on the compacted list; QR = list entries per thread (n <= 256 * QR).
-// The list holds every entry whose top-k bin is >= the crossing bin: all survivors plus the few candidates below the exact
-// cut, which are dropped here (they contribute nothing once xK is known).
-struct K3Tail {      // returned BY VALUE: reference parameters of the out-of-line instance would pin these in local memory
-  float xlow;
-  int incl, slot;
-};
-template <int QR>
-__device__ __forceinline__ K3Tail k3_tail(K3Smem& s, int slot, const float2* lxn, const uint16_t* li, int n, float m, float xmin,
-                                          bool use_k, int top_k, bool hist_k, float kscale, float koff, float thr, bool sample,
-                                          long long orow, long long* idx_out, float* prob_out) {
-  const int tid = threadIdx.x;
-  float xlow;
-  bool incl;
-  float xv[QR], nzv[QR];
+// the three histogram updates of one entry (count, high limb, low limb; the arrays are 4 * kBins bytes apart), PREDICATED on
+// x >= t0: written in PTX because the compiler turns the C++ `if` into a branch per entry (BSSY / BRA / BSYNC around three
+// atomics, +140 instructions per thread-row)
+__device__ __forceinline__ void hist3(uint32_t addr, float x, float t0, uint32_t hi, uint32_t lo) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ge.f32 q, %1, %2;\n"
+      "@q red.shared.add.u32 [%0], 1;\n"
+      "@q red.shared.add.u32 [%0+4096], %3;\n"
+      "@q red.shared.add.u32 [%0+8192], %4;\n"
+      "}\n" ::"r"(addr),
+      "f"(x), "f"(t0), "r"(hi), "r"(lo)
+      : "memory");
+}
+// removable mass of the top-p cut: floor(Zi * thr_fix / 2^30), Zi < 2^53, thr_fix <= 2^30
+__device__ __forceinline__ unsigned long long thr_mass(unsigned long long Zi, uint32_t thr_fix) {
+  const unsigned long long lo = Zi * (unsigned long long)thr_fix, hi = __umul64hi(Zi, (unsigned long long)thr_fix);
+  return (hi << 34) | (lo >> 30);
+}
+// (R(n0), R(n1)): the spec's division-free reciprocal (sdvar_spec_rcp), two at a time on the packed pipe
+__device__ __forceinline__ f32x2 spec_rcp2(float n0, float n1) {
+  f32x2 y = pk2(u2f(0x7EF311C7u - f2u(n0)), u2f(0x7EF311C7u - f2u(n1)));
+  const f32x2 nn = pk2(u2f(f2u(n0) ^ 0x80000000u), u2f(f2u(n1) ^ 0x80000000u)), one = splat2(1.0f);
 #pragma unroll
-  for (int q = 0; q < QR; ++q) {
-    const int i = q * kThreads + tid;
-    const float2 t = i < n ? lxn[i] : make_float2(-INFINITY, 1.0f);
-    xv[q] = t.x; nzv[q] = t.y;
+  for (int i = 0; i < kRcpSteps; ++i) {
+    const f32x2 t = fma2(nn, y, one);
+    y = fma2(y, t, y);
   }
-  // ---- exact k-th largest value among the candidates of the crossing bin ----
-  float xK = xmin;
-  if (use_k && hist_k) {
-    const int bst = s.bstar;
-    const uint32_t above = s.above;
-#pragma unroll
-    for (int q = 0; q < QR; ++q)
-      if (q * kThreads + tid < n && vbin(xv[q], kscale, koff) == bst) {
-        const int p = atomicAdd(&s.ncand, 1);
-        if (p < 256) s.cand[p] = xv[q];
-      }
-    __syncthreads();
-    const int nc = s.ncand;
-    if (nc <= 256) {
-      if (tid < nc) {
-        const float xi = s.cand[tid];
-        uint32_t g = 0, ge = 0;
-        for (int jj = 0; jj < nc; ++jj) { const float xj = s.cand[jj]; g += xj > xi; ge += xj >= xi; }
-        const uint32_t kk = (uint32_t)top_k - above;
-        if (g < kk && kk <= ge) s.xK = xi;
-      }
-      __syncthreads();
-      xK = s.xK;
-    } else {
-      // fall-back: bisection over the candidates' keys (all other list entries are above the bin and count as `above`)
-      uint32_t lo = 0u, hi = 0xFFFFFFFFu;      // invariant: #{cand key >= lo} >= kk, #{cand key >= hi} < kk  (hi exclusive top)
-      const int kk = top_k - (int)above;
-      uint32_t key[QR];
-#pragma unroll
-      for (int q = 0; q < QR; ++q)
-        key[q] = (q * kThreads + tid < n && vbin(xv[q], kscale, koff) == bst) ? fkey(__fadd_rn(xv[q], 0.0f)) : 0u;   // 0: below every real key
-#pragma unroll 1
-      for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t tr = lo | (1u << bit);
-        int c = 0;
-#pragma unroll
-        for (int q = 0; q < QR; ++q) c += (key[q] >= tr) ? 1 : 0;
-        c = block_sum_int(c, s.red, slot);
-        if (c >= kk) lo = tr;
-      }
-      (void)hi;
-      xK = fkey_inv(lo);
-    }
-    if (tid == 0) s.ncand = 0;      // next use is behind at least one barrier
-  } else if (use_k) {
-    xK = s.xK;                        // found by the caller's fall-back
-  }
-  // ---- exponentials of the survivors; dropped candidates get exp(-inf) = 0 and vanish from every sum ----
-  float ev[QR];
-  uint32_t hi = 0, lo = 0;
-#pragma unroll
-  for (int q = 0; q < QR; q += 2) {
-    const float x0 = (xv[q] >= xK) ? __fsub_rn(xv[q], m) : -INFINITY;
-    const float x1 = (q + 1 < QR && xv[q + 1] >= xK) ? __fsub_rn(xv[q + 1], m) : -INFINITY;
-    float e0, e1;
-    unpk2(spec_expf2(x0, x1), e0, e1);
-    ev[q] = e0;
-    if (q + 1 < QR) ev[q + 1] = e1;
-    uint32_t h, l;
-    fix_e(e0, h, l); hi += h; lo += l;
-    fix_e(e1, h, l); hi += h; lo += l;
-  }
-  const unsigned long long Zi = block_sum_fix(hi, lo, s, 0);
-  unsigned long long Z2i = Zi;
-  xlow = xK; incl = true;            // keep <=> x >= xK
-  if (thr >= 0.0f) {
-    const float Z = __fmul_rn(__ull2float_rn(Zi), 1.0f / kFixE);
-    const uint32_t thr_i = (uint32_t)__fmul_rn(thr, kFixM);
-    const float range = __fsub_rn(m, xK);
-    uint32_t mass[QR];
-#pragma unroll
-    for (int q = 0; q < QR; ++q) mass[q] = ev[q] > 0.0f ? __float2uint_rn(__fmul_rn(__fdiv_rn(ev[q], Z), kFixM)) : 0u;
-    bool all_but_max = false, have = false;
-    float xB = -INFINITY;
-    bool strictB = true;
-    if (range > 0.0f && range < INFINITY && __fmul_rn(fabsf(xK), __fdiv_rn(511.0f, range)) < 262144.0f) {
-      const float scale = __fdiv_rn(511.0f, range), off = __fmaf_rn(-xK, scale, 0.5f);
-#pragma unroll
-      for (int q = 0; q < QR; ++q)
-        if (xv[q] >= xK) atomicAdd(&s.hist[vbin(xv[q], scale, off)], mass[q]);
-      __syncthreads();
-      // ascending scan of the bin masses: the crossing bin is the first whose inclusive cumulation exceeds thr_i
-      const uint32_t m0 = s.hist[2 * tid], m1 = s.hist[2 * tid + 1];
-      uint32_t tot;
-      const uint32_t inc = block_incl_scan(m0 + m1, s, tot);
-      const uint32_t before = inc - (m0 + m1);
-      s.hist[2 * tid] = 0; s.hist[2 * tid + 1] = 0;
-      if (before <= thr_i && thr_i < before + m0) { s.bstar = 2 * tid; s.above = before; }
-      else if (before + m0 <= thr_i && thr_i < inc) { s.bstar = 2 * tid + 1; s.above = before + m0; }
-      __syncthreads();
-      if (tot <= thr_i) {
-        all_but_max = true;                  // the whole row is removable: only the maximum survives
-      } else {
-        const int bst = s.bstar;
-        const uint32_t below = s.above;
-#pragma unroll
-        for (int q = 0; q < QR; ++q)
-          if (xv[q] >= xK && vbin(xv[q], scale, off) == bst) {
-            const int p = atomicAdd(&s.ncand, 1);
-            if (p < 256) { s.cand[p] = xv[q]; s.candm[p] = mass[q]; }
-          }
-        __syncthreads();
-        const int nc = s.ncand;
-        if (nc <= 256) {
-          if (tid < nc) {
-            const float xi = s.cand[tid];
-            uint32_t le = below;
-            for (int jj = 0; jj < nc; ++jj) le += (s.cand[jj] <= xi) ? s.candm[jj] : 0u;
-            const uint32_t k = fkey(__fadd_rn(xi, 0.0f));
-            if (le <= thr_i) atomicMax(&s.tkey, k);
-            atomicMin(&s.minkey, k);
-          }
-          __syncthreads();
-          const uint32_t tk = s.tkey;
-          strictB = tk == 0u;
-          xB = fkey_inv(strictB ? s.minkey : tk);
-          have = true;
-        }
-      }
-    } else if (range > 0.0f || !(range == 0.0f)) {
-      have = false;                            // degenerate value range: bit-serial search below
-    } else {
-      have = true;                             // every survivor equals the maximum: one tie group holding the max, nothing removed
-    }
-    if (!all_but_max && !have) {
-      // fall-back (crossing bin with > 256 entries, or a value range the histogram cannot bin): bit-serial search of the
-      // largest key T with mass{key <= T} <= thr_i over the survivors
-      uint32_t T = 0;
-#pragma unroll 1
-      for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t tr = T | (1u << bit);
-        int a = 0;
-#pragma unroll
-        for (int q = 0; q < QR; ++q)
-          if (xv[q] >= xK && fkey(__fadd_rn(xv[q], 0.0f)) <= tr) a += (int)mass[q];
-        a = block_sum_int(a, s.red, slot);      // masses sum to ~2^30: fits an int
-        if ((uint32_t)a <= thr_i) T = tr;
-      }
-      strictB = T == 0u;
-      xB = T ? fkey_inv(T) : -INFINITY;
-    }
-    // one threshold for everything below: keep <=> incl ? x >= xlow : x > xlow  (the row maximum always satisfies it)
-    if (all_but_max) { xlow = m; incl = true; }
-    else if (strictB) { if (xB > xK) { xlow = xB; incl = true; } }        // removed <=> x < xB
-    else if (xB >= xK) { xlow = xB; incl = false; }                         // removed <=> x <= xB
-    hi = 0; lo = 0;
-#pragma unroll
-    for (int q = 0; q < QR; ++q) {
-      const bool keep = incl ? (xv[q] >= xlow) : (xv[q] > xlow);
-      if (!keep) ev[q] = 0.0f;
-      uint32_t h, l;
-      fix_e(ev[q], h, l); hi += h; lo += l;
-    }
-    if (sample) Z2i = block_sum_fix(hi, lo, s, 1);
-  }
-  if (!sample) return K3Tail{xlow, incl ? 1 : 0, slot};
-  const float Z2 = __fmul_rn(__ull2float_rn(Z2i), 1.0f / kFixE);
-  float best = -1.0f, bestp = 0.0f;
-  int bi = 0x7FFFFFFF;
-#pragma unroll
-  for (int q = 0; q < QR; ++q) {
-    if (ev[q] > 0.0f) {
-      const float pv = __fdiv_rn(ev[q], Z2);
-      const float r = __fdiv_rn(pv, nzv[q]);
-      const int v = (int)li[q * kThreads + tid];
-      if (r > best || (r == best && v < bi)) { best = r; bi = v; bestp = pv; }
-    }
-  }
-  const unsigned long long w = block_max_u64(pack_best(best, bi), s.red, slot);
-  int win = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
-  if (win == 0x7FFFFFFF) win = 0;
-  if (bi == win || (tid == 0 && (uint32_t)(w >> 32) == fkey(-1.0f))) {
-    if (idx_out) idx_out[orow] = win;
-    if (prob_out) prob_out[orow] = (bi == win) ? bestp : 0.0f;
-  }
-  return K3Tail{xlow, incl ? 1 : 0, slot};
+  return y;
 }
 
-// long lists (top-p without top-k, huge tie groups): kept out of line so that its 4*E-register working set does not
-// inflate the register allocation of the common path
-template <int E>
-__device__ __noinline__ K3Tail k3_tail_long(K3Smem& s, int slot, const float2* lxn, const uint16_t* li, int n, float m, float xmin,
-                                            bool use_k, int top_k, bool hist_k, float kscale, float koff, float thr, bool sample,
-                                            long long orow, long long* idx_out, float* prob_out) {
-  return k3_tail<E>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, orow, idx_out, prob_out);
+// ---- generic path of one row (block-wide, any input): bit-serial searches on the order-preserving keys with one block
+// reduction per bit.  ~70 barriers: only for rows the histograms cannot take (non-finite or zero value range, more than
+// kCandMax candidates around a cut, a bin with more than 4095 entries, top_p == 0).  Re-reads the row so that the caller's
+// registers stay out of local memory.  Returns the cut as a key (keep <=> key(x) >= klow) and the final fixed-point sum.
+struct K3Cut {
+  uint32_t klow;
+  unsigned long long Z2i;
+  int slot;
+};
+template <int NV>
+__device__ __noinline__ K3Cut k3_row_slow(K3Smem& s, int slot, const float4* __restrict__ pc, const float4* __restrict__ pu, float t1,
+                                          float t2, bool use_k, int top_k, bool use_p, uint32_t thr_fix, uint32_t kmx) {
+  constexpr int E = NV * 4;
+  const int tid = threadIdx.x;
+  uint32_t key[E], hi[E], lo[E];
+  float x[E];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a = ldg_stream(pc + i * kThreads + tid), c = ldg_stream(pu + i * kThreads + tid);
+    x[4 * i + 0] = __fsub_rn(__fmul_rn(a.x, t1), __fmul_rn(c.x, t2));
+    x[4 * i + 1] = __fsub_rn(__fmul_rn(a.y, t1), __fmul_rn(c.y, t2));
+    x[4 * i + 2] = __fsub_rn(__fmul_rn(a.z, t1), __fmul_rn(c.z, t2));
+    x[4 * i + 3] = __fsub_rn(__fmul_rn(a.w, t1), __fmul_rn(c.w, t2));
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) key[e] = fkey(__fadd_rn(x[e], 0.0f));
+  uint32_t K = 0;
+  if (use_k) {
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t tr = K | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) c += (key[e] >= tr) ? 1 : 0;
+      c = block_sum_int(c, s.red, slot);
+      if (c >= top_k) K = tr;
+    }
+  }
+  const float m = fkey_inv(kmx);
+  uint32_t sh = 0, sl = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const float ee = (key[e] >= K) ? spec_expf(__fsub_rn(x[e], m)) : 0.0f;
+    fix_e(ee, hi[e], lo[e]);
+    sh += hi[e];
+    sl += lo[e];
+  }
+  int buf = 0;
+  const unsigned long long Zi = block_sum_fix(sh, sl, s, buf);
+  buf ^= 1;
+  uint32_t klow = K;
+  unsigned long long Z2i = Zi;
+  if (use_p) {
+    const unsigned long long thrE = thr_mass(Zi, thr_fix);
+    uint32_t T = 0;      // largest key value with E{alive, key <= T} <= thrE
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t tr = T | (1u << bit);
+      sh = 0; sl = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (key[e] <= tr) { sh += hi[e]; sl += lo[e]; }      // entries below the top-k cut carry zero limbs
+      const unsigned long long a = block_sum_fix(sh, sl, s, buf);
+      buf ^= 1;
+      if (a <= thrE) T = tr;
+    }
+    const uint32_t cut = T >= kmx ? kmx : T + 1u;            // removed <=> key <= T and key != key(max)
+    klow = max(K, cut);
+    sh = 0; sl = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (key[e] >= klow) { sh += hi[e]; sl += lo[e]; }
+    Z2i = block_sum_fix(sh, sl, s, buf);
+  }
+  return K3Cut{klow, Z2i, slot};
 }
 
 template <int NV, int OCC>
 __global__ void __launch_bounds__(kThreads, OCC)
 k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int in_off, int out_ld, int out_off, SegTable seg,
-                   int top_k, float thr, const float* __restrict__ noise, long long* __restrict__ idx_out,
+                   int top_k, float thr, float zprune, const float* __restrict__ noise, long long* __restrict__ idx_out,
                    float* __restrict__ mixed_out, float* __restrict__ prob_out) {
   constexpr int V = NV * 1024;
   constexpr int E = NV * 4;
-  constexpr int QF = E < 6 ? E : 6;     // fast tail: lists of up to 1536 entries
-  extern __shared__ __align__(16) unsigned char k3_dyn[];
-  float2* lxn = reinterpret_cast<float2*>(k3_dyn);           // [V + 2] (logit, noise) of the listed entries (+ the dummy slot)
-  uint16_t* li = reinterpret_cast<uint16_t*>(lxn + V + 2);   // [V + 2] their vocabulary index
   __shared__ K3Smem s;
+  extern __shared__ __align__(16) unsigned char k3_noise[];      // [V] floats: the row's noise, fetched by cp.async at row start
   int slot = 0;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const long long rows = (long long)B * L;
-  for (int i = tid; i < kBins; i += kThreads) s.hist[i] = 0;
-  if (tid == 0) { s.ncand = 0; s.n_list = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; }
+  for (int i = tid; i < kBins; i += kThreads) { s.hcnt[i] = 0; s.hhi[i] = 0; s.hlo[i] = 0; }
+  if (tid == 0) { s.nc = 0; s.slow = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; s.bPlo = 0x7FFFFFFF; s.bPhi = -1; }
   __syncthreads();
   const bool sample = noise != nullptr;
   const bool use_k = top_k > 0 && top_k < V;
+  const bool use_p = thr >= 0.0f;
+  const uint32_t thr_fix = use_p ? (uint32_t)__fmul_rn(thr, kFixM) : 0u;      // floor
   const bool small = rows < 0x7FFFFFFFLL;
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+  const int q0 = kBins - 4 - 4 * tid;       // this thread scans bins q0+3, q0+2, q0+1, q0 (descending)
+  bool prune = zprune < 1e30f;
+  for (long long row = blockIdx.x; row < rows;) {
     int b, pos;
     if (small) { b = (int)((uint32_t)row / (uint32_t)L); pos = (int)((uint32_t)row - (uint32_t)b * (uint32_t)L); }
     else { b = (int)(row / L); pos = (int)(row - (long long)b * L); }
@@ -618,133 +525,355 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
         x[4 * i + 3] = __fsub_rn(__fmul_rn(a[i].w, t1), __fmul_rn(c[i].w, t2));
       }
     }
-    // ---- row max / min ----
-    float mx = -INFINITY, mn = INFINITY;
-#pragma unroll
-    for (int e = 0; e < E; ++e) { mx = fmaxf(mx, x[e]); mn = fminf(mn, x[e]); }
-    uint32_t kmx = fkey(__fadd_rn(mx, 0.0f)), kmnc = ~fkey(__fadd_rn(mn, 0.0f));
-    block_max_u32x2(kmx, kmnc, s.red, slot);
-    const float m = fkey_inv(kmx), xmin = fkey_inv(~kmnc);
-
-    // ---- top-k, coarse: histogram of the value-space bins, suffix scan -> crossing bin b* (exact cut: in the tail) ----
-    bool hist_k = false;
-    float kscale = 0.0f, koff = 0.0f, xcut = xmin;      // list <=> vbin(x) >= b*  (hist) or x >= xcut (fall-back / no top-k)
-    int bst = 0;
-    if (use_k) {
-      const float range = __fsub_rn(m, xmin);
-      if (range > 0.0f && range < INFINITY && __fmul_rn(fabsf(xmin), __fdiv_rn(511.0f, range)) < 262144.0f) {
-        hist_k = true;
-        kscale = __fdiv_rn(511.0f, range);
-        koff = __fmaf_rn(-xmin, kscale, 0.5f);
-#pragma unroll
-        for (int e = 0; e < E; ++e) atomicAdd(&s.hist[vbin(x[e], kscale, koff)], 1u);
-      }
-    }
-    float4 nz[NV];
-    if (sample) {      // issued here so that the latency overlaps the scan
+    if (sample) {      // every thread fetches (and later reads) its own chunks: no barrier needed, only the wait
       const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) nz[i] = ldg_stream(pn + i * kThreads + tid);
+      for (int i = 0; i < NV; ++i)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(k3_noise) + (uint32_t)(i * kThreads + tid) * 16u),
+                     "l"(pn + i * kThreads + tid)
+                     : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    if (use_k) {
-      if (hist_k) {
-        __syncthreads();
-        // suffix scan: thread t owns bins 511-2t (first) and 510-2t
-        const uint32_t c0 = s.hist[kBins - 1 - 2 * tid], c1 = s.hist[kBins - 2 - 2 * tid];
-        uint32_t tot;
-        const uint32_t inc = block_incl_scan(c0 + c1, s, tot);
-        const uint32_t before = inc - (c0 + c1);
-        s.hist[kBins - 1 - 2 * tid] = 0; s.hist[kBins - 2 - 2 * tid] = 0;
-        const uint32_t k = (uint32_t)top_k;
-        if (before < k && k <= before + c0) { s.bstar = kBins - 1 - 2 * tid; s.above = before; }
-        else if (before + c0 < k && k <= inc) { s.bstar = kBins - 2 - 2 * tid; s.above = before + c0; }
-        __syncthreads();
-        bst = s.bstar;
+    // ---- row max / min, and (heuristic only) mean / variance ----
+    float mx = -INFINITY, mn = INFINITY, s1 = 0.0f, s2 = 0.0f;      // s1, s2: over a quarter of the row (every fourth entry)
+#pragma unroll
+    for (int e = 0; e < E; ++e) { mx = fmaxf(mx, x[e]); mn = fminf(mn, x[e]); }
+#pragma unroll
+    for (int e = 0; e < E; e += 4) { s1 += x[e]; s2 = fmaf(x[e], x[e], s2); }
+    uint32_t kmx = fkey(__fadd_rn(mx, 0.0f)), kmnc = ~fkey(__fadd_rn(mn, 0.0f));
+    block_stats(kmx, kmnc, s1, s2, s.red, slot);
+    const float m = fkey_inv(kmx), xmin = fkey_inv(~kmnc);
+
+    // ---- value bins.  tb(x) = fma(x, scale, offm) lands in [2^21, 2^22), where one ulp is 1/4: bits(tb) - bits(kMagic4) counts
+    // quarter bins, so (bits(tb) & 0xffc) IS the byte offset of bin(x) in a histogram -- one LOP per entry, no float->int
+    // conversion, monotone in x.  Bins only LOCATE the cuts; every sum that decides something is an exact integer, so neither
+    // the binning nor the pruning below is part of the spec.
+    // Pruning (top-k only): entries below t0 = mean + zprune * sigma cannot survive the top-k cut IF at least top_k entries lie
+    // at or above t0 -- which the scan's total verifies; such entries are left out of the histograms (shared-memory atomics
+    // run at ~2 lanes per clock and bound this kernel).  When the check fails the row is redone with t0 = min. ----
+    bool fast = false;
+    float scale = 0.0f, offm = 0.0f, t0 = xmin;
+    if (__fsub_rn(m, xmin) > 0.0f && __fsub_rn(m, xmin) < INFINITY && thr_fix < (1u << 30)) {
+      if (use_k && prune) {
+        const float mean = s1 * (4.0f / (float)V);
+        const float var = fmaxf(fmaf(-mean, mean, s2 * (4.0f / (float)V)), 0.0f);
+        float sd;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(var));      // a guess, identical in every thread
+        const float tt = fmaf(zprune, sd, mean);
+        if (tt > xmin && tt < m) t0 = tt;
+      }
+      scale = __fdividef((float)(kBins - 3), __fsub_rn(m, t0));          // any value will do as long as the checks below hold
+      offm = __fmaf_rn(-t0, scale, kMagic4 + 1.0f);
+      const uint32_t blo = f2u(__fmaf_rn(t0, scale, offm)) - kMagic4Bits, bhi = f2u(__fmaf_rn(m, scale, offm)) - kMagic4Bits;
+      fast = __fmul_rn(fmaxf(fabsf(xmin), fabsf(m)), scale) < 262144.0f && blo < 4u * kBins && bhi < 4u * kBins;
+    }
+    prune = zprune < 1e30f;      // (a redone row ran without; the next row prunes again)
+
+    // ---- pass 1: exponentials (kept in registers), fixed-point limbs, three histogram atomics per entry ----
+    float ev[E];
+    {
+      const f32x2 nm2 = splat2(-m);
+      if (fast) {
+        const f32x2 sc2 = splat2(scale), of2 = splat2(offm), p20 = splat2(1048576.0f), mg = splat2(kMagic), nmg = splat2(-kMagic);
+        const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(&s.hcnt[0]);
+        static_assert(offsetof(K3Smem, hhi) - offsetof(K3Smem, hcnt) == 4096 && offsetof(K3Smem, hlo) - offsetof(K3Smem, hcnt) == 8192, "hist3 layout");
+#pragma unroll
+        for (int q = 0; q < E; q += 2) {
+          const f32x2 xp = pk2(x[q], x[q + 1]);
+          float d0, d1;
+          unpk2(add2(xp, nm2), d0, d1);                       // x + (-m) == x - m exactly
+          const f32x2 e2 = spec_expf2(d0, d1);
+          unpk2(e2, ev[q], ev[q + 1]);
+          // E = rint(e * 2^40) = hi * 2^20 + lo with hi = rint(e * 2^20), lo = rint((e * 2^20 - hi) * 2^20) in [-2^19, 2^19]:
+          // both roundings by the magic addend; bits(th) = kMagicBits + hi, bits(tl) = kMagicBits + lo
+          const f32x2 a2 = mul2(e2, p20);
+          const f32x2 th = add2(a2, mg);
+          const f32x2 hf = add2(th, nmg);
+          const f32x2 dd = fma2(hf, splat2(-1.0f), a2);
+          const f32x2 tl = fma2(dd, p20, mg);
+          const f32x2 tb = fma2(xp, sc2, of2);
+          float tb0, tb1, th0, th1, tl0, tl1;
+          unpk2(tb, tb0, tb1);
+          unpk2(th, th0, th1);
+          unpk2(tl, tl0, tl1);
+          // (for an entry at or above t0 the mask only drops the quarter-bin bits; it also keeps a NaN from addressing outside)
+          hist3(hbase + (f2u(tb0) & (4u * kBins - 4u)), x[q], t0, f2u(th0), f2u(tl0));
+          hist3(hbase + (f2u(tb1) & (4u * kBins - 4u)), x[q + 1], t0, f2u(th1), f2u(tl1));
+        }
       } else {
-        // fall-back: bisection on the order-preserving keys (round-1 algorithm), any input
-        uint32_t key[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) key[e] = fkey(__fadd_rn(x[e], 0.0f));
-        uint32_t lo = ~kmnc, hi = kmx + 1u;
-        int cL = V, cH = 0;
-#pragma unroll 1
-        while (cL - cH > 1 && hi - lo > 1u) {
-          const uint32_t mid = lo + ((hi - lo) >> 1);
-          int c = 0;
-#pragma unroll
-          for (int e = 0; e < E; ++e) c += (key[e] >= mid) ? 1 : 0;
-          c = block_sum_int(c, s.red, slot);
-          if (c >= top_k) { lo = mid; cL = c; } else { hi = mid; cH = c; }
+        for (int q = 0; q < E; q += 2) {
+          float d0, d1;
+          unpk2(add2(pk2(x[q], x[q + 1]), nm2), d0, d1);
+          unpk2(spec_expf2(d0, d1), ev[q], ev[q + 1]);
         }
-        uint32_t K = lo;
-        if (cL - cH == 1 && hi - lo > 1u) {
-          uint32_t mnk = 0, z = 0;
-#pragma unroll
-          for (int e = 0; e < E; ++e) mnk = max(mnk, (key[e] >= lo) ? ~key[e] : 0u);
-          block_max_u32x2(mnk, z, s.red, slot);
-          K = ~mnk;
-        }
-        xcut = fkey_inv(K);
-        if (tid == 0) s.xK = xcut;
       }
     }
 
-    // ---- compact the listed entries (any order: every later sum is an integer sum).  Branch-free: entries that are not
-    // listed are stored to a dummy slot (index V) instead of being jumped over -- a profile of the branchy version showed
-    // ~290 of ~2060 instructions per thread-row in BRA / BSSY / BSYNC and ~120 in spill traffic of the per-element flags.
-    {
-      uint32_t cnt = 0;
-      if (hist_k) {
+    // ---- scan of the bins from the top: entries / E above every bin; the top-k crossing bin ----
+    unsigned long long Etot = 0;
+    uint32_t ntot = 0;
+    if (fast) {
+      __syncthreads();
+      const uint4 c4 = *reinterpret_cast<const uint4*>(&s.hcnt[q0]);
+      const uint4 h4 = *reinterpret_cast<const uint4*>(&s.hhi[q0]);
+      const uint4 l4 = *reinterpret_cast<const uint4*>(&s.hlo[q0]);
+      *reinterpret_cast<uint4*>(&s.hcnt[q0]) = make_uint4(0u, 0u, 0u, 0u);      // ready for the next row
+      *reinterpret_cast<uint4*>(&s.hhi[q0]) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(&s.hlo[q0]) = make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t cc[4] = {c4.w, c4.z, c4.y, c4.x}, hh[4] = {h4.w, h4.z, h4.y, h4.x}, ll[4] = {l4.w, l4.z, l4.y, l4.x};
+      unsigned long long Eb[4];
+      uint32_t ct = 0;
+      unsigned long long Et = 0;
 #pragma unroll
-        for (int e = 0; e < E; ++e) cnt += (vbin(x[e], kscale, koff) >= bst) ? 1u : 0u;
-      } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) cnt += (x[e] >= xcut) ? 1u : 0u;
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t H = hh[k] - cc[k] * kMagicBits;                          // exact mod 2^32: the true sums fit (cc <= 4095)
+        const int Lo = (int)(ll[k] - cc[k] * kMagicBits);
+        Eb[k] = ((unsigned long long)H << 20) + (unsigned long long)(long long)Lo;
+        ct += cc[k];
+        Et += Eb[k];
       }
-      const uint32_t inc = warp_incl_scan(cnt);
-      int base = 0;
-      if (lane == 31) base = atomicAdd(&s.n_list, (int)inc);
-      base = __shfl_sync(0xffffffffu, base, 31);
-      int p = base + (int)(inc - cnt);
+      uint32_t ci = ct;
+      unsigned long long Ei = Et;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t oc = __shfl_up_sync(0xffffffffu, ci, off);
+        const unsigned long long oE = __shfl_up_sync(0xffffffffu, Ei, off);
+        if (lane >= off) { ci += oc; Ei += oE; }
+      }
+      if (lane == 31) { s.wc[wid] = ci; s.wE[wid] = Ei; }
+      __syncthreads();
+      uint32_t cb = ci - ct;
+      unsigned long long eb = Ei - Et;
+#pragma unroll
+      for (int k = 0; k < kWarps; ++k) {
+        const uint32_t wc = s.wc[k];
+        const unsigned long long wE = s.wE[k];
+        if (k < wid) { cb += wc; eb += wE; }
+        Etot += wE;
+        ntot += wc;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int bin = q0 + 3 - k;
+        s.pcab[bin] = cb;
+        s.pdex[bin + 1] = eb;
+        if (cc[k] > 4095u) s.slow = 1;
+        if (use_k && cb < (uint32_t)top_k && (uint32_t)top_k <= cb + cc[k]) s.bK = bin;
+        cb += cc[k];
+        eb += Eb[k];
+      }
+      if (tid == kThreads - 1) s.pdex[0] = eb;      // == Etot
+      __syncthreads();
+      if (use_k && ntot < (uint32_t)top_k) {      // fewer than top_k entries at or above t0: the pruning guess was too high.
+        prune = false;                            // Redo the row without (the histograms are zero again, nothing else was touched)
+        continue;
+      }
+      fast = s.slow == 0;
+    }
+
+    // ---- the bins a top-p crossing can fall into, whatever the exact top-k cut inside bin bK turns out to be ----
+    int bK = -2, plo = kBins, phi = kBins;
+    if (fast) {
+      if (use_k) bK = s.bK;
+      if (use_p) {
+        const unsigned long long zmin = use_k ? s.pdex[bK + 1] : Etot, zmax = use_k ? s.pdex[bK] : Etot;
+        const unsigned long long tmin = zmin - thr_mass(zmin, thr_fix), tmax = zmax - thr_mass(zmax, thr_fix);
+        unsigned long long din = s.pdex[q0 + 4];      // E above bin q0+3
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int bin = q0 + 3 - k;
+          const unsigned long long dex = din;
+          din = s.pdex[bin];                          // E above, this bin included
+          if (din != dex && dex < tmax && din >= tmin) { atomicMin(&s.bPlo, bin); atomicMax(&s.bPhi, bin); }
+        }
+        __syncthreads();
+        plo = s.bPlo;
+        phi = s.bPhi;
+      }
+    }
+
+    // ---- candidates: the entries of bin bK (group 0, only when it lies below the top-p range) and of bins plo..phi (group 1) ----
+    int nc = 0;
+    bool kgroup = false;
+    if (fast) {
+      kgroup = use_k && bK < plo;
+      // in quarter-bin units relative to bits(tb): bin == bK <=> bits - cK < 4; plo <= bin <= phi <=> bits - cP < 4 * (phi - plo + 1);
+      // an entry below t0 (not in the histograms) has bits < kMagic4Bits, i.e. a huge unsigned difference: never a candidate
+      const uint32_t cK = kMagic4Bits + 4u * (uint32_t)bK, wK = kgroup ? 4u : 0u;
+      const uint32_t cP = kMagic4Bits + 4u * (uint32_t)plo, wP = 4u * (uint32_t)(phi - plo + 1), span = (uint32_t)(phi - plo);
+      uint32_t mask = 0;
+      {
+        const f32x2 sc2 = splat2(scale), of2 = splat2(offm);
+#pragma unroll
+        for (int q = 0; q < E; q += 2) {
+          float tb0, tb1;
+          unpk2(fma2(pk2(x[q], x[q + 1]), sc2, of2), tb0, tb1);
+          if (f2u(tb0) - cK < wK || f2u(tb0) - cP < wP) mask |= 1u << q;
+          if (f2u(tb1) - cK < wK || f2u(tb1) - cP < wP) mask |= 2u << q;
+        }
+      }
+      while (mask) {                        // rare: ~20-40 entries of the row; the entry is re-read to keep x[] / ev[] in registers
+        const int i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int f = (i >> 2) * kThreads + tid;
+        const float xc = __ldg(reinterpret_cast<const float*>(pc + f) + (i & 3)), xu = __ldg(reinterpret_cast<const float*>(pu + f) + (i & 3));
+        const float xe = __fsub_rn(__fmul_rn(xc, t1), __fmul_rn(xu, t2));
+        uint32_t h, l;
+        fix_e(spec_expf(__fsub_rn(xe, m)), h, l);
+        const uint32_t o = (f2u(__fmaf_rn(xe, scale, offm)) - kMagic4Bits) >> 2;
+        const int p = atomicAdd(&s.nc, 1);
+        if (p < kCandMax) {
+          s.cx[p] = xe;
+          s.cE[p] = ((unsigned long long)h << 20) + (unsigned long long)l;
+          s.cg[p] = (o - (uint32_t)plo <= span) ? 1 : 0;
+        }
+      }
+      __syncthreads();
+      nc = s.nc;
+      fast = nc <= kCandMax;
+    }
+
+    // ---- exact cuts among the candidates: all-pairs ranks / sums, 256 / P threads per candidate ----
+    uint32_t klow = 0;
+    unsigned long long Z2i = 0;
+    bool z2_shared = false;
+    if (fast) {
+      int P = 8, lg = 5;                     // lg = log2(threads per candidate)
+      while (P < nc) { P <<= 1; --lg; }
+      const int G = 1 << lg, i = tid >> lg, sub = tid & (G - 1);
+      float xi = 0.0f;
+      int gi = 0;
+      uint32_t cnt = 0;                      // (entries >= x_i) + 65536 * (entries > x_i), same group
+      unsigned long long Ege = 0;            // E of the entries >= x_i, same group
+      if (i < nc) {
+        xi = s.cx[i];
+        gi = s.cg[i];
+        for (int jj = sub; jj < nc; jj += G) {
+          const float xj = s.cx[jj];
+          const bool same = s.cg[jj] == gi;
+          const bool ge = same && xj >= xi, gt = same && xj > xi;
+          cnt += (ge ? 1u : 0u) + (gt ? 65536u : 0u);
+          Ege += ge ? s.cE[jj] : 0ull;
+        }
+      }
+      for (int off = G >> 1; off >= 1; off >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        Ege += __shfl_xor_sync(0xffffffffu, Ege, off);
+      }
+      const bool lead = i < nc && sub == 0;
+      const uint32_t cge = cnt & 0xFFFFu, cgt = cnt >> 16;
+      unsigned long long Egt = 0, baseE = 0;
+      if (lead) {
+        Egt = Ege - (unsigned long long)(cge - cgt) * s.cE[i];      // ties share x, hence e, hence E
+        baseE = gi ? s.pdex[phi + 1] : s.pdex[bK + 1];
+        if (use_k && (gi == 0 || !kgroup)) {
+          const uint32_t base = gi ? s.pcab[phi] : s.pcab[bK];
+          if (base + cgt < (uint32_t)top_k && (uint32_t)top_k <= base + cge) { s.xK = xi; s.Zi = baseE + Ege; }
+        }
+      }
+      float xK = xmin;
+      unsigned long long Zi = Etot;
+      if (use_k) {
+        __syncthreads();
+        xK = s.xK;
+        Zi = s.Zi;
+      }
+      klow = fkey(__fadd_rn(xK, 0.0f));
+      Z2i = Zi;
+      if (use_p) {
+        const unsigned long long target = Zi - thr_mass(Zi, thr_fix);      // removed <=> E{alive, x_w > x_v} >= target
+        const uint32_t ki = fkey(__fadd_rn(xi, 0.0f));
+        const bool removed = lead && gi == 1 && xi >= xK && xi < m && baseE + Egt >= target;
+        if (removed) atomicMax(&s.tkey, ki);
+        if (lead && gi == 1) atomicMin(&s.minkey, ki);
+        __syncthreads();
+        const uint32_t tk = s.tkey;
+        if (tk != 0u) {
+          klow = tk + 1u;                    // tk < key(max): no overflow; tk >= key(xK): removed entries are alive
+          if (removed && ki == tk) s.Z2i = baseE + Egt;      // read by the winner of the race, behind its barrier
+          z2_shared = true;
+        } else if (use_k ? kgroup : (plo > 0 && s.pcab[plo - 1] < (uint32_t)V)) {
+          // no candidate is removed, but alive entries lie below bin plo, and every one of those is (E above them >=
+          // E{bins >= plo} >= target): the cut sits right below the lowest entry of bin plo
+          klow = s.minkey;
+          Z2i = s.pdex[plo];
+        }
+      }
+    } else {
+      const K3Cut c = k3_row_slow<NV>(s, slot, pc, pu, t1, t2, use_k, top_k, use_p, thr_fix, kmx);
+      klow = c.klow;
+      Z2i = c.Z2i;
+      slot = c.slot;
+      // re-materialise the row behind the call instead of keeping 2 E registers alive across it (which would put spill
+      // stores on the fast path)
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        const float nn[4] = {nz[i].x, nz[i].y, nz[i].z, nz[i].w};
+        const float4 a = ldg_stream(pc + i * kThreads + tid), cu = ldg_stream(pu + i * kThreads + tid);
+        x[4 * i + 0] = __fsub_rn(__fmul_rn(a.x, t1), __fmul_rn(cu.x, t2));
+        x[4 * i + 1] = __fsub_rn(__fmul_rn(a.y, t1), __fmul_rn(cu.y, t2));
+        x[4 * i + 2] = __fsub_rn(__fmul_rn(a.z, t1), __fmul_rn(cu.z, t2));
+        x[4 * i + 3] = __fsub_rn(__fmul_rn(a.w, t1), __fmul_rn(cu.w, t2));
+      }
+      const f32x2 nm2 = splat2(-m);
+#pragma unroll
+      for (int q = 0; q < E; q += 2) {
+        float d0, d1;
+        unpk2(add2(pk2(x[q], x[q + 1]), nm2), d0, d1);
+        unpk2(spec_expf2(d0, d1), ev[q], ev[q + 1]);
+      }
+    }
+    // one threshold for everything below: keep <=> x >= xthr (finite: a -inf logit is never in the race)
+    const float xthr = fkey_inv(max(klow, 0x00800000u));
+
+    if (sample) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      float4 nz[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) nz[i] = reinterpret_cast<const float4*>(k3_noise)[i * kThreads + tid];
+      float best = -1.0f;
+      int bi = 0x7FFFFFFF;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float r0, r1, r2, r3;
+        unpk2(mul2(pk2(ev[4 * i], ev[4 * i + 1]), spec_rcp2(nz[i].x, nz[i].y)), r0, r1);
+        unpk2(mul2(pk2(ev[4 * i + 2], ev[4 * i + 3]), spec_rcp2(nz[i].z, nz[i].w)), r2, r3);
+        const float rr[4] = {r0, r1, r2, r3};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float xe = x[4 * i + c];
-          const bool a = hist_k ? (vbin(xe, kscale, koff) >= bst) : (xe >= xcut);
-          const int dst = a ? p : V;
-          lxn[dst] = make_float2(xe, sample ? nn[c] : 1.0f);
-          li[dst] = (uint16_t)(4 * (i * kThreads + tid) + c);
-          p += a ? 1 : 0;
+          const float r = (x[4 * i + c] >= xthr) ? rr[c] : -1.0f;
+          if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; }
+        }
+      }
+      const unsigned long long w = block_max_u64(pack_best(best, bi), s.red, slot);
+      int win = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
+      const bool none = (uint32_t)(w >> 32) == fkey(-1.0f);      // nothing alive (a row of -inf / NaN): index 0, probability 0
+      if (none) win = 0;
+      if (none ? tid == 0 : bi == win) {
+        if (idx_out) idx_out[orow] = win;
+        if (prob_out) {
+          float pw = 0.0f;
+          if (!none) {
+            const int f = win >> 2, c = win & 3;
+            const float xc = __ldg(reinterpret_cast<const float*>(pc + f) + c), xu = __ldg(reinterpret_cast<const float*>(pu + f) + c);
+            const float ew = spec_expf(__fsub_rn(__fsub_rn(__fmul_rn(xc, t1), __fmul_rn(xu, t2)), m));
+            const unsigned long long z = z2_shared ? s.Z2i : Z2i;
+            pw = __fdiv_rn(ew, __fmul_rn(__ull2float_rn(z), 1.0f / kFixE));
+          }
+          prob_out[orow] = pw;
         }
       }
     }
-    __syncthreads();
-    const int n = s.n_list;
-    const K3Tail tl = (n <= QF * kThreads)
-        ? k3_tail<QF>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, orow, idx_out, prob_out)
-        : k3_tail_long<E>(s, slot, lxn, li, n, m, xmin, use_k, top_k, hist_k, kscale, koff, thr, sample, orow, idx_out, prob_out);
-    slot = tl.slot;
-    const float xlow = tl.xlow;
-    const bool incl = tl.incl != 0;
-
     if (mixed_out != nullptr) {
       float4* po = reinterpret_cast<float4*>(mixed_out + orow * V);
-      if (incl) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
-          stg_stream(po + i * kThreads + tid, make_float4(x[4 * i] >= xlow ? x[4 * i] : -INFINITY, x[4 * i + 1] >= xlow ? x[4 * i + 1] : -INFINITY,
-                                                           x[4 * i + 2] >= xlow ? x[4 * i + 2] : -INFINITY, x[4 * i + 3] >= xlow ? x[4 * i + 3] : -INFINITY));
-      } else {
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-          stg_stream(po + i * kThreads + tid, make_float4(x[4 * i] > xlow ? x[4 * i] : -INFINITY, x[4 * i + 1] > xlow ? x[4 * i + 1] : -INFINITY,
-                                                           x[4 * i + 2] > xlow ? x[4 * i + 2] : -INFINITY, x[4 * i + 3] > xlow ? x[4 * i + 3] : -INFINITY));
-      }
+      for (int i = 0; i < NV; ++i)
+        stg_stream(po + i * kThreads + tid, make_float4(x[4 * i] >= xthr ? x[4 * i] : -INFINITY, x[4 * i + 1] >= xthr ? x[4 * i + 1] : -INFINITY,
+                                                         x[4 * i + 2] >= xthr ? x[4 * i + 2] : -INFINITY, x[4 * i + 3] >= xthr ? x[4 * i + 3] : -INFINITY));
     }
-    __syncthreads();      // every thread is past its last read of the row's shared state
-    if (tid == 0) { s.ncand = 0; s.n_list = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; }
+    if (!sample) __syncthreads();      // (the race's reduction is the barrier otherwise) every thread is past its reads of the row's shared state
+    if (tid == 0) { s.nc = 0; s.slow = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; s.bPlo = 0x7FFFFFFF; s.bPhi = -1; }
+    row += gridDim.x;
   }
 }
 
@@ -1013,18 +1142,32 @@ extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L
   cudaStream_t st = (cudaStream_t)stream;
   ProfileScope prof(st, FAM_SAMPLE, (double)rows * (8.0 * V + (noise ? 4.0 * V + 8.0 : 0.0) + (mixed_out ? 4.0 * V : 0.0)));
   const bool filtered = (top_k > 0 && top_k < V) || one_minus_top_p >= 0.0f;
-  static const int occ = [] { const char* e = getenv("SDVAR_K3_OCC"); return e && atoi(e) == 4 ? 4 : 3; }();   // CTAs per SM (A/B switch)
-  const size_t dyn = (size_t)(V + 2) * 10;      // list: (logit, noise) fp32 pairs + vocabulary index (u16), + a dummy slot
+  // pruning threshold of the filtered kernel in standard deviations above the row mean: the (1 - f0) quantile of a normal
+  // distribution for f0 = 1.3 * top_k / V + 0.03 of the row at or above it (a guess the kernel verifies row by row)
+  float zprune = 3e38f;
+  if (top_k > 0 && top_k < V && getenv("SDVAR_K3_NOPRUNE") == nullptr) {
+    const double f0 = 1.3 * (double)top_k / (double)V + 0.03;
+    if (f0 < 0.6) {
+      double lo = -1.0, hi = 6.0;
+      for (int it = 0; it < 60; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (0.5 * erfc(mid / 1.4142135623730951) > f0) lo = mid; else hi = mid;
+      }
+      zprune = (float)lo;
+    }
+  }
+  static const int occ = [] { const char* e = getenv("SDVAR_K3_OCC"); return e && atoi(e) == 3 ? 3 : 4; }();   // CTAs per SM (A/B switch)
+  const size_t dyn = (size_t)V * 4;      // the filtered kernel's noise row
 #define SDVAR_K3(NV)                                                                                                        \
   case NV:                                                                                                                  \
     if (filtered && occ == 3) {                                                                                             \
       SDVAR_SET_SMEM_ONCE((k3_filtered_kernel<NV, 3>), dyn);                                                                \
       k3_filtered_kernel<NV, 3><<<row_grid(rows, 3), kThreads, dyn, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, top_k, \
-                                                          one_minus_top_p, noise, idx_out, mixed_out, prob_out);           \
+                                                          one_minus_top_p, zprune, noise, idx_out, mixed_out, prob_out);   \
     } else if (filtered) {                                                                                                  \
       SDVAR_SET_SMEM_ONCE((k3_filtered_kernel<NV, 4>), dyn);                                                                \
       k3_filtered_kernel<NV, 4><<<grid, kThreads, dyn, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, top_k, \
-                                                          one_minus_top_p, noise, idx_out, mixed_out, prob_out);           \
+                                                          one_minus_top_p, zprune, noise, idx_out, mixed_out, prob_out);   \
     } else {                                                                                                                \
       k3_plain_kernel<NV><<<grid, kThreads, 0, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, noise, idx_out, \
                                                      mixed_out, prob_out);                                                 \
