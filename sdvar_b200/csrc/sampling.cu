@@ -174,26 +174,6 @@ __device__ __forceinline__ void block_max_u32x2(uint32_t& a, uint32_t& b, RedSme
   for (int k = 0; k < kWarps; ++k) { a = max(a, s.u[slot][0][k]); b = max(b, s.u[slot][1][k]); }
   slot ^= 1;
 }
-// two u32 maxima and two float sums behind ONE barrier (the sums feed a heuristic: their order is fixed but not part of any spec)
-__device__ __forceinline__ void block_stats(uint32_t& a, uint32_t& b, float& f0, float& f1, RedSmem& s, int& slot) {
-  a = __reduce_max_sync(0xffffffffu, a);
-  b = __reduce_max_sync(0xffffffffu, b);
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    f0 += __shfl_xor_sync(0xffffffffu, f0, off);
-    f1 += __shfl_xor_sync(0xffffffffu, f1, off);
-  }
-  const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { s.u[slot][0][w] = a; s.u[slot][1][w] = b; s.f[slot][0][w] = f0; s.f[slot][1][w] = f1; }
-  __syncthreads();
-  f0 = 0.0f; f1 = 0.0f;
-#pragma unroll
-  for (int k = 0; k < kWarps; ++k) {
-    a = max(a, s.u[slot][0][k]); b = max(b, s.u[slot][1][k]);
-    f0 += s.f[slot][0][k]; f1 += s.f[slot][1][k];
-  }
-  slot ^= 1;
-}
 __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, RedSmem& s, int& slot) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -232,20 +212,26 @@ __global__ void spec_expf_kernel(const float* __restrict__ x, long long n, float
 //   k3_plain_kernel     no top-k / top-p: CFG mix, softmax in the canonical 256-lane float order, exponential race.
 //   k3_filtered_kernel  top-k and/or top-p.  Round 1 searched both cuts by bisection (~26 block-wide barrier rounds, 0.15-0.23
 //                       of HBM); round 2 (first half) compacted the survivors of a histogram cut into shared memory and worked
-//                       on the list (16 barriers, ~2060 instructions per thread-row, 0.28-0.38).  v3, this one:
-//     1. the row never leaves the registers.  ONE pass computes every exponential (packed fp32x2) and adds each entry to three
-//        shared-memory histograms over 1024 value bins: count, and the two 20-bit limbs of E = rint(e * 2^40).  Bin index and
-//        limbs come from magic-addend roundings on the packed pipe -- no float<->int conversion, no division;
+//                       on the list (16 barriers, ~1950 instructions per warp-row, 0.28-0.37).  v3, this one (0.37-0.47):
+//     1. the row never leaves the registers: 128 threads x 32 entries for V <= 4096 (the cut-location phases cost every thread
+//        the same however many entries it owns, so fewer, fatter threads halve that overhead per row; 128 registers, no spills).
+//        ONE pass computes every exponential (packed fp32x2) and adds each entry to three shared-memory histograms over 1024
+//        value bins: count, and the two 20-bit limbs of E = rint(e * 2^40).  Bin offset and limbs come from magic-addend
+//        roundings on the packed pipe -- no float<->int conversion, no division;
 //     2. one block scan over the bins (from the top) gives, for every bin, the entries and the mass above it, hence the bin
 //        the top-k cut falls into AND the few bins the top-p cut can fall into (the spec states the top-p test on the
 //        fixed-point numerators: E{x_w > x_v} >= Zi - floor(Zi * thr), no per-entry probability);
 //     3. the entries of those bins (~20-40 of the row) are the only ones looked at individually: all-pairs ranks and sums
-//        among them, 256 / P threads per candidate, settle both cuts exactly (tie groups whole) and yield Zi and the final
-//        sum Z2i without another pass;
-//     4. the race runs on the numerators, argmax e * R(noise), R the spec's division-free reciprocal (packed Newton steps).
+//        among them, NT / P threads per candidate, settle both cuts exactly (tie groups whole) and yield Zi and the final
+//        sum Z2i without another pass (tests/test_k3_model.py restates this logic on the CPU against the definition);
+//     4. the race runs on the numerators, argmax e * R(noise), R the spec's division-free reciprocal (packed Newton steps);
+//        the noise row is fetched into shared memory by cp.async at row start.
 //     Every sum that decides something is an integer sum of fixed-point terms, so the atomics may run in any order and the
 //     kernel is bit-exact to oracle/spec_c.  9 barriers per row.  Rows the histograms cannot take (non-finite or zero value
-//     range, > 256 candidates, top_p == 0) go through k3_row_slow (bit-serial searches, any input).
+//     range, more candidates than threads, top_p == 0) go through k3_row_slow (bit-serial searches, any input).
+//     What bounds it now (profiles/ncu_k3_r02b.md): ~2400 instructions per warp-row at 16 resident warps and 12 288
+//     shared-memory atomics per row (~2 lanes per clock per SM measured) -- instruction issue and the atomics each account for
+//     about the whole row time; removing either alone (pruned histograms / branch-free code) gave 0-5 %.
 constexpr int kBins = 1024;
 constexpr int kCandMax = 256;
 constexpr int kRcpSteps = 4;                // SDVAR_RCP_STEPS of the spec
@@ -372,21 +358,6 @@ __device__ __forceinline__ unsigned long long block_sum_fix(uint32_t hi, uint32_
   for (int k = 0; k < kWarps / 2; ++k) { const ulonglong2 v = z2[k]; t += v.x + v.y; }
   return t;
 }
-// the three histogram updates of one entry (count, high limb, low limb; the arrays are 4 * kBins bytes apart), PREDICATED on
-// x >= t0: written in PTX because the compiler turns the C++ `if` into a branch per entry (BSSY / BRA / BSYNC around three
-// atomics, +140 instructions per thread-row)
-__device__ __forceinline__ void hist3(uint32_t addr, float x, float t0, uint32_t hi, uint32_t lo) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "setp.ge.f32 q, %1, %2;\n"
-      "@q red.shared.add.u32 [%0], 1;\n"
-      "@q red.shared.add.u32 [%0+4096], %3;\n"
-      "@q red.shared.add.u32 [%0+8192], %4;\n"
-      "}\n" ::"r"(addr),
-      "f"(x), "f"(t0), "r"(hi), "r"(lo)
-      : "memory");
-}
 // removable mass of the top-p cut: floor(Zi * thr_fix / 2^30), Zi < 2^53, thr_fix <= 2^30
 __device__ __forceinline__ unsigned long long thr_mass(unsigned long long Zi, uint32_t thr_fix) {
   const unsigned long long lo = Zi * (unsigned long long)thr_fix, hi = __umul64hi(Zi, (unsigned long long)thr_fix);
@@ -404,25 +375,78 @@ __device__ __forceinline__ f32x2 spec_rcp2(float n0, float n1) {
   return y;
 }
 
+// ---- block reductions of the filtered kernel, NW warps per CTA (128 threads x 32 entries for V <= 4096: the cut-location
+// phases cost every THREAD the same whatever the row length per thread, so half the threads halve that overhead per row)
+template <int NW>
+__device__ __forceinline__ void k3_block_max2(uint32_t& a, uint32_t& b, RedSmem& s, int& slot) {
+  a = __reduce_max_sync(0xffffffffu, a);
+  b = __reduce_max_sync(0xffffffffu, b);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s.u[slot][0][w] = a; s.u[slot][1][w] = b; }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NW; ++k) { a = max(a, s.u[slot][0][k]); b = max(b, s.u[slot][1][k]); }
+  slot ^= 1;
+}
+template <int NW>
+__device__ __forceinline__ int k3_block_sum_int(int c, RedSmem& s, int& slot) {
+  c = __reduce_add_sync(0xffffffffu, c);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) s.i[slot][w] = c;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int k = 0; k < NW; ++k) t += s.i[slot][k];
+  slot ^= 1;
+  return t;
+}
+template <int NW>
+__device__ __forceinline__ unsigned long long k3_block_max_u64(unsigned long long v, RedSmem& s, int& slot) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, off);
+    v = o > v ? o : v;
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) s.u64[slot][w] = v;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NW; ++k) v = s.u64[slot][k] > v ? s.u64[slot][k] : v;
+  slot ^= 1;
+  return v;
+}
+// block sum of per-thread limb sums -> u64 total (integer sums: any order gives the same total; per-thread sums < 2^26, warp < 2^31)
+template <int NW>
+__device__ __forceinline__ unsigned long long k3_block_sum_fix(uint32_t hi, uint32_t lo, K3Smem& s, int buf) {
+  hi = __reduce_add_sync(0xffffffffu, hi);
+  lo = __reduce_add_sync(0xffffffffu, lo);
+  if ((threadIdx.x & 31) == 0) s.zpart[buf][threadIdx.x >> 5] = ((unsigned long long)hi << 20) + (unsigned long long)lo;
+  __syncthreads();
+  unsigned long long t = 0;
+#pragma unroll
+  for (int k = 0; k < NW; ++k) t += s.zpart[buf][k];
+  return t;
+}
+
 // ---- generic path of one row (block-wide, any input): bit-serial searches on the order-preserving keys with one block
 // reduction per bit.  ~70 barriers: only for rows the histograms cannot take (non-finite or zero value range, more than
-// kCandMax candidates around a cut, a bin with more than 4095 entries, top_p == 0).  Re-reads the row so that the caller's
+// threads candidates around a cut, a bin with more than 4095 entries, top_p == 0).  Re-reads the row so that the caller's
 // registers stay out of local memory.  Returns the cut as a key (keep <=> key(x) >= klow) and the final fixed-point sum.
 struct K3Cut {
   uint32_t klow;
   unsigned long long Z2i;
   int slot;
 };
-template <int NV>
+template <int NV, int NT>
 __device__ __noinline__ K3Cut k3_row_slow(K3Smem& s, int slot, const float4* __restrict__ pc, const float4* __restrict__ pu, float t1,
                                           float t2, bool use_k, int top_k, bool use_p, uint32_t thr_fix, uint32_t kmx) {
-  constexpr int E = NV * 4;
+  constexpr int CH = NV * 256 / NT, E = CH * 4, NW = NT / 32;
   const int tid = threadIdx.x;
   uint32_t key[E], hi[E], lo[E];
   float x[E];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float4 a = ldg_stream(pc + i * kThreads + tid), c = ldg_stream(pu + i * kThreads + tid);
+  for (int i = 0; i < CH; ++i) {
+    const float4 a = ldg_stream(pc + i * NT + tid), c = ldg_stream(pu + i * NT + tid);
     x[4 * i + 0] = __fsub_rn(__fmul_rn(a.x, t1), __fmul_rn(c.x, t2));
     x[4 * i + 1] = __fsub_rn(__fmul_rn(a.y, t1), __fmul_rn(c.y, t2));
     x[4 * i + 2] = __fsub_rn(__fmul_rn(a.z, t1), __fmul_rn(c.z, t2));
@@ -438,7 +462,7 @@ __device__ __noinline__ K3Cut k3_row_slow(K3Smem& s, int slot, const float4* __r
       int c = 0;
 #pragma unroll
       for (int e = 0; e < E; ++e) c += (key[e] >= tr) ? 1 : 0;
-      c = block_sum_int(c, s.red, slot);
+      c = k3_block_sum_int<NW>(c, s.red, slot);
       if (c >= top_k) K = tr;
     }
   }
@@ -452,7 +476,7 @@ __device__ __noinline__ K3Cut k3_row_slow(K3Smem& s, int slot, const float4* __r
     sl += lo[e];
   }
   int buf = 0;
-  const unsigned long long Zi = block_sum_fix(sh, sl, s, buf);
+  const unsigned long long Zi = k3_block_sum_fix<NW>(sh, sl, s, buf);
   buf ^= 1;
   uint32_t klow = K;
   unsigned long long Z2i = Zi;
@@ -466,7 +490,7 @@ __device__ __noinline__ K3Cut k3_row_slow(K3Smem& s, int slot, const float4* __r
 #pragma unroll
       for (int e = 0; e < E; ++e)
         if (key[e] <= tr) { sh += hi[e]; sl += lo[e]; }      // entries below the top-k cut carry zero limbs
-      const unsigned long long a = block_sum_fix(sh, sl, s, buf);
+      const unsigned long long a = k3_block_sum_fix<NW>(sh, sl, s, buf);
       buf ^= 1;
       if (a <= thrE) T = tr;
     }
@@ -476,24 +500,29 @@ __device__ __noinline__ K3Cut k3_row_slow(K3Smem& s, int slot, const float4* __r
 #pragma unroll
     for (int e = 0; e < E; ++e)
       if (key[e] >= klow) { sh += hi[e]; sl += lo[e]; }
-    Z2i = block_sum_fix(sh, sl, s, buf);
+    Z2i = k3_block_sum_fix<NW>(sh, sl, s, buf);
   }
   return K3Cut{klow, Z2i, slot};
 }
 
-template <int NV, int OCC>
-__global__ void __launch_bounds__(kThreads, OCC)
+template <int NV, int NT, int OCC>
+__global__ void __launch_bounds__(NT, OCC)
 k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, int in_off, int out_ld, int out_off, SegTable seg,
-                   int top_k, float thr, float zprune, const float* __restrict__ noise, long long* __restrict__ idx_out,
+                   int top_k, float thr, const float* __restrict__ noise, long long* __restrict__ idx_out,
                    float* __restrict__ mixed_out, float* __restrict__ prob_out) {
   constexpr int V = NV * 1024;
-  constexpr int E = NV * 4;
+  constexpr int CH = NV * 256 / NT;          // float4 chunks per thread: thread t owns chunks f = i * NT + t
+  constexpr int E = CH * 4;                  // entries per thread (<= 32: one flag bit each)
+  constexpr int NW = NT / 32;
+  constexpr int BPT = kBins / NT;            // bins per thread in the scan
+  constexpr int kCand = NT < kCandMax ? NT : kCandMax;
+  static_assert(E <= 32 && BPT % 4 == 0, "k3_filtered_kernel shape");
   __shared__ K3Smem s;
   extern __shared__ __align__(16) unsigned char k3_noise[];      // [V] floats: the row's noise, fetched by cp.async at row start
   int slot = 0;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const long long rows = (long long)B * L;
-  for (int i = tid; i < kBins; i += kThreads) { s.hcnt[i] = 0; s.hhi[i] = 0; s.hlo[i] = 0; }
+  for (int i = tid; i < kBins; i += NT) { s.hcnt[i] = 0; s.hhi[i] = 0; s.hlo[i] = 0; }
   if (tid == 0) { s.nc = 0; s.slow = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; s.bPlo = 0x7FFFFFFF; s.bPhi = -1; }
   __syncthreads();
   const bool sample = noise != nullptr;
@@ -501,9 +530,8 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
   const bool use_p = thr >= 0.0f;
   const uint32_t thr_fix = use_p ? (uint32_t)__fmul_rn(thr, kFixM) : 0u;      // floor
   const bool small = rows < 0x7FFFFFFFLL;
-  const int q0 = kBins - 4 - 4 * tid;       // this thread scans bins q0+3, q0+2, q0+1, q0 (descending)
-  bool prune = zprune < 1e30f;
-  for (long long row = blockIdx.x; row < rows;) {
+  const int q0 = kBins - BPT - BPT * tid;   // this thread scans bins q0+BPT-1 .. q0 (descending)
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
     int b, pos;
     if (small) { b = (int)((uint32_t)row / (uint32_t)L); pos = (int)((uint32_t)row - (uint32_t)b * (uint32_t)L); }
     else { b = (int)(row / L); pos = (int)(row - (long long)b * L); }
@@ -514,11 +542,11 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
     const float4* pu = reinterpret_cast<const float4*>(logits + ((long long)(B + b) * in_ld + in_off + pos) * V);
     float x[E];
     {
-      float4 a[NV], c[NV];
+      float4 a[CH], c[CH];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) { a[i] = ldg_stream(pc + i * kThreads + tid); c[i] = ldg_stream(pu + i * kThreads + tid); }
+      for (int i = 0; i < CH; ++i) { a[i] = ldg_stream(pc + i * NT + tid); c[i] = ldg_stream(pu + i * NT + tid); }
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
+      for (int i = 0; i < CH; ++i) {
         x[4 * i + 0] = __fsub_rn(__fmul_rn(a[i].x, t1), __fmul_rn(c[i].x, t2));
         x[4 * i + 1] = __fsub_rn(__fmul_rn(a[i].y, t1), __fmul_rn(c[i].y, t2));
         x[4 * i + 2] = __fsub_rn(__fmul_rn(a[i].z, t1), __fmul_rn(c[i].z, t2));
@@ -528,46 +556,35 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
     if (sample) {      // every thread fetches (and later reads) its own chunks: no barrier needed, only the wait
       const float4* pn = reinterpret_cast<const float4*>(noise + row * V);
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(k3_noise) + (uint32_t)(i * kThreads + tid) * 16u),
-                     "l"(pn + i * kThreads + tid)
+      for (int i = 0; i < CH; ++i)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(k3_noise) + (uint32_t)(i * NT + tid) * 16u),
+                     "l"(pn + i * NT + tid)
                      : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    // ---- row max / min, and (heuristic only) mean / variance ----
-    float mx = -INFINITY, mn = INFINITY, s1 = 0.0f, s2 = 0.0f;      // s1, s2: over a quarter of the row (every fourth entry)
+    // ---- row max / min ----
+    float mx = -INFINITY, mn = INFINITY;
 #pragma unroll
     for (int e = 0; e < E; ++e) { mx = fmaxf(mx, x[e]); mn = fminf(mn, x[e]); }
-#pragma unroll
-    for (int e = 0; e < E; e += 4) { s1 += x[e]; s2 = fmaf(x[e], x[e], s2); }
     uint32_t kmx = fkey(__fadd_rn(mx, 0.0f)), kmnc = ~fkey(__fadd_rn(mn, 0.0f));
-    block_stats(kmx, kmnc, s1, s2, s.red, slot);
+    k3_block_max2<NW>(kmx, kmnc, s.red, slot);
     const float m = fkey_inv(kmx), xmin = fkey_inv(~kmnc);
 
     // ---- value bins.  tb(x) = fma(x, scale, offm) lands in [2^21, 2^22), where one ulp is 1/4: bits(tb) - bits(kMagic4) counts
     // quarter bins, so (bits(tb) & 0xffc) IS the byte offset of bin(x) in a histogram -- one LOP per entry, no float->int
-    // conversion, monotone in x.  Bins only LOCATE the cuts; every sum that decides something is an exact integer, so neither
-    // the binning nor the pruning below is part of the spec.
-    // Pruning (top-k only): entries below t0 = mean + zprune * sigma cannot survive the top-k cut IF at least top_k entries lie
-    // at or above t0 -- which the scan's total verifies; such entries are left out of the histograms (shared-memory atomics
-    // run at ~2 lanes per clock and bound this kernel).  When the check fails the row is redone with t0 = min. ----
+    // conversion, monotone in x.  Bins only LOCATE the cuts; every sum that decides something is an exact integer, so the
+    // binning is not part of the spec.
+    // (Measured and dropped: leaving entries below mean + z sigma out of the histograms, verified by the scan's total.  It cut
+    // the shared-memory atomics 3.3x but ptxas wraps every predicated ATOMS in a branch of its own -- +12 instructions per
+    // entry -- and the atomics were not the limiter: 4 % faster with the branches, slower than this version without.) ----
     bool fast = false;
-    float scale = 0.0f, offm = 0.0f, t0 = xmin;
+    float scale = 0.0f, offm = 0.0f;
     if (__fsub_rn(m, xmin) > 0.0f && __fsub_rn(m, xmin) < INFINITY && thr_fix < (1u << 30)) {
-      if (use_k && prune) {
-        const float mean = s1 * (4.0f / (float)V);
-        const float var = fmaxf(fmaf(-mean, mean, s2 * (4.0f / (float)V)), 0.0f);
-        float sd;
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(var));      // a guess, identical in every thread
-        const float tt = fmaf(zprune, sd, mean);
-        if (tt > xmin && tt < m) t0 = tt;
-      }
-      scale = __fdividef((float)(kBins - 3), __fsub_rn(m, t0));          // any value will do as long as the checks below hold
-      offm = __fmaf_rn(-t0, scale, kMagic4 + 1.0f);
-      const uint32_t blo = f2u(__fmaf_rn(t0, scale, offm)) - kMagic4Bits, bhi = f2u(__fmaf_rn(m, scale, offm)) - kMagic4Bits;
+      scale = __fdividef((float)(kBins - 3), __fsub_rn(m, xmin));          // any value will do as long as the checks below hold
+      offm = __fmaf_rn(-xmin, scale, kMagic4 + 1.0f);
+      const uint32_t blo = f2u(__fmaf_rn(xmin, scale, offm)) - kMagic4Bits, bhi = f2u(__fmaf_rn(m, scale, offm)) - kMagic4Bits;
       fast = __fmul_rn(fmaxf(fabsf(xmin), fabsf(m)), scale) < 262144.0f && blo < 4u * kBins && bhi < 4u * kBins;
     }
-    prune = zprune < 1e30f;      // (a redone row ran without; the next row prunes again)
 
     // ---- pass 1: exponentials (kept in registers), fixed-point limbs, three histogram atomics per entry ----
     float ev[E];
@@ -575,8 +592,6 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
       const f32x2 nm2 = splat2(-m);
       if (fast) {
         const f32x2 sc2 = splat2(scale), of2 = splat2(offm), p20 = splat2(1048576.0f), mg = splat2(kMagic), nmg = splat2(-kMagic);
-        const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(&s.hcnt[0]);
-        static_assert(offsetof(K3Smem, hhi) - offsetof(K3Smem, hcnt) == 4096 && offsetof(K3Smem, hlo) - offsetof(K3Smem, hcnt) == 8192, "hist3 layout");
 #pragma unroll
         for (int q = 0; q < E; q += 2) {
           const f32x2 xp = pk2(x[q], x[q + 1]);
@@ -596,9 +611,14 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
           unpk2(tb, tb0, tb1);
           unpk2(th, th0, th1);
           unpk2(tl, tl0, tl1);
-          // (for an entry at or above t0 the mask only drops the quarter-bin bits; it also keeps a NaN from addressing outside)
-          hist3(hbase + (f2u(tb0) & (4u * kBins - 4u)), x[q], t0, f2u(th0), f2u(tl0));
-          hist3(hbase + (f2u(tb1) & (4u * kBins - 4u)), x[q + 1], t0, f2u(th1), f2u(tl1));
+          // (the mask only drops the quarter-bin bits of a finite row; it also keeps a NaN from addressing outside the arrays)
+          const uint32_t o0 = (f2u(tb0) & (4u * kBins - 4u)) >> 2, o1 = (f2u(tb1) & (4u * kBins - 4u)) >> 2;
+          atomicAdd(&s.hcnt[o0], 1u);
+          atomicAdd(&s.hhi[o0], f2u(th0));
+          atomicAdd(&s.hlo[o0], f2u(tl0));
+          atomicAdd(&s.hcnt[o1], 1u);
+          atomicAdd(&s.hhi[o1], f2u(th1));
+          atomicAdd(&s.hlo[o1], f2u(tl1));
         }
       } else {
 #pragma unroll
@@ -612,21 +632,27 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
 
     // ---- scan of the bins from the top: entries / E above every bin; the top-k crossing bin ----
     unsigned long long Etot = 0;
-    uint32_t ntot = 0;
     if (fast) {
       __syncthreads();
-      const uint4 c4 = *reinterpret_cast<const uint4*>(&s.hcnt[q0]);
-      const uint4 h4 = *reinterpret_cast<const uint4*>(&s.hhi[q0]);
-      const uint4 l4 = *reinterpret_cast<const uint4*>(&s.hlo[q0]);
-      *reinterpret_cast<uint4*>(&s.hcnt[q0]) = make_uint4(0u, 0u, 0u, 0u);      // ready for the next row
-      *reinterpret_cast<uint4*>(&s.hhi[q0]) = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(&s.hlo[q0]) = make_uint4(0u, 0u, 0u, 0u);
-      const uint32_t cc[4] = {c4.w, c4.z, c4.y, c4.x}, hh[4] = {h4.w, h4.z, h4.y, h4.x}, ll[4] = {l4.w, l4.z, l4.y, l4.x};
-      unsigned long long Eb[4];
+      uint32_t cc[BPT], hh[BPT], ll[BPT];      // index k <-> bin q0 + BPT - 1 - k (descending)
+#pragma unroll
+      for (int g = 0; g < BPT / 4; ++g) {
+        const int qq = q0 + BPT - 4 - 4 * g;
+        const uint4 c4 = *reinterpret_cast<const uint4*>(&s.hcnt[qq]);
+        const uint4 h4 = *reinterpret_cast<const uint4*>(&s.hhi[qq]);
+        const uint4 l4 = *reinterpret_cast<const uint4*>(&s.hlo[qq]);
+        *reinterpret_cast<uint4*>(&s.hcnt[qq]) = make_uint4(0u, 0u, 0u, 0u);      // ready for the next row
+        *reinterpret_cast<uint4*>(&s.hhi[qq]) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(&s.hlo[qq]) = make_uint4(0u, 0u, 0u, 0u);
+        cc[4 * g] = c4.w; cc[4 * g + 1] = c4.z; cc[4 * g + 2] = c4.y; cc[4 * g + 3] = c4.x;
+        hh[4 * g] = h4.w; hh[4 * g + 1] = h4.z; hh[4 * g + 2] = h4.y; hh[4 * g + 3] = h4.x;
+        ll[4 * g] = l4.w; ll[4 * g + 1] = l4.z; ll[4 * g + 2] = l4.y; ll[4 * g + 3] = l4.x;
+      }
+      unsigned long long Eb[BPT];
       uint32_t ct = 0;
       unsigned long long Et = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < BPT; ++k) {
         const uint32_t H = hh[k] - cc[k] * kMagicBits;                          // exact mod 2^32: the true sums fit (cc <= 4095)
         const int Lo = (int)(ll[k] - cc[k] * kMagicBits);
         Eb[k] = ((unsigned long long)H << 20) + (unsigned long long)(long long)Lo;
@@ -646,16 +672,15 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
       uint32_t cb = ci - ct;
       unsigned long long eb = Ei - Et;
 #pragma unroll
-      for (int k = 0; k < kWarps; ++k) {
+      for (int k = 0; k < NW; ++k) {
         const uint32_t wc = s.wc[k];
         const unsigned long long wE = s.wE[k];
         if (k < wid) { cb += wc; eb += wE; }
         Etot += wE;
-        ntot += wc;
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int bin = q0 + 3 - k;
+      for (int k = 0; k < BPT; ++k) {
+        const int bin = q0 + BPT - 1 - k;
         s.pcab[bin] = cb;
         s.pdex[bin + 1] = eb;
         if (cc[k] > 4095u) s.slow = 1;
@@ -663,12 +688,8 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
         cb += cc[k];
         eb += Eb[k];
       }
-      if (tid == kThreads - 1) s.pdex[0] = eb;      // == Etot
+      if (tid == NT - 1) s.pdex[0] = eb;      // == Etot
       __syncthreads();
-      if (use_k && ntot < (uint32_t)top_k) {      // fewer than top_k entries at or above t0: the pruning guess was too high.
-        prune = false;                            // Redo the row without (the histograms are zero again, nothing else was touched)
-        continue;
-      }
       fast = s.slow == 0;
     }
 
@@ -679,10 +700,10 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
       if (use_p) {
         const unsigned long long zmin = use_k ? s.pdex[bK + 1] : Etot, zmax = use_k ? s.pdex[bK] : Etot;
         const unsigned long long tmin = zmin - thr_mass(zmin, thr_fix), tmax = zmax - thr_mass(zmax, thr_fix);
-        unsigned long long din = s.pdex[q0 + 4];      // E above bin q0+3
+        unsigned long long din = s.pdex[q0 + BPT];      // E above this thread's top bin
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int bin = q0 + 3 - k;
+        for (int k = 0; k < BPT; ++k) {
+          const int bin = q0 + BPT - 1 - k;
           const unsigned long long dex = din;
           din = s.pdex[bin];                          // E above, this bin included
           if (din != dex && dex < tmax && din >= tmin) { atomicMin(&s.bPlo, bin); atomicMax(&s.bPhi, bin); }
@@ -699,7 +720,6 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
     if (fast) {
       kgroup = use_k && bK < plo;
       // in quarter-bin units relative to bits(tb): bin == bK <=> bits - cK < 4; plo <= bin <= phi <=> bits - cP < 4 * (phi - plo + 1);
-      // an entry below t0 (not in the histograms) has bits < kMagic4Bits, i.e. a huge unsigned difference: never a candidate
       const uint32_t cK = kMagic4Bits + 4u * (uint32_t)bK, wK = kgroup ? 4u : 0u;
       const uint32_t cP = kMagic4Bits + 4u * (uint32_t)plo, wP = 4u * (uint32_t)(phi - plo + 1), span = (uint32_t)(phi - plo);
       uint32_t mask = 0;
@@ -716,14 +736,14 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
       while (mask) {                        // rare: ~20-40 entries of the row; the entry is re-read to keep x[] / ev[] in registers
         const int i = __ffs(mask) - 1;
         mask &= mask - 1;
-        const int f = (i >> 2) * kThreads + tid;
+        const int f = (i >> 2) * NT + tid;
         const float xc = __ldg(reinterpret_cast<const float*>(pc + f) + (i & 3)), xu = __ldg(reinterpret_cast<const float*>(pu + f) + (i & 3));
         const float xe = __fsub_rn(__fmul_rn(xc, t1), __fmul_rn(xu, t2));
         uint32_t h, l;
         fix_e(spec_expf(__fsub_rn(xe, m)), h, l);
         const uint32_t o = (f2u(__fmaf_rn(xe, scale, offm)) - kMagic4Bits) >> 2;
         const int p = atomicAdd(&s.nc, 1);
-        if (p < kCandMax) {
+        if (p < kCand) {
           s.cx[p] = xe;
           s.cE[p] = ((unsigned long long)h << 20) + (unsigned long long)l;
           s.cg[p] = (o - (uint32_t)plo <= span) ? 1 : 0;
@@ -731,15 +751,15 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
       }
       __syncthreads();
       nc = s.nc;
-      fast = nc <= kCandMax;
+      fast = nc <= kCand;
     }
 
-    // ---- exact cuts among the candidates: all-pairs ranks / sums, 256 / P threads per candidate ----
+    // ---- exact cuts among the candidates: all-pairs ranks / sums, NT / P threads per candidate ----
     uint32_t klow = 0;
     unsigned long long Z2i = 0;
     bool z2_shared = false;
     if (fast) {
-      int P = 8, lg = 5;                     // lg = log2(threads per candidate)
+      int P = 8, lg = NT == 128 ? 4 : 5;     // lg = log2(threads per candidate) = log2(NT / P)
       while (P < nc) { P <<= 1; --lg; }
       const int G = 1 << lg, i = tid >> lg, sub = tid & (G - 1);
       float xi = 0.0f;
@@ -801,15 +821,15 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
         }
       }
     } else {
-      const K3Cut c = k3_row_slow<NV>(s, slot, pc, pu, t1, t2, use_k, top_k, use_p, thr_fix, kmx);
+      const K3Cut c = k3_row_slow<NV, NT>(s, slot, pc, pu, t1, t2, use_k, top_k, use_p, thr_fix, kmx);
       klow = c.klow;
       Z2i = c.Z2i;
       slot = c.slot;
       // re-materialise the row behind the call instead of keeping 2 E registers alive across it (which would put spill
       // stores on the fast path)
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float4 a = ldg_stream(pc + i * kThreads + tid), cu = ldg_stream(pu + i * kThreads + tid);
+      for (int i = 0; i < CH; ++i) {
+        const float4 a = ldg_stream(pc + i * NT + tid), cu = ldg_stream(pu + i * NT + tid);
         x[4 * i + 0] = __fsub_rn(__fmul_rn(a.x, t1), __fmul_rn(cu.x, t2));
         x[4 * i + 1] = __fsub_rn(__fmul_rn(a.y, t1), __fmul_rn(cu.y, t2));
         x[4 * i + 2] = __fsub_rn(__fmul_rn(a.z, t1), __fmul_rn(cu.z, t2));
@@ -828,13 +848,13 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
 
     if (sample) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      float4 nz[NV];
+      float4 nz[CH];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) nz[i] = reinterpret_cast<const float4*>(k3_noise)[i * kThreads + tid];
+      for (int i = 0; i < CH; ++i) nz[i] = reinterpret_cast<const float4*>(k3_noise)[i * NT + tid];
       float best = -1.0f;
       int bi = 0x7FFFFFFF;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
+      for (int i = 0; i < CH; ++i) {
         float r0, r1, r2, r3;
         unpk2(mul2(pk2(ev[4 * i], ev[4 * i + 1]), spec_rcp2(nz[i].x, nz[i].y)), r0, r1);
         unpk2(mul2(pk2(ev[4 * i + 2], ev[4 * i + 3]), spec_rcp2(nz[i].z, nz[i].w)), r2, r3);
@@ -842,10 +862,10 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float r = (x[4 * i + c] >= xthr) ? rr[c] : -1.0f;
-          if (r > best) { best = r; bi = 4 * (i * kThreads + tid) + c; }
+          if (r > best) { best = r; bi = 4 * (i * NT + tid) + c; }
         }
       }
-      const unsigned long long w = block_max_u64(pack_best(best, bi), s.red, slot);
+      const unsigned long long w = k3_block_max_u64<NW>(pack_best(best, bi), s.red, slot);
       int win = (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
       const bool none = (uint32_t)(w >> 32) == fkey(-1.0f);      // nothing alive (a row of -inf / NaN): index 0, probability 0
       if (none) win = 0;
@@ -867,13 +887,12 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
     if (mixed_out != nullptr) {
       float4* po = reinterpret_cast<float4*>(mixed_out + orow * V);
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        stg_stream(po + i * kThreads + tid, make_float4(x[4 * i] >= xthr ? x[4 * i] : -INFINITY, x[4 * i + 1] >= xthr ? x[4 * i + 1] : -INFINITY,
+      for (int i = 0; i < CH; ++i)
+        stg_stream(po + i * NT + tid, make_float4(x[4 * i] >= xthr ? x[4 * i] : -INFINITY, x[4 * i + 1] >= xthr ? x[4 * i + 1] : -INFINITY,
                                                          x[4 * i + 2] >= xthr ? x[4 * i + 2] : -INFINITY, x[4 * i + 3] >= xthr ? x[4 * i + 3] : -INFINITY));
     }
     if (!sample) __syncthreads();      // (the race's reduction is the barrier otherwise) every thread is past its reads of the row's shared state
     if (tid == 0) { s.nc = 0; s.slow = 0; s.tkey = 0; s.minkey = 0xFFFFFFFFu; s.bPlo = 0x7FFFFFFF; s.bPhi = -1; }
-    row += gridDim.x;
   }
 }
 
@@ -1142,32 +1161,18 @@ extern "C" int sdvar_sample_cfg_topk_topp(const float* logits_2BLV, int B, int L
   cudaStream_t st = (cudaStream_t)stream;
   ProfileScope prof(st, FAM_SAMPLE, (double)rows * (8.0 * V + (noise ? 4.0 * V + 8.0 : 0.0) + (mixed_out ? 4.0 * V : 0.0)));
   const bool filtered = (top_k > 0 && top_k < V) || one_minus_top_p >= 0.0f;
-  // pruning threshold of the filtered kernel in standard deviations above the row mean: the (1 - f0) quantile of a normal
-  // distribution for f0 = 1.3 * top_k / V + 0.03 of the row at or above it (a guess the kernel verifies row by row)
-  float zprune = 3e38f;
-  if (top_k > 0 && top_k < V && getenv("SDVAR_K3_NOPRUNE") == nullptr) {
-    const double f0 = 1.3 * (double)top_k / (double)V + 0.03;
-    if (f0 < 0.6) {
-      double lo = -1.0, hi = 6.0;
-      for (int it = 0; it < 60; ++it) {
-        const double mid = 0.5 * (lo + hi);
-        if (0.5 * erfc(mid / 1.4142135623730951) > f0) lo = mid; else hi = mid;
-      }
-      zprune = (float)lo;
-    }
-  }
-  static const int occ = [] { const char* e = getenv("SDVAR_K3_OCC"); return e && atoi(e) == 3 ? 3 : 4; }();   // CTAs per SM (A/B switch)
+  static const int nt = [] { const char* e = getenv("SDVAR_K3_THREADS"); return e && atoi(e) == 256 ? 256 : 128; }();   // threads per row (A/B switch)
   const size_t dyn = (size_t)V * 4;      // the filtered kernel's noise row
 #define SDVAR_K3(NV)                                                                                                        \
   case NV:                                                                                                                  \
-    if (filtered && occ == 3) {                                                                                             \
-      SDVAR_SET_SMEM_ONCE((k3_filtered_kernel<NV, 3>), dyn);                                                                \
-      k3_filtered_kernel<NV, 3><<<row_grid(rows, 3), kThreads, dyn, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, top_k, \
-                                                          one_minus_top_p, zprune, noise, idx_out, mixed_out, prob_out);   \
+    if (filtered && nt == 128 && NV <= 4) {                                                                                 \
+      SDVAR_SET_SMEM_ONCE((k3_filtered_kernel<NV, (NV <= 4 ? 128 : 256), 4>), dyn);                                         \
+      k3_filtered_kernel<NV, (NV <= 4 ? 128 : 256), 4><<<grid, (NV <= 4 ? 128 : 256), dyn, st>>>(                          \
+          logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, top_k, one_minus_top_p, noise, idx_out, mixed_out, prob_out); \
     } else if (filtered) {                                                                                                  \
-      SDVAR_SET_SMEM_ONCE((k3_filtered_kernel<NV, 4>), dyn);                                                                \
-      k3_filtered_kernel<NV, 4><<<grid, kThreads, dyn, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, top_k, \
-                                                          one_minus_top_p, zprune, noise, idx_out, mixed_out, prob_out);   \
+      SDVAR_SET_SMEM_ONCE((k3_filtered_kernel<NV, 256, 4>), dyn);                                                           \
+      k3_filtered_kernel<NV, 256, 4><<<grid, kThreads, dyn, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, top_k, \
+                                                          one_minus_top_p, noise, idx_out, mixed_out, prob_out);   \
     } else {                                                                                                                \
       k3_plain_kernel<NV><<<grid, kThreads, 0, st>>>(logits_2BLV, B, L, in_ld, in_off, out_ld, out_off, seg, noise, idx_out, \
                                                      mixed_out, prob_out);                                                 \

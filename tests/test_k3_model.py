@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-NB, CAND_MAX = 1024, 256
+NB, CAND_MAX = 1024, 128
 
 
 def fkey(x):
@@ -123,14 +123,14 @@ def cuts_like_the_kernel(x, E, top_k, thr_fix):
 def _rows():
     g = np.random.default_rng(7)
     V = 4096
-    for i in range(10):
+    for i in range(4):
         yield f"gauss{i}", (g.standard_normal(V) * (0.05 if i % 2 else 3.0)).astype(np.float32)
-    for i in range(6):      # peaked: real checkpoints put most of the mass on a few entries
+    for i in range(3):      # peaked: real checkpoints put most of the mass on a few entries
         x = (g.standard_normal(V) * 2).astype(np.float32)
-        x[g.integers(0, V, 3)] += np.float32(6 + 3 * i)
+        x[g.integers(0, V, 3)] += np.float32(6 + 6 * i)
         yield f"peaked{i}", x
-    for i in range(6):      # quantised: tie groups around both cuts
-        yield f"ties{i}", (np.round(g.standard_normal(V) * (2 + i)) / np.float32(4)).astype(np.float32)
+    for i in range(3):      # quantised: tie groups around both cuts
+        yield f"ties{i}", (np.round(g.standard_normal(V) * (2 + 2 * i)) / np.float32(4)).astype(np.float32)
     x = g.standard_normal(V).astype(np.float32); x[:3000] = x[3000]
     yield "one_giant_tie_group", x
     x = np.full(V, 0.25, np.float32); x[7] = 0.5
@@ -155,7 +155,7 @@ def test_kernel_cut_location_equals_the_definition(top_k, top_p):
         klow, Z2i = r
         assert np.array_equal(fkey(x) >= klow, kept), (name, top_k, top_p)
         assert Z2i == Z2, (name, top_k, top_p)
-    assert fast >= 15
+    assert fast >= 8
 
 
 def test_definition_restatement_equals_the_c_spec():

@@ -605,16 +605,24 @@ def test_sample_window_outputs_and_strided_rows(cuda_lib):
 
 
 @pytest.mark.parametrize("top_k,top_p,scale", [(900, 0.96, 0.05), (3000, 0.5, 3.0), (0, 0.96, 1.0), (4095, 0.999, 1.0), (1, 0.0, 1.0),
-                                                 (900, 0.0, 0.0)])
+                                                 (900, 0.0, 0.0), (900, 0.96, -1.0), (900, 0.96, -2.0)])
 def test_sample_filtered_edge_cases_bit_exact(cuda_lib, top_k, top_p, scale):
-    """the histogram / compaction path on its edges: top-p only (every entry survives the cut: long survivor list), nearly
-    everything kept, top_k=1, all logits EQUAL (scale 0: one giant tie group -> bisection fall-backs) and quantised logits
-    with many exact ties around the k-th value."""
+    """the histogram path on its edges: top-p only (every entry alive), nearly everything kept, top_k=1, all logits EQUAL
+    (scale 0: no value range -> the generic bit-serial path), quantised logits with many exact ties around both cuts, 400
+    copies of one value right at the top-k cut (scale -1: more candidates than threads -> generic path) and rows holding -inf
+    (scale -2: non-finite range -> generic path)."""
     from oracle import spec
     B, L, V = 2, 24, 4096
     lg = hashed(f"k3.edge.{top_k}", 6, (2 * B, L, V), scale if scale > 0 else 1.0)
     if scale == 0.0:
         lg = torch.zeros_like(lg) + 0.25
+    if scale == -1.0:
+        srt = lg.sort(dim=-1).values
+        lg = torch.where((lg >= srt[..., V - 1100:V - 1099]) & (lg <= srt[..., V - 700:V - 699]), srt[..., V - 900:V - 899], lg)
+        lg[B:] = 0.0                                           # uncond rows zero: the mixed row keeps the cond row's tie group
+    if scale == -2.0:
+        lg[:, :, ::7] = float("-inf")
+        lg[B:] = 0.0
     lg[:, L // 2:] = (lg[:, L // 2:] * 8).round() / 8          # second half of the rows: heavy ties
     noise = torch.empty(B * L, V).exponential_(generator=torch.Generator().manual_seed(4))
     t1, t2 = spec.cfg_scalars(1.5, [3], 10)
