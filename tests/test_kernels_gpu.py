@@ -637,6 +637,42 @@ def test_sample_filtered_edge_cases_bit_exact(cuda_lib, top_k, top_p, scale):
     assert torch.equal(prob.cpu().view(torch.int32), rp.view(torch.int32))
 
 
+@pytest.mark.parametrize("V", [1024, 2048, 8192])
+def test_sample_and_verify_other_vocabulary_sizes_bit_exact(cuda_lib, V):
+    """the C ABI takes V in {1024, 2048, 4096, 8192}: each is its own instantiation of K3 (128 threads x V/128 entries up to
+    4096, 256 x 32 at 8192) and K4; bit-exact to the C spec like V = 4096."""
+    from oracle import spec
+    B, L = 2, 12
+    lg = hashed(f"k3.V{V}", 8, (2 * B, L, V), 2.0)
+    lg[:, L // 2:] = (lg[:, L // 2:] * 4).round() / 4
+    noise = torch.empty(B * L, V).exponential_(generator=torch.Generator().manual_seed(5))
+    t1, t2 = spec.cfg_scalars(1.5, [5], 10)
+    for top_k, top_p in ((V // 5, 0.96), (0, 0.9), (V // 3, 0.0), (0, 0.0)):
+        ri, rm, rp = spec.sample(lg, [0, L], t1, t2, top_k, top_p, noise)
+        idx = torch.empty(B, L, dtype=torch.int64, device=DEV)
+        mixed = torch.empty(B, L, V, device=DEV)
+        prob = torch.empty(B, L, device=DEV)
+        cuda_lib.sample_cfg_topk_topp(lg.to(DEV), B, L, V, [0, L], t1, t2, top_k, spec.top_p_threshold(top_p), noise.to(DEV), idx, mixed, prob)
+        torch.cuda.synchronize()
+        assert torch.equal(mixed.cpu().view(torch.int32), rm.view(torch.int32)), (top_k, top_p)
+        assert torch.equal(idx.cpu(), ri), (top_k, top_p)
+        assert torch.equal(prob.cpu().view(torch.int32), rp.view(torch.int32)), (top_k, top_p)
+    # K4 on the filtered rows of the last two settings as target / draft
+    xt = spec.sample(lg, [0, L], t1, t2, V // 5, 0.96, None)[1]
+    xd = spec.sample(hashed(f"k4.V{V}", 9, (2 * B, L, V), 2.0), [0, L], t1, t2, V // 5, 0.96, None)[1]
+    d = torch.randint(0, V, (B, L), generator=torch.Generator().manual_seed(6))
+    u = torch.rand(B, L, generator=torch.Generator().manual_seed(7))
+    ref = spec.verify(xt, xd, d, u, noise, [0, L])
+    o = torch.empty(B, L, dtype=torch.int64, device=DEV); a = torch.empty(B, L, dtype=torch.uint8, device=DEV)
+    fr = torch.empty(B, 1, dtype=torch.int32, device=DEV); na = torch.empty(B, 1, dtype=torch.int32, device=DEV)
+    st = torch.empty(B, dtype=torch.int32, device=DEV); sm = torch.empty(4, dtype=torch.int32, device=DEV)
+    ws = torch.zeros(cuda_lib.verify_workspace_ints(B, 1), dtype=torch.int32, device=DEV)
+    cuda_lib.verify_accept_resample(xt.to(DEV), xd.to(DEV), d.to(DEV), u.to(DEV), noise.to(DEV), B, L, V, [0, L], o, a, None, None, fr, na, st, sm, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(o.cpu(), ref["out_idx"]) and torch.equal(a.cpu(), ref["accept"])
+    assert torch.equal(fr.cpu(), ref["first_reject"]) and torch.equal(sm.cpu(), ref["summary"])
+
+
 def test_verify_window_stage_major_aux_bit_exact(cuda_lib):
     """one K4 launch over a 3-stage window with u / noise given as the per-stage draws laid end to end (stage-major), vs the
     C spec fed the same values in dense (b, pos) order; the workspace is left zero and a second launch reproduces the first."""
