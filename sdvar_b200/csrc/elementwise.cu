@@ -201,6 +201,125 @@ ln_modulate_tma_kernel(const float* __restrict__ x, int M, int tokens_per_img, c
   }
 }
 
+// Same ring, rows handed out in BLOCKS of (image, 64 consecutive tokens): the image's scale / shift rows are staged in shared
+// memory once per block (double-buffered, one barrier per block) instead of being fetched through L1 for every token row -- in
+// the kernel above ~30 % of those 2 x C x 4 bytes per row miss L1 and the warp sits on the L2 latency (long_scoreboard 4.3 per
+// issue in profiles/ncu_k3_k4_conv_r02.md).  Same per-row arithmetic in the same order: bit-identical output.
+template <int NITER>
+__global__ void __launch_bounds__(256, 1)
+ln_modulate_tma2_kernel(const float* __restrict__ x, int M, int tokens_per_img, const float* __restrict__ scale,
+                        const float* __restrict__ shift, int ld_mod, const int* __restrict__ slot_map, float eps,
+                        __nv_bfloat16* __restrict__ out) {
+  constexpr int C = NITER * 128;
+  constexpr uint32_t kRowBytes = C * 4;
+  constexpr int kBlkRows = 64;
+  extern __shared__ __align__(128) unsigned char ln_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ring = reinterpret_cast<float*>(ln_smem) + (size_t)warp * kLnStages * C;          // [kLnStages][C] of this warp
+  float* smod = reinterpret_cast<float*>(ln_smem + (size_t)8 * kLnStages * kRowBytes);      // [2 buffers][scale, shift][C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)8 * kLnStages * kRowBytes + (size_t)4 * kRowBytes) + warp * kLnStages;
+  const int tpi = tokens_per_img;
+  const int cpi = (tpi + kBlkRows - 1) / kBlkRows;                                          // blocks per image
+  const long long nblk = (((long long)M + tpi - 1) / tpi) * cpi;
+  // rows of block b that fall to this warp: r0 + warp + 8 j, j = 0.. while below lim
+  auto block_geom = [&](long long b, long long& r0, int& lim, int& img) {
+    img = (int)(b / cpi);
+    const int ch = (int)(b - (long long)img * cpi);
+    r0 = (long long)img * tpi + (long long)ch * kBlkRows;
+    long long l = tpi - ch * kBlkRows;
+    l = l < kBlkRows ? l : kBlkRows;
+    const long long rest = (long long)M - r0;
+    lim = (int)(l < rest ? l : rest);
+  };
+  // issue-side iterator over this warp's rows, in the order the consumer visits them
+  long long iblk = blockIdx.x;
+  int ij = 0;
+  auto next_row = [&]() -> long long {
+    while (iblk < nblk) {
+      long long r0; int lim, img;
+      block_geom(iblk, r0, lim, img);
+      const int rr = warp + 8 * ij;
+      if (rr < lim) {
+        if (++ij == 8) { ij = 0; iblk += gridDim.x; }
+        return r0 + rr;
+      }
+      ij = 0;
+      iblk += gridDim.x;
+    }
+    return -1;
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < kLnStages; ++st)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bars[st])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int st = 0; st < kLnStages; ++st) {
+    const long long r = next_row();
+    if (r >= 0 && lane == 0) ln_bulk_g2s(ring + st * C, x + r * C, kRowBytes, &bars[st]);
+  }
+  uint32_t k = 0;
+  int par = 0;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x, par ^= 1) {
+    long long r0; int lim, img0;
+    block_geom(blk, r0, lim, img0);
+    const int img = slot_map != nullptr ? __ldg(slot_map + img0) : img0;
+    float4* md = reinterpret_cast<float4*>(smod + (size_t)par * 2 * C);
+    {
+      const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)img * ld_mod);
+      const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)img * ld_mod);
+      for (int i = threadIdx.x; i < 2 * NITER * 32; i += 256) md[i] = i < NITER * 32 ? __ldg(sc + i) : __ldg(sh + (i - NITER * 32));
+    }
+    __syncthreads();      // buffer `par` is complete; buffer par^1 is free again once every warp is past this barrier
+    for (int j = 0; j < 8; ++j, ++k) {
+      const int rr = warp + 8 * j;
+      if (rr >= lim) break;
+      const long long row = r0 + rr;
+      const uint32_t st = k % kLnStages;
+      ln_mbar_wait(&bars[st], (k / kLnStages) & 1);
+      const float4* src = reinterpret_cast<const float4*>(ring + st * C);
+      float4 v[NITER];
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) v[i] = src[i * 32 + lane];
+      __syncwarp();                                   // every lane has its values: the stage can be refilled
+      {
+        const long long nr = next_row();
+        if (nr >= 0 && lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          ln_bulk_g2s(ring + st * C, x + nr * C, kRowBytes, &bars[st]);
+        }
+      }
+      float sum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      const float mean = sum * (1.0f / (float)C);
+      float var = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        var += (a * a + b * b) + (c * c + d * d);
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) var += __shfl_xor_sync(0xffffffffu, var, off);
+      const float rstd = rsqrtf(var * (1.0f / (float)C) + eps);
+      uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * C);
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) {
+        const float4 s4 = md[i * 32 + lane], h4 = md[NITER * 32 + i * 32 + lane];
+        const float y0 = (v[i].x - mean) * rstd * (1.0f + s4.x) + h4.x;
+        const float y1 = (v[i].y - mean) * rstd * (1.0f + s4.y) + h4.y;
+        const float y2 = (v[i].z - mean) * rstd * (1.0f + s4.z) + h4.z;
+        const float y3 = (v[i].w - mean) * rstd * (1.0f + s4.w) + h4.w;
+        o[i * 32 + lane] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+      }
+    }
+  }
+}
+
 __global__ void silu_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
@@ -259,8 +378,20 @@ extern "C" int sdvar_ln_modulate(const float* x, int M, int C, int tokens_per_im
   if (M >= tma_min_rows && ((uintptr_t)x & 15) == 0) {
     const int sms = sm_count();
     const int grid = (M + 7) / 8 < sms ? (M + 7) / 8 : sms;
+    // blocked variant: images of >= 128 tokens and >= 16384 rows (same-box A/B at C = 1920 / 1024: 256 tokens x 128 images 75.9 ->
+    // 70.0 us / 53.7 -> 41.2 us, 169 tokens 50.2 -> 49.5 / 36.0 -> 31.0; 100 tokens and fewer: the strided kernel wins)
+    static const bool blocked = getenv("SDVAR_LN_NO_BLOCKS") == nullptr;      // A/B switch
 #define SDVAR_LN_TMA(NITER)                                                                                              \
   case NITER * 128: {                                                                                                    \
+    const size_t smem2 = (size_t)(8 * kLnStages + 4) * NITER * 128 * 4 + 8 * kLnStages * 8;                              \
+    if (blocked && tokens_per_img >= 128 && M >= 16384 && smem2 <= 227 * 1024) {                                         \
+      const long long nblk = (((long long)M + tokens_per_img - 1) / tokens_per_img) * ((tokens_per_img + 63) / 64);      \
+      SDVAR_SET_SMEM_ONCE(ln_modulate_tma2_kernel<NITER>, smem2);                                                        \
+      ln_modulate_tma2_kernel<NITER><<<(int)(nblk < sms ? nblk : sms), 256, smem2, (cudaStream_t)stream>>>(              \
+          x, M, tokens_per_img, scale, shift, ld_mod, slot_map, eps, reinterpret_cast<__nv_bfloat16*>(out));             \
+      SDVAR_LAUNCH_CHECK();                                                                                              \
+      return SDVAR_OK;                                                                                                   \
+    }                                                                                                                    \
     const size_t smem = (size_t)8 * kLnStages * NITER * 128 * 4 + 8 * kLnStages * 8;                                     \
     SDVAR_SET_SMEM_ONCE(ln_modulate_tma_kernel<NITER>, smem);                                                            \
     ln_modulate_tma_kernel<NITER><<<grid, 256, smem, (cudaStream_t)stream>>>(x, M, tokens_per_img, scale, shift, ld_mod, slot_map, eps, \

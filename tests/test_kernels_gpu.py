@@ -194,10 +194,12 @@ def test_stage_input_maps_vs_oracle(cuda_lib):
 
 
 # ---------------------------------------------------------------------------------- transformer pieces
-@pytest.mark.parametrize("M,C,tpi", [(7, 1024, 7), (130, 1920, 13), (64, 2304, 1), (4099, 1920, 37), (20001, 1024, 256), (5000, 2304, 8)])
+@pytest.mark.parametrize("M,C,tpi", [(7, 1024, 7), (130, 1920, 13), (64, 2304, 1), (4099, 1920, 37), (20001, 1024, 256), (5000, 2304, 8),
+                                     (6007, 1920, 100), (16500, 1920, 169), (17000, 1536, 128), (16390, 1280, 130), (9000, 2304, 64)])
 def test_ln_modulate(cuda_lib, M, C, tpi):
     """small M: register-resident kernel; M >= 4096: the persistent TMA-ring kernel (ragged last rows, rings wrapping several
-    times, every model width the ring is instantiated for)"""
+    times, every model width the ring is instantiated for); M >= 16384 with >= 128 tokens per image: its blocked variant
+    (scale / shift staged per (image, 64-token block): partial blocks, ragged last image)"""
     imgs = (M + tpi - 1) // tpi
     x = hashed("ln.x", 0, (M, C), 2.0) + 0.3
     mod = hashed("ln.m", 0, (imgs, 6 * C), 0.5)
@@ -758,22 +760,24 @@ def test_groupnorm_large_mean_small_std(cuda_lib):
 
 
 def test_ln_modulate_ring_equals_register_kernel_bitwise(cuda_lib):
-    """the two ln_modulate kernels share their per-row arithmetic: identical bits on the same input (checked by forcing the
-    small-M kernel through a sliced launch), and a slot map redirects the modulation rows"""
-    M, C, tpi = 8192, 1920, 64
-    x = (hashed("ln.ring", 0, (M, C), 2.0) + 0.3).to(DEV)
-    mod = hashed("ln.ring.m", 1, (M // tpi, 6 * C), 0.5).to(DEV)
-    big = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
-    cuda_lib.ln_modulate(x, M, C, tpi, mod.data_ptr() + 2 * C * 4, mod.data_ptr() + 4 * C * 4, 6 * C, 1e-6, big)
-    small = torch.empty_like(big)
-    for r0 in range(0, M, 2048):      # 2048-row launches (< 4096 rows) take the register-resident kernel; 2048 % tpi == 0
-        cuda_lib.ln_modulate(x[r0:r0 + 2048], 2048, C, tpi, mod.data_ptr() + (r0 // tpi) * 6 * C * 4 + 2 * C * 4,
-                             mod.data_ptr() + (r0 // tpi) * 6 * C * 4 + 4 * C * 4, 6 * C, 1e-6, small[r0:r0 + 2048])
-    assert torch.equal(big, small)
-    perm = torch.randperm(M // tpi, generator=torch.Generator().manual_seed(0)).to(DEV).to(torch.int32)
-    viaslot = torch.empty_like(big)
-    cuda_lib.ln_modulate(x, M, C, tpi, mod.data_ptr() + 2 * C * 4, mod.data_ptr() + 4 * C * 4, 6 * C, 1e-6, viaslot, slot_map=perm)
-    mod_p = mod[perm.long()].contiguous()
-    direct = torch.empty_like(big)
-    cuda_lib.ln_modulate(x, M, C, tpi, mod_p.data_ptr() + 2 * C * 4, mod_p.data_ptr() + 4 * C * 4, 6 * C, 1e-6, direct)
-    assert torch.equal(viaslot, direct)
+    """the ln_modulate kernels share their per-row arithmetic: identical bits on the same input (checked by forcing the
+    small-M kernel through sliced launches) for the blocked TMA-ring variant (16384 rows, 128-token images) and the strided one
+    (8192 rows, 64-token images), and a slot map redirects the modulation rows"""
+    C = 1920
+    for M, tpi in ((16384, 128), (8192, 64)):
+        x = (hashed("ln.ring", 0, (M, C), 2.0) + 0.3).to(DEV)
+        mod = hashed("ln.ring.m", 1, (M // tpi, 6 * C), 0.5).to(DEV)
+        big = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+        cuda_lib.ln_modulate(x, M, C, tpi, mod.data_ptr() + 2 * C * 4, mod.data_ptr() + 4 * C * 4, 6 * C, 1e-6, big)
+        small = torch.empty_like(big)
+        for r0 in range(0, M, 2048):      # 2048-row launches (< 4096 rows) take the register-resident kernel; 2048 % tpi == 0
+            cuda_lib.ln_modulate(x[r0:r0 + 2048], 2048, C, tpi, mod.data_ptr() + (r0 // tpi) * 6 * C * 4 + 2 * C * 4,
+                                 mod.data_ptr() + (r0 // tpi) * 6 * C * 4 + 4 * C * 4, 6 * C, 1e-6, small[r0:r0 + 2048])
+        assert torch.equal(big, small), (M, tpi)
+        perm = torch.randperm(M // tpi, generator=torch.Generator().manual_seed(0)).to(DEV).to(torch.int32)
+        viaslot = torch.empty_like(big)
+        cuda_lib.ln_modulate(x, M, C, tpi, mod.data_ptr() + 2 * C * 4, mod.data_ptr() + 4 * C * 4, 6 * C, 1e-6, viaslot, slot_map=perm)
+        mod_p = mod[perm.long()].contiguous()
+        direct = torch.empty_like(big)
+        cuda_lib.ln_modulate(x, M, C, tpi, mod_p.data_ptr() + 2 * C * 4, mod_p.data_ptr() + 4 * C * 4, 6 * C, 1e-6, direct)
+        assert torch.equal(viaslot, direct), (M, tpi)
