@@ -91,16 +91,6 @@ __device__ __forceinline__ f32x2 spec_expf2(float x0, float x1) {
   return pk2((x0 >= kExpMin) ? e0 : 0.0f, (x1 >= kExpMin) ? e1 : 0.0f);
 }
 
-// IEEE a / b for a >= 0 and b > 0.  ptxas' inline division has a fast path for operands with ordinary exponents and CALLs a
-// ~60-instruction subroutine otherwise -- and a ZERO numerator counts as "otherwise".  Most numerators here are exact zeros
-// (masked-out vocabulary entries), which sent every warp through the subroutine on every division (40 % of K3's
-// instructions).  Dividing 1 instead and selecting 0 afterwards gives the same bits (0 / b == +0).
-__device__ __forceinline__ float fdiv_nz(float a, float b) {
-  const bool z = a == 0.0f;
-  const float q = __fdiv_rn(z ? 1.0f : a, b);
-  return z ? 0.0f : q;
-}
-
 // ---- block reductions.  `slot` alternates between two smem buffers so one barrier per reduction suffices.
 struct RedSmem {
   float f[2][2][kWarps];
@@ -138,20 +128,6 @@ __device__ __forceinline__ float block_sum(float a, RedSmem& s, int& slot) {
   for (int k = 1; k < kWarps; ++k) a = __fadd_rn(a, s.f[slot][0][k]);
   slot ^= 1;
   return a;
-}
-// canonical float sum and an integer count with a single barrier
-__device__ __forceinline__ void block_sum_fi(float& a, int& c, RedSmem& s, int& slot) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, off));
-  c = __reduce_add_sync(0xffffffffu, c);
-  const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { s.f[slot][0][w] = a; s.i[slot][w] = c; }
-  __syncthreads();
-  a = s.f[slot][0][0];
-  c = s.i[slot][0];
-#pragma unroll
-  for (int k = 1; k < kWarps; ++k) { a = __fadd_rn(a, s.f[slot][0][k]); c += s.i[slot][k]; }
-  slot ^= 1;
 }
 __device__ __forceinline__ int block_sum_int(int c, RedSmem& s, int& slot) {
   c = __reduce_add_sync(0xffffffffu, c);
@@ -344,19 +320,6 @@ __device__ __forceinline__ void fix_e(float e, uint32_t& hi, uint32_t& lo) {
   const float fh = floorf(a);
   hi = (uint32_t)fh;
   lo = __float2uint_rn(__fmul_rn(__fsub_rn(a, fh), 1048576.0f));   // both operations exact; one rounding in the conversion
-}
-// block sum of per-thread limb sums -> u64 total: two warp reductions, one 64-bit partial per warp, one barrier, then every
-// thread adds the 8 partials (4 LDS.128).  Integer sums: any order gives the same total.  (per-thread sums < 2^26, warp < 2^31)
-__device__ __forceinline__ unsigned long long block_sum_fix(uint32_t hi, uint32_t lo, K3Smem& s, int buf) {
-  hi = __reduce_add_sync(0xffffffffu, hi);
-  lo = __reduce_add_sync(0xffffffffu, lo);
-  if ((threadIdx.x & 31) == 0) s.zpart[buf][threadIdx.x >> 5] = ((unsigned long long)hi << 20) + (unsigned long long)lo;
-  __syncthreads();
-  const ulonglong2* z2 = reinterpret_cast<const ulonglong2*>(s.zpart[buf]);
-  unsigned long long t = 0;
-#pragma unroll
-  for (int k = 0; k < kWarps / 2; ++k) { const ulonglong2 v = z2[k]; t += v.x + v.y; }
-  return t;
 }
 // removable mass of the top-p cut: floor(Zi * thr_fix / 2^30), Zi < 2^53, thr_fix <= 2^30
 __device__ __forceinline__ unsigned long long thr_mass(unsigned long long Zi, uint32_t thr_fix) {
