@@ -776,7 +776,7 @@ k3_filtered_kernel(const float* __restrict__ logits, int B, int L, int in_ld, in
           klow = tk + 1u;                    // tk < key(max): no overflow; tk >= key(xK): removed entries are alive
           if (removed && ki == tk) s.Z2i = baseE + Egt;      // read by the winner of the race, behind its barrier
           z2_shared = true;
-        } else if (use_k ? kgroup : (plo > 0 && s.pcab[plo - 1] < (uint32_t)V)) {
+        } else if (plo < kBins && (use_k ? kgroup : (plo > 0 && s.pcab[plo - 1] < (uint32_t)V))) {      // (plo >= kBins: NaN row, no crossing bin)
           // no candidate is removed, but alive entries lie below bin plo, and every one of those is (E above them >=
           // E{bins >= plo} >= target): the cut sits right below the lowest entry of bin plo
           klow = s.minkey;
